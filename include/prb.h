@@ -1,0 +1,107 @@
+/* prb.h -- C ABI of the B200-native Poisson surface reconstruction pipeline.
+ *
+ * Drop-in boundary.  The reference (DavidXu-JJ/PoissonRecon_GPU) has no plugin / FFI surface:
+ * its only contract is "process in, files out" (main.cu:3247-3252 hard-coded paths,
+ * main.cu:517-520 input dispatch by extension, main.cu:4566 PlyWriteTriangles).  This header is
+ * therefore the boundary a maintainer of the reference would bind instead of calling
+ * pipelineBuildNodeArray / LaplacianIteration / the inline marching-cubes stages of main():
+ *
+ *   reference stage (file:line)                                   entry point here
+ *   ------------------------------------------------------------  ---------------------------
+ *   pipelineBuildNodeArray            main.cu:511-841             prb_set_points + prb_build_octree
+ *   computeVectorField + divergence   main.cu:3355-3462           prb_splat
+ *   LaplacianIteration + CG           main.cu:1223-1332,          prb_solve
+ *     solverCG_DeviceToDevice         CG_CUDA.cuh:344-509
+ *   iso-value                         main.cu:3480-3499           prb_solve (tail)
+ *   vertex/edge/face arrays, MC,      main.cu:3504-4564           prb_extract
+ *     refinement passes
+ *   insertTriangle / mesh container   main.cu:3220-3245           prb_get_mesh
+ *   whole main()                      main.cu:3247-4573           prb_run
+ *
+ * Conventions: plain C, opaque handle, int status (0 = ok, <0 = error, message from
+ * prb_last_error()); no exceptions cross the boundary; the caller owns input buffers; the
+ * library owns outputs until prb_destroy or the next prb_set_points; one context per GPU; a
+ * context is not thread-safe; all work runs on an internal non-default stream.
+ * There is no CPU fallback: every entry point fails with PRB_ERR_CUDA if no sm_100 device.
+ */
+#ifndef PRB_H_
+#define PRB_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct prb_context prb_context;
+
+enum {
+    PRB_OK = 0,
+    PRB_ERR_ARG = -1,     /* bad argument (depth out of range, null pointer, n <= 0, unknown name) */
+    PRB_ERR_CUDA = -2,    /* CUDA runtime failure / no usable device */
+    PRB_ERR_STATE = -3,   /* stage called out of order */
+    PRB_ERR_NOMEM = -4
+};
+
+/* Per-run statistics (counts are the parity probes the reference prints: NodeArray_sz
+ * main.cu:3278, VertexArray_sz :3575, EdgeArray_sz :3609, SubdivideNum :3836, isoValue :3499). */
+typedef struct prb_stats {
+    int64_t n_points;
+    int32_t depth;
+    int32_t n_nodes;               /* NodeArray_sz */
+    int32_t nodes_per_depth[16];   /* NodeArrayCount_h */
+    int32_t cg_iters[16];          /* CG iterations per depth */
+    int32_t n_subdivide;           /* SubdivideNum */
+    int32_t n_passes;              /* mesh passes emitted (main + refinement) */
+    int64_t n_vertices, n_triangles;
+    float iso_value;
+    float center[3], scale;        /* file coords = p*scale + center (plyfile.cu:2801-2803) */
+    /* device time per stage, milliseconds (CUDA events on the context stream) */
+    float ms_h2d, ms_octree, ms_splat, ms_divergence, ms_solve, ms_iso, ms_extract, ms_total;
+    int64_t cg_row_iters;          /* sum_d rows_d * iters_d (roofline numerator) */
+    int32_t kernel_launches;       /* kernels launched by the last prb_run */
+} prb_stats;
+
+/* Create a context on CUDA device `device` for octree depth `depth` (2..12; the reference's
+ * compile-time `maxDepth`, main.cu:69). */
+int prb_create(int device, int depth, prb_context** out);
+void prb_destroy(prb_context* ctx);
+const char* prb_last_error(void);
+
+/* Oriented samples: xyz and normals as float32 [n][3], raw file coordinates.  Pointers may be
+ * host (pageable or pinned) or device memory; they are copied.  Replaces the two PointStream
+ * passes + H2D copies of main.cu:530-581. */
+int prb_set_points(prb_context* ctx, const float* xyz, const float* normals, int64_t n);
+
+/* Staged execution (each requires the previous stage). */
+int prb_build_octree(prb_context* ctx);
+int prb_splat(prb_context* ctx);
+int prb_solve(prb_context* ctx);
+int prb_extract(prb_context* ctx);
+/* All four stages. */
+int prb_run(prb_context* ctx);
+
+/* Triangle mesh of the last prb_extract, in HOST memory owned by the context: vertices are
+ * float32 [nv][3] in the normalised unit cube (like the reference's in-core mesh); file
+ * coordinates are v*scale + center (prb_stats).  Triangles are int32 [nt][3]. */
+int prb_get_mesh(prb_context* ctx, const float** vertices, int64_t* nv, const int32_t** triangles, int64_t* nt);
+/* Same data left on the device (no D2H copy). */
+int prb_get_mesh_device(prb_context* ctx, const float** d_vertices, int64_t* nv, const int32_t** d_triangles, int64_t* nt);
+
+int prb_get_stats(prb_context* ctx, prb_stats* out);
+
+/* Parity / debug getters: copies a named intermediate array to host memory `dst` (if non-null
+ * and cap_bytes is large enough) and returns its size in bytes, or a negative error.  Names:
+ *   points normals sorted_idx sorted_key base count key pidx pnum parent didx dnum children
+ *   neighs p2n vectorfield divergence x pointvalue iso center_scale cg_iters lap_stencil
+ *   vvalue_slots vertex_owner_mask passes mesh_v mesh_t subdivide                      */
+int64_t prb_get_array(prb_context* ctx, const char* name, void* dst, int64_t cap_bytes);
+/* Overwrite an intermediate (teacher forcing in parity tests): vectorfield divergence x iso. */
+int prb_set_array(prb_context* ctx, const char* name, const void* src, int64_t bytes);
+
+/* Options: "cg_tol" (default 1e-5, CG_CUDA.cuh:347), "cg_max_iter" (10000, CG_CUDA.cuh:263),
+ * "refine" (1 = run the refinement passes, main.cu:3799-4564). */
+int prb_set_option(prb_context* ctx, const char* key, double value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRB_H_ */

@@ -14,6 +14,8 @@ git-ignored oracle/_ref/.  The patch does not touch any kernel or algorithm; it 
   (2) takes maxDepth from -DREF_DEPTH instead of main.cu:69,
   (3) dumps intermediate arrays to $REF_DUMP_DIR when that variable is set,
   (4) records the CG iteration count per depth (one extra store by thread 0 at kernel exit),
+  (6) adds __launch_bounds__(1024) to the six kernels the reference launches with 1024-thread
+      blocks (they exceed 64 registers on sm_100 with nvcc 12.9 and would silently fail to launch),
   (5) initialises two host ints the reference leaves uninitialised when a refinement pass has
       zero roots (main.cu:4439-4446, 4521-4527: cudaMemcpy from a null device pointer fails
       silently because CHECK is compiled out, Debug.cuh:8) -- without this the reference reads
@@ -116,6 +118,18 @@ def patch_main(src):
                  "        int RebuildLastVexAddr=0;\n        int RebuildLastVexNums=0;\n", "uninit vex")
     s = sub_once(s, "        int RebuildLastTriAddr;\n        int RebuildLastTriNums;\n",
                  "        int RebuildLastTriAddr=0;\n        int RebuildLastTriNums=0;\n", "uninit tri")
+    # (6) kernels the reference launches with 1024-thread blocks (main.cu:3370-3446, 1231-1256):
+    # nvcc 12.9 / sm_100 gives some of them > 64 registers, so the launch fails with
+    # cudaErrorLaunchOutOfResources -- silently, because CHECK is compiled out (Debug.cuh:8) --
+    # and the stale error aborts the next thrust call.  A launch bound is a register-allocation
+    # hint only; no kernel code changes.
+    for kname in ("computeVectorField(", "precomputeEncodedFunctionIdxOfNode(", "computeEncodedFinerNodesDivergence(",
+                  "generateDIdxArray(", "computeEncodedCoarserNodesDivergence(", "GenerateSingleNodeLaplacian("):
+        tag = "__global__ void " + kname
+        if s.count(tag) < 1:
+            raise SystemExit("launch-bound anchor missing: " + kname)
+        s = s.replace(tag, "__global__ void __launch_bounds__(1024) " + kname)
+    s = sub_once(s, "int main(int argc,char **argv) {\n", "int main(int argc,char **argv) {\n    setvbuf(stdout,NULL,_IOLBF,0);\n", "line-buffered stdout")
     # final mesh dump
     s = sub_once(s, "    PlyWriteTriangles(outName,&mesh, PLY_ASCII,center,scale,NULL,0);\n",
                  '    if(mesh.inCorePoints.size()) refDumpHost("mesh_v",mesh.inCorePoints.data(),sizeof(float)*3*mesh.inCorePoints.size());\n'

@@ -955,6 +955,33 @@ void* orc_create() {
 void orc_destroy(void* h) { delete (Oracle*)h; }
 // stages: 1 = octree only, 2 = +splat/divergence, 3 = +solve/iso, 4 = everything
 int orc_run(void* h, const float* xyz, const float* nrm, int n, int depth, int stages) { return ((Oracle*)h)->run(xyz, nrm, n, depth, stages); }
+// Teacher forcing for stage-by-stage pinning: overwrite an intermediate with the reference's
+// own values, then re-run a single stage with orc_stage().
+int orc_set(void* h, const char* name, const void* src, long long bytes) {
+    Oracle& o = *(Oracle*)h;
+    std::string s(name);
+    std::vector<float>* v = nullptr;
+    if (s == "vectorfield") v = &o.V; else if (s == "divergence") v = &o.divg; else if (s == "x") v = &o.x;
+    if (s == "iso") { if (bytes != 4) return -2; std::memcpy(&o.iso, src, 4); return 0; }
+    if (!v) return -1;
+    if ((long long)(v->size() * 4) != bytes) return -2;
+    std::memcpy(v->data(), src, (size_t)bytes);
+    return 0;
+}
+int orc_stage(void* h, const char* name) {
+    Oracle& o = *(Oracle*)h;
+    std::string s(name);
+    if (s == "splat") o.splat();
+    else if (s == "divergence") o.divergence();
+    else if (s == "solve") o.solve();
+    else if (s == "iso") o.iso_value();
+    else if (s == "mc") {
+        o.build_vertices(); o.build_edges(); o.build_faces(); o.vertex_values();
+        o.meshV.clear(); o.meshT.clear(); o.passes.clear();
+        o.mc_main_pass(); o.find_subdivide(); o.refine();
+    } else return -1;
+    return 0;
+}
 // Copies a named array into dst (if dst != NULL and cap is large enough); returns its size in bytes
 // or -1 for an unknown name.
 long long orc_get(void* h, const char* name, void* dst, long long cap) {

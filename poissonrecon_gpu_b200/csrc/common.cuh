@@ -1,0 +1,175 @@
+// Shared declarations of the sm_100a pipeline: context, device buffers, launch helpers and the
+// small closed-form tables (neighbour LUTs, cube corner / edge numbering) used by every stage.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "prb.h"
+#include "bspline_host.h"
+
+namespace prb {
+
+typedef long long i64;
+typedef unsigned long long u64;
+
+void set_error(const std::string& msg);
+
+#define PRB_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            prb::set_error(std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+            return PRB_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+#define PRB_TRY(call)                 \
+    do {                              \
+        int r__ = (call);             \
+        if (r__ != PRB_OK) return r__; \
+    } while (0)
+
+constexpr int kMaxDepth = 12;
+constexpr int kSMs = 148;   // B200: 2 dies x 74 SMs; persistent grids are sized in multiples of this
+
+// Stream-ordered device buffer (cudaMallocAsync pool: allocation cost disappears after warm-up).
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaStream_t s = nullptr;
+    int alloc(size_t count, cudaStream_t st) {
+        release();
+        s = st;
+        n = count;
+        if (count == 0) { p = nullptr; return PRB_OK; }
+        PRB_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), st));
+        return PRB_OK;
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+        n = 0;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// One pass (the main depth-D pass or a refinement pass) of mesh output.
+struct PassRecord { int kind, nv, nt; };   // kind: 0 main, 1 coarse (single root), 2 batched per depth
+
+struct Context {
+    int device = 0, D = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[10];
+    int stage = 0;                 // 0 none, 1 points, 2 octree, 3 splat, 4 solve, 5 extract
+    int launches = 0;
+    double cgTol = 1e-5;
+    int cgMaxIter = 10000;
+    int doRefine = 1;
+    int smCount = kSMs;
+    // ---- samples
+    i64 N = 0;
+    DBuf<float> rawP, rawN;        // file coordinates, [N][3]
+    DBuf<float> P, Nr;             // Morton-sorted, normalised samples / rescaled normals [N][3]
+    DBuf<u64> sortedKey;           // Morton key per sorted sample
+    DBuf<int> sortedIdx;           // sorted position -> input index
+    DBuf<int> p2n;                 // sorted sample -> depth-D slot (local)
+    float center[3] = {0, 0, 0}, scale = 1;
+    // ---- octree: one global node index space, depth slabs at base[d] (SoA)
+    int M = 0;
+    int base[kMaxDepth + 2] = {0}, cnt[kMaxDepth + 1] = {0};
+    DBuf<int> dBase;               // device copy of base[0..D+1]
+    DBuf<u64> key;
+    DBuf<int> parent, child0, pidx, pnum, didx, dnum;
+    DBuf<int> neighs;              // [M][27]
+    DBuf<ushort4> offs;            // per node (ox, oy, oz, depth)
+    DBuf<int> nbBase;              // [M/8 groups][27] child-block bases for the sibling-block SpMV (group 0 = root pad)
+    // ---- tables
+    BSplineTables tab;
+    DBuf<float> dMaxDepthFn, dBaseFn, dDfT, dStencil;
+    DBuf<int> dDfOffset;
+    // ---- fields
+    DBuf<float> V;                 // [M_D][3]
+    DBuf<float> divg, x;
+    DBuf<float> pointValue;
+    float iso = 0;
+    int cgIters[kMaxDepth + 1] = {0};
+    i64 cgRowIters = 0;
+    // ---- mesh
+    DBuf<float> meshV;             // device
+    DBuf<int> meshT;
+    i64 nMeshV = 0, nMeshT = 0;
+    std::vector<float> hMeshV;
+    std::vector<int> hMeshT;
+    bool hMeshValid = false;
+    std::vector<PassRecord> passes;
+    std::vector<int> subdivide;    // host copy of the refined leaves (node ids)
+    DBuf<float> vval;              // [M][8] corner values (valid at the owner's slot)
+    prb_stats stats;
+};
+
+// stages (implemented in the .cu files)
+int stage_octree(Context& c);
+int stage_splat(Context& c);
+int stage_solve(Context& c);
+int stage_iso(Context& c);
+int stage_extract(Context& c);
+int upload_tables(Context& c);
+
+// exclusive scan of n ints on the context stream; returns the grand total through *total_host
+// (synchronises the stream) when total_host != nullptr.
+int exclusive_scan(Context& c, const int* in, int* out, i64 n, i64* total_host);
+
+#define PRB_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
+    do {                                                                        \
+        kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);         \
+        (ctx).launches++;                                                       \
+    } while (0)
+
+inline int div_up(i64 a, i64 b) { return (int)((a + b - 1) / b); }
+// grid for a grid-stride kernel: enough CTAs to fill the machine, a multiple of the SM count
+inline int grid_for(const Context& c, i64 n, int block, int perSM = 8) {
+    i64 need = (n + block - 1) / block;
+    i64 cap = (i64)c.smCount * perSM;
+    if (need <= cap) return need > 0 ? (int)need : 1;
+    return (int)cap;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Closed forms shared by host and device.
+// Neighbour slot j = 9(dx+1)+3(dy+1)+(dz+1); child code c = x<<2|y<<1|z (reference LUTparent /
+// LUTchild, main.cu:80-99: per axis t = bit + dir, parent dir = floor(t/2), child bit = t&1).
+__host__ __device__ inline void lut_parent_child(int c, int j, int& pj, int& cc) {
+    int dx = j / 9 - 1, dy = (j / 3) % 3 - 1, dz = j % 3 - 1;
+    int tx = ((c >> 2) & 1) + dx, ty = ((c >> 1) & 1) + dy, tz = (c & 1) + dz;
+    int px = tx < 0 ? 0 : (tx > 1 ? 2 : 1), py = ty < 0 ? 0 : (ty > 1 ? 2 : 1), pz = tz < 0 ? 0 : (tz > 1 ? 2 : 1);
+    pj = px * 9 + py * 3 + pz;
+    cc = ((tx & 1) << 2) | ((ty & 1) << 1) | (tz & 1);
+}
+// cube corner numbering of the MC tables ("ring" order, main.cu:2444-2455)
+__host__ __device__ inline int ring_index(int x, int y, int z) {
+    int r = x | (z << 2);
+    if (y) r += (r & 1) ? 1 : 3;
+    return r;
+}
+// inverse: ring index -> bit code x|y<<1|z<<2
+__host__ __device__ inline int ring_to_bits(int r) {
+    const int t[8] = {0, 1, 3, 2, 4, 5, 7, 6};
+    return t[r];
+}
+// edge e = orientation<<2 | off0 | off1<<1 (off0/off1: the two other axes, ascending; main.cu:1823-1840);
+// offset of the edge along axis a, or -1 along its own axis
+__host__ __device__ inline int edge_off(int e, int a) {
+    int o = e >> 2;
+    if (a == o) return -1;
+    int dim = (a > 0 && o != 0) + (a > 1 && o != 1);
+    if (a == 1 && o == 0) dim = 0;
+    if (a == 2 && o == 0) dim = 1;
+    if (a == 2 && o == 1) dim = 1;
+    if (a == 0) dim = 0;
+    if (a == 1 && o == 2) dim = 1;
+    return (e >> dim) & 1;
+}
+
+}  // namespace prb
