@@ -97,6 +97,10 @@ int64_t prb_get_array(prb_context* ctx, const char* name, void* dst, int64_t cap
 /* Overwrite an intermediate (teacher forcing in parity tests): vectorfield divergence x iso. */
 int prb_set_array(prb_context* ctx, const char* name, const void* src, int64_t bytes);
 
+/* Parity / debug: re-run a single stage ("divergence", "solve", "iso", "extract") on the current
+ * intermediates (used with prb_set_array for stage-by-stage comparison against the oracle). */
+int prb_run_stage(prb_context* ctx, const char* name);
+
 /* Options: "cg_tol" (default 1e-5, CG_CUDA.cuh:347), "cg_max_iter" (10000, CG_CUDA.cuh:263),
  * "refine" (1 = run the refinement passes, main.cu:3799-4564). */
 int prb_set_option(prb_context* ctx, const char* key, double value);

@@ -112,6 +112,7 @@ struct Context {
 // stages (implemented in the .cu files)
 int stage_octree(Context& c);
 int stage_splat(Context& c);
+int stage_divergence(Context& c);
 int stage_solve(Context& c);
 int stage_iso(Context& c);
 int stage_extract(Context& c);
@@ -163,13 +164,13 @@ __host__ __device__ inline int ring_to_bits(int r) {
 __host__ __device__ inline int edge_off(int e, int a) {
     int o = e >> 2;
     if (a == o) return -1;
-    int dim = (a > 0 && o != 0) + (a > 1 && o != 1);
-    if (a == 1 && o == 0) dim = 0;
-    if (a == 2 && o == 0) dim = 1;
-    if (a == 2 && o == 1) dim = 1;
-    if (a == 0) dim = 0;
-    if (a == 1 && o == 2) dim = 1;
+    int dim = (a == 0) ? 0 : (a == 1 ? (o != 0) : 1);   // number of axes below a other than o
     return (e >> dim) & 1;
+}
+// the two axes other than o, ascending
+__host__ __device__ inline void other_axes(int o, int& a0, int& a1) {
+    a0 = (o == 0) ? 1 : 0;
+    a1 = (o == 2) ? 1 : 2;
 }
 
 }  // namespace prb

@@ -1,0 +1,629 @@
+// Iso-value (A11) and iso-surface extraction (A12): corner values, marching cubes on the
+// depth-D slots, and the refinement passes over empty coarser leaves crossed by the surface.
+//
+// Replaces calculatePointsImplicitFunctionValue (main.cu:1334-1381), the vertex / edge / face
+// array construction (main.cu:1423-2082, 2827-2955), the depth-D marching-cubes pass
+// (main.cu:2259-2757, 3652-3795) and the subdivision passes (main.cu:2957-3217, 3799-4564).
+// The reference materialises 56-byte VertexNode / 24-byte EdgeNode / 20-byte FaceNode arrays with
+// copy_if over 8/12/6 candidates per node and writes back-pointers into its 276-byte nodes.
+// Here ownership ("min-key incident cell", which equals min node index inside a depth) is decided
+// on the fly from the neighbour table, corner values live in one float[8] record per cell at the
+// owner's slot, crossed edges are a 12-bit mask per cell, and output addresses come from two
+// scans.  Vertex and triangle ORDER equal the reference's (edges by owner cell then edge kind;
+// triangles by cell then case-table order), so meshes compare index by index.
+#include "common.cuh"
+#include "mc_case_table.h"
+
+namespace prb {
+
+__constant__ signed char cMcTri[256][16];
+__constant__ unsigned char cMcCount[256];
+__constant__ unsigned char cEdgeVertex[12][2];   // ring indices, ascending (MarchingCubes.cuh:693-706)
+__constant__ unsigned char cFaceEdgeMask[6][2];  // 12-bit mask of the 4 edges of each face (MarchingCubes.cuh:734-741), lo/hi byte
+
+static bool g_tablesReady = false;
+static int upload_mc_tables() {
+    if (g_tablesReady) return PRB_OK;
+    signed char tri[256][16];
+    unsigned char cnt[256], ev[12][2], fe[6][2];
+    for (int c = 0; c < 256; c++) {
+        int n = 0;
+        for (int k = 0; k < 16; k++) {
+            char h = kMcCaseHex[16 * c + k];
+            int v = (h == 'f') ? -1 : (h <= '9' ? h - '0' : h - 'a' + 10);
+            tri[c][k] = (signed char)v;
+            if (v >= 0) n++;
+        }
+        cnt[c] = (unsigned char)(n / 3);
+    }
+    for (int e = 0; e < 12; e++) {
+        int o = e >> 2, r[2];
+        for (int s = 0; s < 2; s++) {
+            int xyz[3];
+            for (int a = 0; a < 3; a++) xyz[a] = (a == o) ? s : edge_off(e, a);
+            r[s] = ring_index(xyz[0], xyz[1], xyz[2]);
+        }
+        ev[e][0] = (unsigned char)(r[0] < r[1] ? r[0] : r[1]);
+        ev[e][1] = (unsigned char)(r[0] < r[1] ? r[1] : r[0]);
+    }
+    for (int f = 0; f < 6; f++) {
+        int m = 0;
+        for (int e = 0; e < 12; e++) if (edge_off(e, f >> 1) == (f & 1)) m |= 1 << e;
+        fe[f][0] = (unsigned char)(m & 255);
+        fe[f][1] = (unsigned char)(m >> 8);
+    }
+    PRB_CUDA(cudaMemcpyToSymbol(cMcTri, tri, sizeof(tri)));
+    PRB_CUDA(cudaMemcpyToSymbol(cMcCount, cnt, sizeof(cnt)));
+    PRB_CUDA(cudaMemcpyToSymbol(cEdgeVertex, ev, sizeof(ev)));
+    PRB_CUDA(cudaMemcpyToSymbol(cFaceEdgeMask, fe, sizeof(fe)));
+    g_tablesReady = true;
+    return PRB_OK;
+}
+
+// value at t of base function #fi (4 cumulative pieces x (c0..c3,start); ConfirmedPPolynomial.cuh:79-91)
+__device__ __forceinline__ float base_value(const float* __restrict__ baseFn, int fi, float t) {
+    const float* f = baseFn + 20 * (i64)fi;
+    float res = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (!(t > f[5 * i + 4])) break;
+        float v = f[5 * i];
+        float pw = t;
+        v = __fmaf_rn(pw, f[5 * i + 1], v);
+        pw = __fmul_rn(pw, t);
+        v = __fmaf_rn(pw, f[5 * i + 2], v);
+        res = __fadd_rn(res, v);
+    }
+    return res;
+}
+// sum over the 27 neighbours of `node` (depth d, offsets o) of x[n] * F_n(pos); j order, float
+__device__ __forceinline__ void accumulate_level(float& val, const int* __restrict__ nb, ushort4 o, const float* __restrict__ x,
+                                                 const float* __restrict__ baseFn, const float pos[3]) {
+    int d = o.w, n = 1 << d, f0 = n - 1;
+    float vx[3], vy[3], vz[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        int ax = (int)o.x + k - 1, ay = (int)o.y + k - 1, az = (int)o.z + k - 1;
+        vx[k] = (ax >= 0 && ax < n) ? base_value(baseFn, f0 + ax, pos[0]) : 0.f;
+        vy[k] = (ay >= 0 && ay < n) ? base_value(baseFn, f0 + ay, pos[1]) : 0.f;
+        vz[k] = (az >= 0 && az < n) ? base_value(baseFn, f0 + az, pos[2]) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 27; j++) {
+        int q = nb[j];
+        if (q >= 0) val = __fmaf_rn(__fmul_rn(__fmul_rn(x[q], vx[j / 9]), vy[(j / 3) % 3]), vz[j % 3], val);
+    }
+}
+
+// ------------------------------------------------------------------ A11 iso value
+__global__ void __launch_bounds__(128) k_point_values(const float* __restrict__ P, const int* __restrict__ p2n, i64 N, int baseD,
+                                                      const int* __restrict__ neighs, const int* __restrict__ parent, const ushort4* __restrict__ offs,
+                                                      const float* __restrict__ x, const float* __restrict__ baseFn, float* __restrict__ pv, double* __restrict__ sum) {
+    double acc = 0.0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (i64)gridDim.x * blockDim.x) {
+        float pos[3] = {P[3 * i], P[3 * i + 1], P[3 * i + 2]};
+        int now = baseD + p2n[i];
+        float val = 0.f;
+        while (now != -1) {
+            accumulate_level(val, neighs + 27 * (i64)now, offs[now], x, baseFn, pos);
+            now = parent[now];
+        }
+        pv[i] = val;
+        acc += (double)val;
+    }
+    __shared__ double red[4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(sum, red[0] + red[1] + red[2] + red[3]);
+}
+
+int stage_iso(Context& c) {
+    cudaStream_t st = c.stream;
+    PRB_TRY(c.pointValue.alloc((size_t)c.N, st));
+    DBuf<double> sum;
+    PRB_TRY(sum.alloc(1, st));
+    PRB_CUDA(cudaMemsetAsync(sum.p, 0, sizeof(double), st));
+    PRB_LAUNCH(c, k_point_values, grid_for(c, c.N, 128, 16), 128, 0, c.P.p, c.p2n.p, c.N, c.base[c.D], c.neighs.p, c.parent.p, c.offs.p, c.x.p, c.dBaseFn.p,
+               c.pointValue.p, sum.p);
+    double h = 0;
+    PRB_CUDA(cudaMemcpyAsync(&h, sum.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    PRB_CUDA(cudaStreamSynchronize(st));
+    // thrust::reduce(float) + "isoValue /= count" (main.cu:3494-3496)
+    float iso = (float)h;
+    iso /= (float)c.N;
+    c.iso = iso;
+    sum.release();
+    return PRB_OK;
+}
+
+// ------------------------------------------------------------------ topology helpers
+// A pass works on a set of depth-D cells addressed by ids.  Real pass: id = node index, the
+// neighbour table is `neighs`, candidates are ids >= 0.  Refinement pass: id = M + virtual
+// index, table = vneigh (row 0 = id M), candidates are ids >= M (virtual cells only,
+// main.cu:1609,2000).
+struct Topo {
+    const int* nbr;     // 27 ids per row
+    int rowBase;        // id of row 0
+    int minId;          // candidates: id >= minId
+    int cellBase;       // id of the first depth-D cell of the pass
+    int nCells;
+};
+__device__ __forceinline__ int topo_nb(const Topo& T, int id, int j) { return T.nbr[27 * (i64)(id - T.rowBase) + j]; }
+
+// owner of corner j (bits x|y<<1|z<<2) of cell id: smallest candidate among the <= 8 incident
+// cells (= min key, main.cu:1474-1484); m = which axes were stepped to reach it
+__device__ __forceinline__ int corner_owner(const Topo& T, int id, int j, int& m) {
+    int sx = (j & 1) ? 1 : -1, sy = (j & 2) ? 1 : -1, sz = (j & 4) ? 1 : -1;
+    int best = 0x7fffffff;
+    m = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        int dx = (q & 1) ? sx : 0, dy = (q & 2) ? sy : 0, dz = (q & 4) ? sz : 0;
+        int nb = topo_nb(T, id, 9 * (dx + 1) + 3 * (dy + 1) + (dz + 1));
+        if (nb >= T.minId && nb < best) { best = nb; m = q; }
+    }
+    return best;
+}
+// owner of edge e of cell id among the <= 4 incident cells; e2 = the edge's kind in the owner's frame
+__device__ __forceinline__ int edge_owner(const Topo& T, int id, int e, int& e2) {
+    int o = e >> 2, a0, a1;
+    other_axes(o, a0, a1);
+    int s0 = (e & 1) ? 1 : -1, s1 = (e & 2) ? 1 : -1;
+    int best = 0x7fffffff, bm = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        int d[3] = {0, 0, 0};
+        if (q & 1) d[a0] = s0;
+        if (q & 2) d[a1] = s1;
+        int nb = topo_nb(T, id, 9 * (d[0] + 1) + 3 * (d[1] + 1) + (d[2] + 1));
+        if (nb >= T.minId && nb < best) { best = nb; bm = q; }
+    }
+    e2 = (o << 2) | ((e & 1) ^ (bm & 1)) | ((((e >> 1) & 1) ^ ((bm >> 1) & 1)) << 1);
+    return best;
+}
+// the 8 corner values of a cell in ring order; vals holds 8 floats per id (bit order) at the owner
+__device__ __forceinline__ void cell_corner_values(const Topo& T, int id, const float* __restrict__ vals, int valBase, float v[8]) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        int j = ring_to_bits(r), m;
+        int ow = corner_owner(T, id, j, m);
+        v[r] = vals[8 * (i64)(ow - valBase) + (j ^ m)];
+    }
+}
+
+// ------------------------------------------------------------------ corner values, real tree (main.cu:2259-2326)
+__global__ void __launch_bounds__(128) k_vertex_values(Topo T, int M, int D, const int* __restrict__ parent, const int* __restrict__ child0,
+                                                       const ushort4* __restrict__ offs, const float* __restrict__ x, const float* __restrict__ baseFn,
+                                                       float iso, float* __restrict__ vval) {
+    const int exceedTab[8] = {0, 1, 3, 2, 4, 5, 7, 6};     // childrenVertexKind, MarchingCubes.cuh:721-723 (applied as the reference does)
+    i64 total = 8 * (i64)M;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        int i = (int)(t >> 3), j = (int)(t & 7), m;
+        if (i == 0) continue;                              // root vertices are dropped (validVertex, main.cu:1634-1638)
+        if (corner_owner(T, i, j, m) != i) continue;
+        ushort4 o = offs[i];
+        int depth = o.w;
+        float w = 1.0f / (float)(1 << depth);
+        float pos[3] = {(float)((int)o.x + (j & 1)) * w, (float)((int)o.y + ((j >> 1) & 1)) * w, (float)((int)o.z + ((j >> 2) & 1)) * w};
+        float val = 0.f;
+        int now = i;
+        while (now != -1) {
+            accumulate_level(val, T.nbr + 27 * (i64)now, offs[now], x, baseFn, pos);
+            now = parent[now];
+        }
+        now = i;
+        int ex = exceedTab[j];
+        while (depth < D) {
+            ++depth;
+            int c0 = child0[now];
+            if (c0 < 0) break;
+            now = c0 + ex;
+            accumulate_level(val, T.nbr + 27 * (i64)now, offs[now], x, baseFn, pos);
+        }
+        vval[t] = __fsub_rn(val, iso);
+    }
+}
+
+// ------------------------------------------------------------------ classification of depth-D cells
+// per cell: MC case, triangle count, mask of OWNED crossed edges (v1*v2 <= 0, main.cu:2475)
+__global__ void __launch_bounds__(128) k_classify(Topo T, const float* __restrict__ vals, int valBase, unsigned char* __restrict__ cat,
+                                                  int* __restrict__ ntri, unsigned short* __restrict__ emask, int* __restrict__ nvtx) {
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < T.nCells; l += gridDim.x * blockDim.x) {
+        int id = T.cellBase + l;
+        float v[8];
+        cell_corner_values(T, id, vals, valBase, v);
+        int c = 0;
+#pragma unroll
+        for (int r = 0; r < 8; r++) if (v[r] < 0.f) c |= 1 << r;
+        unsigned m = 0;
+#pragma unroll
+        for (int e = 0; e < 12; e++) {
+            if (__fmul_rn(v[cEdgeVertex[e][0]], v[cEdgeVertex[e][1]]) <= 0.f) {
+                int e2;
+                if (edge_owner(T, id, e, e2) == id) m |= 1u << e;
+            }
+        }
+        cat[l] = (unsigned char)c;
+        ntri[l] = cMcCount[c];
+        emask[l] = (unsigned short)m;
+        nvtx[l] = __popc(m);
+    }
+}
+// interpolated vertices (main.cu:2584-2627), written at vbase[cell] + rank of the edge inside the mask
+__global__ void __launch_bounds__(128) k_emit_vertices(Topo T, const float* __restrict__ vals, int valBase, const ushort4* __restrict__ cellOffs, int D,
+                                                       const unsigned short* __restrict__ emask, const int* __restrict__ vbase, float* __restrict__ outV) {
+    const float w = 1.0f / (float)(1 << D);
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < T.nCells; l += gridDim.x * blockDim.x) {
+        unsigned m = emask[l];
+        if (!m) continue;
+        int id = T.cellBase + l;
+        float v[8];
+        cell_corner_values(T, id, vals, valBase, v);
+        ushort4 o = cellOffs[l];
+        int k = 0;
+        for (int e = 0; e < 12; e++) {
+            if (!(m & (1u << e))) continue;
+            int r1 = cEdgeVertex[e][0], r2 = cEdgeVertex[e][1], dim = e >> 2;
+            int b1 = ring_to_bits(r1), b2 = ring_to_bits(r2);
+            float p1[3] = {(float)((int)o.x + (b1 & 1)) * w, (float)((int)o.y + ((b1 >> 1) & 1)) * w, (float)((int)o.z + ((b1 >> 2) & 1)) * w};
+            float p2d = (float)((dim == 0 ? (int)o.x + (b2 & 1) : (dim == 1 ? (int)o.y + ((b2 >> 1) & 1) : (int)o.z + ((b2 >> 2) & 1)))) * w;
+            float f1 = v[r1], f2 = v[r2];
+            float pivot = __fdiv_rn(f1, __fsub_rn(f1, f2));
+            float another = __fsub_rn(1.0f, pivot);
+            float out[3] = {p1[0], p1[1], p1[2]};
+            out[dim] = __fmaf_rn(p2d, pivot, __fmul_rn(p1[dim], another));
+            i64 a = 3 * (i64)(vbase[l] + k);
+            outV[a] = out[0]; outV[a + 1] = out[1]; outV[a + 2] = out[2];
+            k++;
+        }
+    }
+}
+// triangles (main.cu:2699-2757) + marking of faces touched by the surface and of their parent faces
+__global__ void __launch_bounds__(128) k_emit_triangles(Topo T, const unsigned char* __restrict__ cat, const int* __restrict__ ntri, const int* __restrict__ tbase,
+                                                        const unsigned short* __restrict__ emask, const int* __restrict__ vbase, int* __restrict__ outT,
+                                                        int markFaces, int D, const int* __restrict__ parent, const ushort4* __restrict__ offs,
+                                                        unsigned* __restrict__ fmark) {
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < T.nCells; l += gridDim.x * blockDim.x) {
+        int nt = ntri[l];
+        if (!nt) continue;
+        int id = T.cellBase + l, c = cat[l];
+        unsigned used = 0;
+        for (int j = 0; j < 3 * nt; j++) {
+            int e = cMcTri[c][j], e2;
+            used |= 1u << e;
+            int ow = edge_owner(T, id, e, e2);
+            int ol = ow - T.cellBase;
+            outT[3 * (i64)tbase[l] + j] = vbase[ol] + __popc((unsigned)emask[ol] & ((1u << e2) - 1u));
+        }
+        if (!markFaces) continue;
+        for (int f = 0; f < 6; f++) {
+            unsigned fm = (unsigned)cFaceEdgeMask[f][0] | ((unsigned)cFaceEdgeMask[f][1] << 8);
+            if (!(used & fm)) continue;
+            // face (node, f) and the chain of parent faces (main.cu:2738-2755).  A face is shared
+            // by the two cells across it; its hasParentFace flag was set by its OWNER (min index)
+            // with the reference's parentFaceKind table (MarchingCubes.cuh:708-717: child code
+            // read as x=bit0, literal row 7).
+            int node = id;
+            int axis = f >> 1, dd[3] = {0, 0, 0};
+            dd[axis] = (f & 1) ? 1 : -1;
+            int jn = 9 * (dd[0] + 1) + 3 * (dd[1] + 1) + (dd[2] + 1);
+            while (true) {
+                int across = T.nbr[27 * (i64)node + jn];
+                atomicOr(&fmark[node], 1u << f);
+                if (across >= 0) atomicOr(&fmark[across], 1u << (f ^ 1));
+                int owner = (across >= 0 && across < node) ? across : node;
+                int fo = (owner == node) ? f : (f ^ 1);
+                int pa = parent[owner];
+                if (pa < 0) break;
+                ushort4 oo = offs[owner];
+                int son = (((int)oo.x & 1) << 2) | (((int)oo.y & 1) << 1) | ((int)oo.z & 1);
+                int pk = (((son >> (fo >> 1)) & 1) == (fo & 1)) ? fo : -1;
+                if (son == 7 && fo == 0) pk = 0;
+                if (pk == -1) break;
+                node = parent[node];
+                if (node < 0) break;
+            }
+        }
+    }
+}
+// empty leaves below depth D that must be refined (main.cu:2957-2992)
+__global__ void __launch_bounds__(128) k_find_subdivide(Topo T, int nNodes, const int* __restrict__ child0, const float* __restrict__ vval,
+                                                        const unsigned* __restrict__ fmark, int* __restrict__ flag) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nNodes; i += gridDim.x * blockDim.x) {
+        int f = 0;
+        if (i > 0 && child0[i] < 0) {
+            float v[8];
+            cell_corner_values(T, i, vval, 0, v);
+            int sign = (v[0] < 0.f) ? -1 : 1;
+            int ht = 0;
+#pragma unroll
+            for (int r = 1; r < 8; r++) if ((float)sign * v[r] < 0.f) ht = 1;
+            f = (ht || fmark[i] != 0u) ? 1 : 0;
+        }
+        flag[i] = f;
+    }
+}
+__global__ void __launch_bounds__(256) k_compact_ids(const int* __restrict__ flag, const int* __restrict__ excl, int n, int* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (flag[i]) out[excl[i]] = i;
+}
+
+// ------------------------------------------------------------------ refinement: virtual complete subtrees
+struct VTree {
+    int M, D, rd, nr;
+    int depthAddr[kMaxDepth + 2];   // first virtual index of each level (valid for rd..D)
+    const int* roots;               // real node ids of the pass, ascending
+};
+__device__ __forceinline__ int vt_per(const VTree& V, int d) { return 1 << (3 * (d - V.rd)); }
+
+// neighbours of the virtual nodes of level d from their parents' (computeRebuildNeighbor, main.cu:3188-3217)
+__global__ void __launch_bounds__(256) k_vneigh(VTree V, int d, const int* __restrict__ neighs, const int* __restrict__ parent, const int* __restrict__ child0,
+                                                const ushort4* __restrict__ offs, const int* __restrict__ rootMap, int* __restrict__ vneigh) {
+    const int per = vt_per(V, d);
+    const i64 total = (i64)V.nr * per * 27;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        int vl = (int)(t / 27), j = (int)(t - (i64)vl * 27);
+        int r = vl / per, l = vl - r * per;
+        int c, np, pj, cc;
+        if (d == V.rd) {
+            int root = V.roots[r];
+            ushort4 o = offs[root];
+            c = (((int)o.x & 1) << 2) | (((int)o.y & 1) << 1) | ((int)o.z & 1);
+            lut_parent_child(c, j, pj, cc);
+            np = neighs[27 * (i64)parent[root] + pj];
+        } else {
+            c = l & 7;
+            lut_parent_child(c, j, pj, cc);
+            int pv = V.depthAddr[d - 1] + r * (per >> 3) + (l >> 3);
+            np = vneigh[27 * (i64)pv + pj];
+        }
+        int out = -1;
+        if (np >= 0) {
+            if (np < V.M) {
+                int c0 = child0[np];
+                if (c0 >= 0) { int ch = c0 + cc; int vm = rootMap[ch]; out = vm >= 0 ? V.M + vm : ch; }
+            } else {
+                int pvv = np - V.M - V.depthAddr[d - 1];
+                int r2 = pvv / (per >> 3), l2 = pvv - r2 * (per >> 3);
+                out = V.M + V.depthAddr[d] + r2 * per + (l2 << 3) + cc;
+            }
+        }
+        vneigh[27 * (i64)(V.depthAddr[d] + vl) + j] = out;
+    }
+}
+__global__ void k_set_rootmap(const int* __restrict__ roots, int nr, int first, int value, int* __restrict__ rootMap) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nr; r += gridDim.x * blockDim.x) rootMap[roots[r]] = value < 0 ? -1 : first + r;
+}
+// offsets of the depth-D virtual cells: root offsets extended by the octal digits of l
+__global__ void __launch_bounds__(256) k_vcell_offsets(VTree V, const ushort4* __restrict__ offs, ushort4* __restrict__ voffs) {
+    const int per = vt_per(V, V.D), lv = V.D - V.rd;
+    const int total = V.nr * per;
+    for (int vl = blockIdx.x * blockDim.x + threadIdx.x; vl < total; vl += gridDim.x * blockDim.x) {
+        int r = vl / per, l = vl - r * per;
+        ushort4 o = offs[V.roots[r]];
+        int ox = o.x, oy = o.y, oz = o.z;
+        for (int s = lv - 1; s >= 0; --s) {
+            int c = (l >> (3 * s)) & 7;
+            ox = (ox << 1) | ((c >> 2) & 1);
+            oy = (oy << 1) | ((c >> 1) & 1);
+            oz = (oz << 1) | (c & 1);
+        }
+        voffs[vl] = make_ushort4((unsigned short)ox, (unsigned short)oy, (unsigned short)oz, (unsigned short)V.D);
+    }
+}
+// corner values of the depth-D virtual cells: only REAL nodes carry a solution; a virtual root
+// stands for the real leaf it replaces (main.cu:2328-2442)
+__global__ void __launch_bounds__(128) k_vvertex_values(VTree V, Topo T, const int* __restrict__ vneigh, const ushort4* __restrict__ voffs,
+                                                        const int* __restrict__ neighs, const int* __restrict__ parent, const ushort4* __restrict__ offs,
+                                                        const float* __restrict__ x, const float* __restrict__ baseFn, float iso, float* __restrict__ sval) {
+    const int perD = vt_per(V, V.D);
+    const i64 total = 8 * (i64)T.nCells;
+    const float w = 1.0f / (float)(1 << V.D);
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        int l = (int)(t >> 3), j = (int)(t & 7), m;
+        int id = T.cellBase + l;
+        if (corner_owner(T, id, j, m) != id) continue;
+        ushort4 o = voffs[l];
+        float pos[3] = {(float)((int)o.x + (j & 1)) * w, (float)((int)o.y + ((j >> 1) & 1)) * w, (float)((int)o.z + ((j >> 2) & 1)) * w};
+        float val = 0.f;
+        int r = l / perD, loc = l - r * perD;
+        // virtual levels D .. rd
+        for (int d = V.D; d >= V.rd; --d) {
+            int per = vt_per(V, d);
+            int v = V.depthAddr[d] + r * per + loc;
+            const int* nb = vneigh + 27 * (i64)v;
+            int od = V.D - d;
+            int nn = 1 << d, f0 = nn - 1;
+            int ox = (int)o.x >> od, oy = (int)o.y >> od, oz = (int)o.z >> od;
+            float vx[3], vy[3], vz[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                int ax = ox + k - 1, ay = oy + k - 1, az = oz + k - 1;
+                vx[k] = (ax >= 0 && ax < nn) ? base_value(baseFn, f0 + ax, pos[0]) : 0.f;
+                vy[k] = (ay >= 0 && ay < nn) ? base_value(baseFn, f0 + ay, pos[1]) : 0.f;
+                vz[k] = (az >= 0 && az < nn) ? base_value(baseFn, f0 + az, pos[2]) : 0.f;
+            }
+#pragma unroll
+            for (int jj = 0; jj < 27; jj++) {
+                int q = nb[jj];
+                if (q < 0) continue;
+                if (q >= V.M) {
+                    if (d != V.rd) continue;                  // virtual non-root: no solution value
+                    q = V.roots[q - V.M - V.depthAddr[V.rd]];  // virtual root -> the real leaf it replaces
+                }
+                val = __fmaf_rn(__fmul_rn(__fmul_rn(x[q], vx[jj / 9]), vy[(jj / 3) % 3]), vz[jj % 3], val);
+            }
+            loc >>= 3;
+        }
+        // real ancestors
+        int now = parent[V.roots[r]];
+        while (now != -1) {
+            accumulate_level(val, neighs + 27 * (i64)now, offs[now], x, baseFn, pos);
+            now = parent[now];
+        }
+        sval[t] = __fsub_rn(val, iso);
+    }
+}
+__global__ void __launch_bounds__(256) k_offset_triangles(int* __restrict__ t, i64 n, int off) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) t[i] += off;
+}
+
+struct PassOut {
+    DBuf<float> v;
+    DBuf<int> t;
+    int nv = 0, nt = 0;
+};
+
+// classification + emission shared by the main pass and the refinement passes
+static int run_mc_on_cells(Context& c, const Topo& T, const float* vals, int valBase, const ushort4* cellOffs, bool markFaces, unsigned* fmark, PassOut& out) {
+    cudaStream_t st = c.stream;
+    const int n = T.nCells;
+    DBuf<unsigned char> cat;
+    DBuf<unsigned short> emask;
+    DBuf<int> ntri, nvtx, tbase, vbase;
+    PRB_TRY(cat.alloc((size_t)n, st));
+    PRB_TRY(emask.alloc((size_t)n, st));
+    PRB_TRY(ntri.alloc((size_t)n, st));
+    PRB_TRY(nvtx.alloc((size_t)n, st));
+    PRB_TRY(tbase.alloc((size_t)n, st));
+    PRB_TRY(vbase.alloc((size_t)n, st));
+    PRB_LAUNCH(c, k_classify, grid_for(c, n, 128, 16), 128, 0, T, vals, valBase, cat.p, ntri.p, emask.p, nvtx.p);
+    i64 totV = 0, totT = 0;
+    PRB_TRY(exclusive_scan(c, nvtx.p, vbase.p, n, &totV));
+    PRB_TRY(exclusive_scan(c, ntri.p, tbase.p, n, &totT));
+    out.nv = (int)totV;
+    out.nt = (int)totT;
+    PRB_TRY(out.v.alloc(3 * (size_t)totV, st));
+    PRB_TRY(out.t.alloc(3 * (size_t)totT, st));
+    if (totV) PRB_LAUNCH(c, k_emit_vertices, grid_for(c, n, 128, 16), 128, 0, T, vals, valBase, cellOffs, c.D, emask.p, vbase.p, out.v.p);
+    if (totT || markFaces)
+        PRB_LAUNCH(c, k_emit_triangles, grid_for(c, n, 128, 16), 128, 0, T, cat.p, ntri.p, tbase.p, emask.p, vbase.p, out.t.p, markFaces ? 1 : 0, c.D,
+                   c.parent.p, c.offs.p, fmark);
+    cat.release(); emask.release(); ntri.release(); nvtx.release(); tbase.release(); vbase.release();
+    return PRB_OK;
+}
+
+static int refine_pass(Context& c, const int* dRoots, int nr, int rd, bool single, DBuf<int>& rootMap, std::vector<PassOut>& outs) {
+    cudaStream_t st = c.stream;
+    const int D = c.D, M = c.M;
+    if (nr == 0) {
+        if (!single) { c.passes.push_back({2, 0, 0}); }
+        return PRB_OK;
+    }
+    VTree V;
+    V.M = M; V.D = D; V.rd = rd; V.nr = nr; V.roots = dRoots;
+    i64 total = 0;
+    for (int d = 0; d <= kMaxDepth + 1; d++) V.depthAddr[d] = 0;
+    for (int d = rd; d <= D; d++) { V.depthAddr[d] = (int)total; total += (i64)nr << (3 * (d - rd)); }
+    if (total * 27 > 0x7fffffffll * 4) { set_error("refinement pass too large"); return PRB_ERR_NOMEM; }
+    DBuf<int> vneigh;
+    PRB_TRY(vneigh.alloc(27 * (size_t)total, st));
+    PRB_LAUNCH(c, k_set_rootmap, grid_for(c, nr, 256), 256, 0, dRoots, nr, V.depthAddr[rd], 0, rootMap.p);
+    for (int d = rd; d <= D; d++) {
+        i64 cnt = ((i64)nr << (3 * (d - rd))) * 27;
+        PRB_LAUNCH(c, k_vneigh, grid_for(c, cnt, 256), 256, 0, V, d, c.neighs.p, c.parent.p, c.child0.p, c.offs.p, rootMap.p, vneigh.p);
+    }
+    PRB_LAUNCH(c, k_set_rootmap, grid_for(c, nr, 256), 256, 0, dRoots, nr, 0, -1, rootMap.p);
+    const int nD = nr << (3 * (D - rd));
+    Topo T;
+    T.nbr = vneigh.p; T.rowBase = M; T.minId = M; T.cellBase = M + V.depthAddr[D]; T.nCells = nD;
+    DBuf<ushort4> voffs;
+    DBuf<float> sval;
+    PRB_TRY(voffs.alloc((size_t)nD, st));
+    PRB_TRY(sval.alloc(8 * (size_t)nD, st));
+    PRB_LAUNCH(c, k_vcell_offsets, grid_for(c, nD, 256), 256, 0, V, c.offs.p, voffs.p);
+    PRB_LAUNCH(c, k_vvertex_values, grid_for(c, 8 * (i64)nD, 128, 16), 128, 0, V, T, vneigh.p, voffs.p, c.neighs.p, c.parent.p, c.offs.p, c.x.p, c.dBaseFn.p, c.iso, sval.p);
+    outs.emplace_back();
+    PassOut& po = outs.back();
+    PRB_TRY(run_mc_on_cells(c, T, sval.p, T.cellBase, voffs.p, false, nullptr, po));
+    if (single && po.nv == 0) {      // main.cu:4095-4103: nothing is inserted for a coarse root without crossings
+        po.v.release(); po.t.release();
+        outs.pop_back();
+    } else {
+        c.passes.push_back({single ? 1 : 2, po.nv, po.nt});
+    }
+    vneigh.release(); voffs.release(); sval.release();
+    return PRB_OK;
+}
+
+int stage_extract(Context& c) {
+    cudaStream_t st = c.stream;
+    const int D = c.D, M = c.M;
+    PRB_TRY(upload_mc_tables());
+    c.passes.clear();
+    c.subdivide.clear();
+    c.hMeshValid = false;
+    Topo R;
+    R.nbr = c.neighs.p; R.rowBase = 0; R.minId = 0; R.cellBase = c.base[D]; R.nCells = c.cnt[D];
+    PRB_TRY(c.vval.alloc(8 * (size_t)M, st));
+    PRB_LAUNCH(c, k_vertex_values, grid_for(c, 8 * (i64)M, 128, 16), 128, 0, R, M, D, c.parent.p, c.child0.p, c.offs.p, c.x.p, c.dBaseFn.p, c.iso, c.vval.p);
+    DBuf<unsigned> fmark;
+    PRB_TRY(fmark.alloc((size_t)M, st));
+    PRB_CUDA(cudaMemsetAsync(fmark.p, 0, sizeof(unsigned) * (size_t)M, st));
+    std::vector<PassOut> outs;
+    outs.reserve(64);
+    outs.emplace_back();
+    PRB_TRY(run_mc_on_cells(c, R, c.vval.p, 0, c.offs.p + c.base[D], true, fmark.p, outs.back()));
+    c.passes.push_back({0, outs.back().nv, outs.back().nt});
+    // ---- leaves to refine
+    const int nUpper = c.base[D];
+    DBuf<int> flag, excl, subIds;
+    PRB_TRY(flag.alloc((size_t)nUpper, st));
+    PRB_TRY(excl.alloc((size_t)nUpper, st));
+    PRB_LAUNCH(c, k_find_subdivide, grid_for(c, nUpper, 128, 16), 128, 0, R, nUpper, c.child0.p, c.vval.p, fmark.p, flag.p);
+    i64 nSub = 0;
+    PRB_TRY(exclusive_scan(c, flag.p, excl.p, nUpper, &nSub));
+    PRB_TRY(subIds.alloc((size_t)nSub, st));
+    if (nSub) {
+        PRB_LAUNCH(c, k_compact_ids, grid_for(c, nUpper, 256), 256, 0, flag.p, excl.p, nUpper, subIds.p);
+        c.subdivide.resize((size_t)nSub);
+        PRB_CUDA(cudaMemcpyAsync(c.subdivide.data(), subIds.p, sizeof(int) * (size_t)nSub, cudaMemcpyDeviceToHost, st));
+        PRB_CUDA(cudaStreamSynchronize(st));
+    }
+    flag.release(); excl.release(); fmark.release();
+    if (c.doRefine) {
+        DBuf<int> rootMap;
+        PRB_TRY(rootMap.alloc((size_t)M, st));
+        PRB_CUDA(cudaMemsetAsync(rootMap.p, 0xff, sizeof(int) * (size_t)M, st));
+        // node ids ascend with depth, so the list is grouped by depth already
+        std::vector<int> firstOfDepth(D + 2, (int)nSub);
+        {
+            size_t q = 0;
+            for (int d = 0; d <= D; d++) {
+                while (q < c.subdivide.size() && c.subdivide[q] < c.base[d]) q++;
+                firstOfDepth[d] = (int)q;
+            }
+            firstOfDepth[D + 1] = (int)nSub;
+        }
+        const int finerDepth = 3;    // main.cu:3886
+        for (int d = 1; d < finerDepth && d < D; d++)                      // coarse roots: one pass each (main.cu:3887-4202)
+            for (int q = firstOfDepth[d]; q < firstOfDepth[d + 1]; q++) PRB_TRY(refine_pass(c, subIds.p + q, 1, d, true, rootMap, outs));
+        for (int d = finerDepth; d < D; d++)                               // batched per depth (main.cu:4211-4561)
+            PRB_TRY(refine_pass(c, subIds.p + firstOfDepth[d], firstOfDepth[d + 1] - firstOfDepth[d], d, false, rootMap, outs));
+        rootMap.release();
+    }
+    subIds.release();
+    // ---- concatenate passes (insertTriangle, main.cu:3220-3245: indices offset by the vertices so far)
+    i64 tv = 0, tt = 0;
+    for (auto& o : outs) { tv += o.nv; tt += o.nt; }
+    PRB_TRY(c.meshV.alloc(3 * (size_t)tv, st));
+    PRB_TRY(c.meshT.alloc(3 * (size_t)tt, st));
+    i64 av = 0, at = 0;
+    for (auto& o : outs) {
+        if (o.nv) PRB_CUDA(cudaMemcpyAsync(c.meshV.p + 3 * av, o.v.p, 12 * (size_t)o.nv, cudaMemcpyDeviceToDevice, st));
+        if (o.nt) {
+            PRB_CUDA(cudaMemcpyAsync(c.meshT.p + 3 * at, o.t.p, 12 * (size_t)o.nt, cudaMemcpyDeviceToDevice, st));
+            if (av) PRB_LAUNCH(c, k_offset_triangles, grid_for(c, 3 * (i64)o.nt, 256), 256, 0, c.meshT.p + 3 * at, 3 * (i64)o.nt, (int)av);
+        }
+        av += o.nv; at += o.nt;
+        o.v.release(); o.t.release();
+    }
+    c.nMeshV = tv;
+    c.nMeshT = tt;
+    PRB_CUDA(cudaGetLastError());
+    return PRB_OK;
+}
+
+}  // namespace prb

@@ -1,0 +1,454 @@
+// Octree construction: normalise -> Morton keys -> radix sort -> unique leaves -> per-depth
+// sibling groups -> SoA node slabs -> 27-neighbour tables.
+//
+// Replaces pipelineBuildNodeArray (main.cu:511-841) and its kernels (main.cu:132-509).  The
+// reference builds each level with two 64 MB hash tables, atomics and per-level cudaMalloc /
+// memset / D2D concatenation; here every level is a flag + scan + compaction over the sorted
+// list of non-empty nodes of the level below (Morton order makes siblings contiguous), and the
+// node records are written once, directly into their final slab of a single SoA index space.
+// Results follow the reference's INTENDED semantics (the reference's own pidx
+// is racy, see tests/golden/ref_sphere100k_d8_report.json "ref_run_to_run").
+#include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+
+namespace prb {
+
+// ------------------------------------------------------------------------------------------
+// exclusive scan (three kernels: tile sums -> scan of sums -> tile scan + offset)
+constexpr int kScanBlock = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanBlock * kScanItems;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* smem /* >= 33 ints */) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) smem[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int nw = blockDim.x >> 5;
+        int s = lane < nw ? smem[lane] : 0;
+        int si = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= o) si += t;
+        }
+        if (lane < nw) smem[lane] = si - s;
+        if (lane == nw - 1) smem[32] = si;
+    }
+    __syncthreads();
+    int r = inc - v + smem[w];
+    *total = smem[32];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kScanBlock) k_scan_tile_sums(const int* __restrict__ in, int* __restrict__ sums, i64 n) {
+    i64 t0 = (i64)blockIdx.x * kScanTile;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        i64 i = t0 + k * kScanBlock + threadIdx.x;
+        if (i < n) s += in[i];
+    }
+    __shared__ int sm[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = threadIdx.x < (kScanBlock >> 5) ? sm[threadIdx.x] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) sums[blockIdx.x] = v;
+    }
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(int* __restrict__ sums, int nb, int* __restrict__ total) {
+    __shared__ int sm[33];
+    int carry = 0;
+    for (int b0 = 0; b0 < nb; b0 += 1024) {
+        int i = b0 + threadIdx.x;
+        int v = i < nb ? sums[i] : 0, tot;
+        int e = block_exclusive_scan(v, &tot, sm);
+        if (i < nb) sums[i] = carry + e;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(kScanBlock) k_scan_apply(const int* __restrict__ in, int* __restrict__ out, const int* __restrict__ sums, i64 n) {
+    __shared__ int sm[33];
+    i64 t0 = (i64)blockIdx.x * kScanTile;
+    int carry = sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        i64 i = t0 + k * kScanBlock + threadIdx.x;
+        int v = i < n ? in[i] : 0, tot;
+        int e = block_exclusive_scan(v, &tot, sm);
+        if (i < n) out[i] = carry + e;
+        carry += tot;
+    }
+}
+
+int exclusive_scan(Context& c, const int* in, int* out, i64 n, i64* total_host) {
+    if (n <= 0) { if (total_host) *total_host = 0; return PRB_OK; }
+    int nb = div_up(n, kScanTile);
+    DBuf<int> sums;
+    PRB_TRY(sums.alloc((size_t)nb + 1, c.stream));
+    PRB_LAUNCH(c, k_scan_tile_sums, nb, kScanBlock, 0, in, sums.p, n);
+    PRB_LAUNCH(c, k_scan_sums, 1, 1024, 0, sums.p, nb, sums.p + nb);
+    PRB_LAUNCH(c, k_scan_apply, nb, kScanBlock, 0, in, out, sums.p, n);
+    if (total_host) {
+        int t = 0;
+        PRB_CUDA(cudaMemcpyAsync(&t, sums.p + nb, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        PRB_CUDA(cudaStreamSynchronize(c.stream));
+        *total_host = t;
+    }
+    sums.release();
+    return PRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// A0: bounding box (main.cu:530-545)
+__global__ void __launch_bounds__(256) k_bbox_partial(const float* __restrict__ xyz, i64 n, float* __restrict__ part) {
+    float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            float v = xyz[3 * i + a];
+            mn[a] = fminf(mn[a], v);
+            mx[a] = fmaxf(mx[a], v);
+        }
+    __shared__ float sm[6][8];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_down_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_down_sync(0xffffffffu, mx[a], o));
+        }
+        if ((threadIdx.x & 31) == 0) { sm[a][threadIdx.x >> 5] = mn[a]; sm[3 + a][threadIdx.x >> 5] = mx[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float v = sm[threadIdx.x][0];
+        for (int w = 1; w < 8; w++) v = threadIdx.x < 3 ? fminf(v, sm[threadIdx.x][w]) : fmaxf(v, sm[threadIdx.x][w]);
+        part[6 * blockIdx.x + threadIdx.x] = v;
+    }
+}
+__global__ void k_bbox_final(const float* __restrict__ part, int nb, float* __restrict__ out) {
+    int a = threadIdx.x;
+    if (a >= 6) return;
+    float v = part[a];
+    for (int b = 1; b < nb; b++) v = a < 3 ? fminf(v, part[6 * b + a]) : fmaxf(v, part[6 * b + a]);
+    out[a] = v;
+}
+
+// A0 + A1: normalise (main.cu:552-571) and Morton-encode (main.cu:132-164).  Host float
+// semantics of the reference are kept: no FMA contraction in the normal length, IEEE division.
+__global__ void __launch_bounds__(256) k_normalise_encode(const float* __restrict__ xyz, const float* __restrict__ nrm, i64 n,
+                                                          float cx, float cy, float cz, float scale, int D,
+                                                          float* __restrict__ P0, float* __restrict__ N0, u64* __restrict__ keys, int* __restrict__ idx) {
+    const float ctr[3] = {cx, cy, cz};
+    const float nscale = (float)(2 << D);
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        float p[3], q[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            p[a] = __fdiv_rn(__fsub_rn(xyz[3 * i + a], ctr[a]), scale);
+            q[a] = nrm[3 * i + a];
+        }
+        float sq = __fadd_rn(__fadd_rn(__fmul_rn(q[0], q[0]), __fmul_rn(q[1], q[1])), __fmul_rn(q[2], q[2]));
+        float len = (float)sqrt((double)sq);
+        if (len > 1e-6f) len = __fdiv_rn(1.0f, len);
+        len = __fmul_rn(len, nscale);
+        // strict '>' against the running cell centre: a point on a cell boundary goes to the lower cell (Q5)
+        float c[3] = {0.5f, 0.5f, 0.5f};
+        float w = 0.25f;
+        u64 k = 0;
+        for (int l = D - 1; l >= 0; --l) {
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                if (p[a] > c[a]) { k |= 1ull << (3 * l + 2 - a); c[a] += w; }
+                else c[a] -= w;
+            }
+            w *= 0.5f;
+        }
+#pragma unroll
+        for (int a = 0; a < 3; a++) { P0[3 * i + a] = p[a]; N0[3 * i + a] = __fmul_rn(q[a], len); }
+        keys[i] = k;
+        idx[i] = (int)i;
+    }
+}
+__global__ void __launch_bounds__(256) k_gather_samples(const int* __restrict__ idx, const float* __restrict__ P0, const float* __restrict__ N0, i64 n,
+                                                        float* __restrict__ P, float* __restrict__ Nr) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        i64 s = idx[i];
+#pragma unroll
+        for (int a = 0; a < 3; a++) { P[3 * i + a] = P0[3 * s + a]; Nr[3 * i + a] = N0[3 * s + a]; }
+    }
+}
+// run heads: first element of every run of equal (key >> shift)
+__global__ void __launch_bounds__(256) k_head_flags(const u64* __restrict__ key, i64 n, int shift, int* __restrict__ flag) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        flag[i] = (i == 0) || ((key[i] >> shift) != (key[i - 1] >> shift));
+}
+__global__ void __launch_bounds__(256) k_compact_leaves(const u64* __restrict__ key, const int* __restrict__ flag, const int* __restrict__ excl, i64 n,
+                                                        u64* __restrict__ lkey, int* __restrict__ fp, int nLeaves) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        if (flag[i]) { lkey[excl[i]] = key[i]; fp[excl[i]] = (int)i; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) fp[nLeaves] = (int)n;
+}
+// one level up: parents of the non-empty nodes of depth d (list `lkey`, sorted)
+__global__ void __launch_bounds__(256) k_compact_parents(const u64* __restrict__ lkey, const int* __restrict__ fp, const int* __restrict__ fdm1,
+                                                         const int* __restrict__ flag, const int* __restrict__ excl, int n, int levelShift, int isDm1,
+                                                         u64* __restrict__ pkey, int* __restrict__ pfp, int* __restrict__ pfc, int* __restrict__ pfdm1,
+                                                         int* __restrict__ prank, int* __restrict__ slot,
+                                                         int nParents, int nPoints, int nDm1) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        int g = excl[r] + flag[r] - 1;
+        prank[r] = g;
+        slot[r] = 8 * g + (int)((lkey[r] >> levelShift) & 7);
+        if (flag[r]) {
+            pkey[g] = lkey[r] & ~(7ull << levelShift);
+            pfp[g] = fp[r];
+            pfc[g] = r;
+            pfdm1[g] = isDm1 ? g : fdm1[r];
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { pfp[nParents] = nPoints; pfc[nParents] = n; pfdm1[nParents] = nDm1; }
+}
+
+struct NodeArrays {
+    u64* key;
+    int *parent, *child0, *pidx, *pnum, *didx, *dnum;
+};
+// one thread per sibling group of depth d: writes the 8 node records (main.cu:226-276 depth D,
+// 301-359 upper levels, 433-490 prefix pidx/didx + keys of empty siblings)
+__global__ void __launch_bounds__(128) k_fill_groups(NodeArrays A, int d, int D, int baseD, int baseParent, int baseChild,
+                                                     int nGroups, const u64* __restrict__ pkey, const int* __restrict__ pslot,
+                                                     const int* __restrict__ fc, const u64* __restrict__ ckey, const int* __restrict__ cfp,
+                                                     const int* __restrict__ cfdm1) {
+    int shift = 3 * (D - d);
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < nGroups; g += gridDim.x * blockDim.x) {
+        int r0 = fc[g], r1 = fc[g + 1];
+        int pn[8], pi[8], dn[8], di[8], ch[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { pn[k] = 0; pi[k] = 0; dn[k] = (d == D) ? 1 : 0; di[k] = 0; ch[k] = -1; }
+        int firstP = 0, firstD = 0;
+        for (int r = r0; r < r1; r++) {
+            int cc = (int)((ckey[r] >> shift) & 7);
+            int p0 = cfp[r], p1 = cfp[r + 1];
+            int dd0 = 0, dd1 = 0;
+            if (d < D) { dd0 = 8 * cfdm1[r]; dd1 = 8 * cfdm1[r + 1]; }
+            if (r == r0) { firstP = p0; firstD = dd0; }
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (k == cc) { pn[k] = p1 - p0; pi[k] = p0; dn[k] = (d == D) ? 1 : dd1 - dd0; di[k] = dd0; ch[k] = (d < D) ? baseChild + 8 * r : -1; }
+        }
+        int nowP = firstP, nowD = firstD;
+        u64 kbase = pkey[g];
+        int par = baseParent + pslot[g];
+        int i0 = baseD + 8 * g;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            A.key[i0 + k] = kbase | ((u64)k << shift);
+            A.parent[i0 + k] = par;
+            A.child0[i0 + k] = ch[k];
+            A.pnum[i0 + k] = pn[k];
+            A.pidx[i0 + k] = nowP;
+            nowP += pn[k];
+            A.dnum[i0 + k] = dn[k];
+            if (d == D) A.didx[i0 + k] = 8 * g + k;
+            else { A.didx[i0 + k] = nowD; nowD += dn[k]; }
+        }
+    }
+}
+__global__ void k_fill_root(NodeArrays A, int nPoints, int nSlotsD, int hasChildren) {
+    A.key[0] = 0; A.parent[0] = -1; A.child0[0] = hasChildren ? 1 : -1; A.pidx[0] = 0; A.pnum[0] = nPoints; A.didx[0] = 0; A.dnum[0] = nSlotsD;
+}
+__global__ void __launch_bounds__(256) k_node_offsets(const u64* __restrict__ key, int base, int count, int d, int D, ushort4* __restrict__ offs) {
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < count; l += gridDim.x * blockDim.x) {
+        u64 k = key[base + l];
+        int ox = 0, oy = 0, oz = 0;
+        for (int lv = 1; lv <= d; lv++) {
+            int c = (int)((k >> (3 * (D - lv))) & 7);
+            ox |= ((c >> 2) & 1) << (d - lv);
+            oy |= ((c >> 1) & 1) << (d - lv);
+            oz |= (c & 1) << (d - lv);
+        }
+        offs[base + l] = make_ushort4((unsigned short)ox, (unsigned short)oy, (unsigned short)oz, (unsigned short)d);
+    }
+}
+// neighbours of depth d from the parents' (main.cu:492-509), one thread per (node, slot)
+__global__ void __launch_bounds__(256) k_neighbours(const int* __restrict__ parent, const int* __restrict__ child0, int* __restrict__ neighs, int base, int count) {
+    i64 total = (i64)count * 27;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        int l = (int)(t / 27), j = (int)(t - (i64)l * 27);
+        int i = base + l, c = l & 7, pj, cc;
+        lut_parent_child(c, j, pj, cc);
+        int np = neighs[27 * (i64)parent[i] + pj];
+        int out = -1;
+        if (np >= 0) { int c0 = child0[np]; if (c0 >= 0) out = c0 + cc; }
+        neighs[27 * (i64)i + j] = out;
+    }
+}
+__global__ void k_root_neighbours(int* __restrict__ neighs) {
+    int j = threadIdx.x;
+    if (j < 27) neighs[j] = (j == 13) ? 0 : -1;
+}
+// child-block bases per sibling group: group G covers nodes 1+8G .. 8+8G
+__global__ void __launch_bounds__(256) k_group_bases(const int* __restrict__ parent, const int* __restrict__ child0, const int* __restrict__ neighs,
+                                                     int nGroups, int* __restrict__ nbBase) {
+    i64 total = (i64)nGroups * 27;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        int G = (int)(t / 27), j = (int)(t - (i64)G * 27);
+        int np = neighs[27 * (i64)parent[1 + 8 * G] + j];
+        nbBase[t] = np >= 0 ? child0[np] : -1;
+    }
+}
+__global__ void __launch_bounds__(256) k_point_to_leaf(const int* __restrict__ flag, const int* __restrict__ excl, const int* __restrict__ slotD, i64 n, int* __restrict__ p2n) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        p2n[i] = slotD[excl[i] + flag[i] - 1];
+}
+
+int stage_octree(Context& c) {
+    const int D = c.D;
+    const i64 N = c.N;
+    cudaStream_t st = c.stream;
+    if (N <= 0 || N > 0x7fffffff / 4) { set_error("point count out of range"); return PRB_ERR_ARG; }
+    // ---- A0 bounding box -> scale / centre (host float arithmetic of main.cu:539-545)
+    {
+        int nb = grid_for(c, N, 256, 4);
+        DBuf<float> part, box;
+        PRB_TRY(part.alloc((size_t)nb * 6, st));
+        PRB_TRY(box.alloc(6, st));
+        PRB_LAUNCH(c, k_bbox_partial, nb, 256, 0, c.rawP.p, N, part.p);
+        PRB_LAUNCH(c, k_bbox_final, 1, 32, 0, part.p, nb, box.p);
+        float h[6];
+        PRB_CUDA(cudaMemcpyAsync(h, box.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        PRB_CUDA(cudaStreamSynchronize(st));
+        float scale = 1;
+        for (int a = 0; a < 3; a++) {
+            if (!a || scale < h[3 + a] - h[a]) scale = float(h[3 + a] - h[a]);
+            c.center[a] = float(h[3 + a] + h[a]) / 2;
+        }
+        scale *= 1.25f;
+        for (int a = 0; a < 3; a++) c.center[a] -= scale / 2;
+        c.scale = scale;
+        part.release();
+        box.release();
+    }
+    // ---- A1/A2 keys + sort (thrust::sort_by_key x2 on 64-bit codes in the reference, main.cu:598-602;
+    //      here one stable LSD sort over the 3D key bits with the sample index as payload)
+    DBuf<float> P0, N0;
+    DBuf<u64> keys0;
+    DBuf<int> idx0;
+    PRB_TRY(P0.alloc(3 * (size_t)N, st));
+    PRB_TRY(N0.alloc(3 * (size_t)N, st));
+    PRB_TRY(keys0.alloc((size_t)N, st));
+    PRB_TRY(idx0.alloc((size_t)N, st));
+    PRB_TRY(c.sortedKey.alloc((size_t)N, st));
+    PRB_TRY(c.sortedIdx.alloc((size_t)N, st));
+    PRB_TRY(c.P.alloc(3 * (size_t)N, st));
+    PRB_TRY(c.Nr.alloc(3 * (size_t)N, st));
+    PRB_LAUNCH(c, k_normalise_encode, grid_for(c, N, 256), 256, 0, c.rawP.p, c.rawN.p, N, c.center[0], c.center[1], c.center[2], c.scale, D,
+               P0.p, N0.p, keys0.p, idx0.p);
+    {
+        size_t tmpBytes = 0;
+        PRB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys0.p, c.sortedKey.p, idx0.p, c.sortedIdx.p, (int)N, 0, 3 * D, st));
+        DBuf<char> tmp;
+        PRB_TRY(tmp.alloc(tmpBytes, st));
+        PRB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, keys0.p, c.sortedKey.p, idx0.p, c.sortedIdx.p, (int)N, 0, 3 * D, st));
+        c.launches += 2 + (3 * D + 7) / 8;   // onesweep: histogram + scan + one pass per digit
+        tmp.release();
+    }
+    PRB_LAUNCH(c, k_gather_samples, grid_for(c, N, 256), 256, 0, c.sortedIdx.p, P0.p, N0.p, N, c.P.p, c.Nr.p);
+    P0.release(); N0.release(); keys0.release(); idx0.release();
+    // ---- A3 unique leaves
+    DBuf<int> flagN, exclN;
+    PRB_TRY(flagN.alloc((size_t)N, st));
+    PRB_TRY(exclN.alloc((size_t)N, st));
+    PRB_LAUNCH(c, k_head_flags, grid_for(c, N, 256), 256, 0, c.sortedKey.p, N, 0, flagN.p);
+    i64 nLeaves = 0;
+    PRB_TRY(exclusive_scan(c, flagN.p, exclN.p, N, &nLeaves));
+    // per-level lists of non-empty nodes
+    std::vector<DBuf<u64>> lkey(D + 1);
+    std::vector<DBuf<int>> fp(D + 1), fc(D + 1), fdm1(D + 1), prank(D + 1), slot(D + 1);
+    std::vector<int> U(D + 1, 0);
+    U[D] = (int)nLeaves;
+    PRB_TRY(lkey[D].alloc((size_t)U[D], st));
+    PRB_TRY(fp[D].alloc((size_t)U[D] + 1, st));
+    PRB_LAUNCH(c, k_compact_leaves, grid_for(c, N, 256), 256, 0, c.sortedKey.p, flagN.p, exclN.p, N, lkey[D].p, fp[D].p, U[D]);
+    // ---- A4/A5 levels D -> 0
+    for (int d = D; d >= 1; --d) {
+        int n = U[d];
+        DBuf<int> fl, ex;
+        PRB_TRY(fl.alloc((size_t)n, st));
+        PRB_TRY(ex.alloc((size_t)n, st));
+        PRB_LAUNCH(c, k_head_flags, grid_for(c, n, 256), 256, 0, lkey[d].p, (i64)n, 3 * (D - d + 1), fl.p);
+        i64 np = 0;
+        PRB_TRY(exclusive_scan(c, fl.p, ex.p, n, &np));
+        U[d - 1] = (int)np;
+        PRB_TRY(lkey[d - 1].alloc((size_t)np, st));
+        PRB_TRY(fp[d - 1].alloc((size_t)np + 1, st));
+        PRB_TRY(fc[d - 1].alloc((size_t)np + 1, st));
+        PRB_TRY(fdm1[d - 1].alloc((size_t)np + 1, st));
+        PRB_TRY(prank[d].alloc((size_t)n, st));
+        PRB_TRY(slot[d].alloc((size_t)n, st));
+        int nDm1 = (D >= 1) ? U[D - 1] : 0;   // U[D-1] is known from the first iteration on
+        if (d == D) nDm1 = (int)np;
+        PRB_LAUNCH(c, k_compact_parents, grid_for(c, n, 256), 256, 0, lkey[d].p, fp[d].p, fdm1[d].p, fl.p, ex.p, n, 3 * (D - d), (d - 1 == D - 1) ? 1 : 0,
+                   lkey[d - 1].p, fp[d - 1].p, fc[d - 1].p, fdm1[d - 1].p, prank[d].p, slot[d].p, (int)np, (int)N, nDm1);
+        fl.release();
+        ex.release();
+    }
+    PRB_TRY(slot[0].alloc(1, st));
+    PRB_CUDA(cudaMemsetAsync(slot[0].p, 0, sizeof(int), st));
+    // ---- node slabs
+    c.cnt[0] = 1;
+    for (int d = 1; d <= D; d++) c.cnt[d] = 8 * U[d - 1];
+    c.base[0] = 0;
+    for (int d = 1; d <= D + 1; d++) c.base[d] = c.base[d - 1] + c.cnt[d - 1];
+    c.M = c.base[D + 1];
+    const int M = c.M;
+    PRB_TRY(c.key.alloc((size_t)M, st));
+    PRB_TRY(c.parent.alloc((size_t)M, st));
+    PRB_TRY(c.child0.alloc((size_t)M, st));
+    PRB_TRY(c.pidx.alloc((size_t)M, st));
+    PRB_TRY(c.pnum.alloc((size_t)M, st));
+    PRB_TRY(c.didx.alloc((size_t)M, st));
+    PRB_TRY(c.dnum.alloc((size_t)M, st));
+    PRB_TRY(c.neighs.alloc(27 * (size_t)M, st));
+    PRB_TRY(c.offs.alloc((size_t)M, st));
+    PRB_TRY(c.dBase.alloc(kMaxDepth + 2, st));
+    PRB_CUDA(cudaMemcpyAsync(c.dBase.p, c.base, sizeof(int) * (kMaxDepth + 2), cudaMemcpyHostToDevice, st));
+    NodeArrays A{c.key.p, c.parent.p, c.child0.p, c.pidx.p, c.pnum.p, c.didx.p, c.dnum.p};
+    PRB_LAUNCH(c, k_fill_root, 1, 1, 0, A, (int)N, c.cnt[D], D >= 1 ? 1 : 0);
+    for (int d = 1; d <= D; d++) {
+        int ng = U[d - 1];
+        PRB_LAUNCH(c, k_fill_groups, grid_for(c, ng, 128), 128, 0, A, d, D, c.base[d], c.base[d - 1], d < D ? c.base[d + 1] : 0, ng,
+                   lkey[d - 1].p, slot[d - 1].p, fc[d - 1].p, lkey[d].p, fp[d].p, fdm1[d].p);
+    }
+    PRB_TRY(c.p2n.alloc((size_t)N, st));
+    PRB_LAUNCH(c, k_point_to_leaf, grid_for(c, N, 256), 256, 0, flagN.p, exclN.p, slot[D].p, N, c.p2n.p);
+    for (int d = 0; d <= D; d++) PRB_LAUNCH(c, k_node_offsets, grid_for(c, c.cnt[d], 256), 256, 0, c.key.p, c.base[d], c.cnt[d], d, D, c.offs.p);
+    // ---- A6 neighbours, level by level
+    PRB_LAUNCH(c, k_root_neighbours, 1, 32, 0, c.neighs.p);
+    for (int d = 1; d <= D; d++)
+        PRB_LAUNCH(c, k_neighbours, grid_for(c, (i64)c.cnt[d] * 27, 256), 256, 0, c.parent.p, c.child0.p, c.neighs.p, c.base[d], c.cnt[d]);
+    int nGroups = (M - 1) / 8;
+    PRB_TRY(c.nbBase.alloc(27 * (size_t)(nGroups > 0 ? nGroups : 1), st));
+    if (nGroups > 0)
+        PRB_LAUNCH(c, k_group_bases, grid_for(c, (i64)nGroups * 27, 256), 256, 0, c.parent.p, c.child0.p, c.neighs.p, nGroups, c.nbBase.p);
+    flagN.release(); exclN.release();
+    for (int d = 0; d <= D; d++) { lkey[d].release(); fp[d].release(); fc[d].release(); fdm1[d].release(); prank[d].release(); slot[d].release(); }
+    PRB_CUDA(cudaGetLastError());
+    return PRB_OK;
+}
+
+}  // namespace prb

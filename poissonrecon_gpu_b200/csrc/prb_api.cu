@@ -1,0 +1,328 @@
+// C ABI (include/prb.h): context management, staging, getters.  No torch types, no exceptions
+// across the boundary.  Everything runs on the context's own non-default stream.
+#include "common.cuh"
+#include <cstring>
+#include <mutex>
+
+namespace prb {
+
+static thread_local std::string g_lastError;
+void set_error(const std::string& msg) { g_lastError = msg; }
+
+static void release_all(Context& c) {
+    c.rawP.release(); c.rawN.release(); c.P.release(); c.Nr.release(); c.sortedKey.release(); c.sortedIdx.release(); c.p2n.release();
+    c.dBase.release(); c.key.release(); c.parent.release(); c.child0.release(); c.pidx.release(); c.pnum.release(); c.didx.release(); c.dnum.release();
+    c.neighs.release(); c.offs.release(); c.nbBase.release();
+    c.V.release(); c.divg.release(); c.x.release(); c.pointValue.release();
+    c.meshV.release(); c.meshT.release(); c.vval.release();
+    c.nMeshV = c.nMeshT = 0;
+    c.hMeshValid = false;
+}
+
+int upload_tables(Context& c) {
+    cudaStream_t st = c.stream;
+    build_bspline_tables(c.D, c.tab);
+    PRB_TRY(c.dMaxDepthFn.alloc(16, st));
+    PRB_TRY(c.dBaseFn.alloc(c.tab.baseFn.size(), st));
+    PRB_TRY(c.dDfT.alloc(c.tab.dfT.size(), st));
+    PRB_TRY(c.dDfOffset.alloc(c.tab.dfOffset.size(), st));
+    PRB_TRY(c.dStencil.alloc(c.tab.stencil.size(), st));
+    PRB_CUDA(cudaMemcpyAsync(c.dMaxDepthFn.p, c.tab.maxDepthFn, 64, cudaMemcpyHostToDevice, st));
+    PRB_CUDA(cudaMemcpyAsync(c.dBaseFn.p, c.tab.baseFn.data(), c.dBaseFn.bytes(), cudaMemcpyHostToDevice, st));
+    PRB_CUDA(cudaMemcpyAsync(c.dDfT.p, c.tab.dfT.data(), c.dDfT.bytes(), cudaMemcpyHostToDevice, st));
+    PRB_CUDA(cudaMemcpyAsync(c.dDfOffset.p, c.tab.dfOffset.data(), c.dDfOffset.bytes(), cudaMemcpyHostToDevice, st));
+    PRB_CUDA(cudaMemcpyAsync(c.dStencil.p, c.tab.stencil.data(), c.dStencil.bytes(), cudaMemcpyHostToDevice, st));
+    PRB_CUDA(cudaStreamSynchronize(st));
+    return PRB_OK;
+}
+
+}  // namespace prb
+
+using namespace prb;
+
+struct prb_context {
+    Context c;
+};
+
+extern "C" {
+
+const char* prb_last_error(void) { return g_lastError.c_str(); }
+
+int prb_create(int device, int depth, prb_context** out) {
+    if (!out) { set_error("out is null"); return PRB_ERR_ARG; }
+    *out = nullptr;
+    if (depth < 2 || depth > kMaxDepth) { set_error("depth must be in [2,12]"); return PRB_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (this library has no CPU fallback)");
+        return PRB_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_error("device index out of range"); return PRB_ERR_ARG; }
+    PRB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PRB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { set_error(std::string("device ") + prop.name + " is not sm_100-class; kernels are built for sm_100a only"); return PRB_ERR_CUDA; }
+    prb_context* h = new prb_context();
+    Context& c = h->c;
+    c.device = device;
+    c.D = depth;
+    c.smCount = prop.multiProcessorCount;
+    PRB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    for (auto& e : c.ev) PRB_CUDA(cudaEventCreate(&e));
+    cudaMemPool_t pool;
+    PRB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long thr = ~0ull;
+    PRB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    std::memset(&c.stats, 0, sizeof(c.stats));
+    int r = upload_tables(c);
+    if (r != PRB_OK) { delete h; return r; }
+    *out = h;
+    return PRB_OK;
+}
+
+void prb_destroy(prb_context* h) {
+    if (!h) return;
+    Context& c = h->c;
+    cudaSetDevice(c.device);
+    release_all(c);
+    c.dMaxDepthFn.release(); c.dBaseFn.release(); c.dDfT.release(); c.dDfOffset.release(); c.dStencil.release();
+    cudaStreamSynchronize(c.stream);
+    for (auto& e : c.ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c.stream);
+    delete h;
+}
+
+int prb_set_option(prb_context* h, const char* key, double value) {
+    if (!h || !key) { set_error("null argument"); return PRB_ERR_ARG; }
+    std::string k(key);
+    if (k == "cg_tol") h->c.cgTol = value;
+    else if (k == "cg_max_iter") h->c.cgMaxIter = (int)value;
+    else if (k == "refine") h->c.doRefine = (int)value;
+    else { set_error("unknown option " + k); return PRB_ERR_ARG; }
+    return PRB_OK;
+}
+
+int prb_set_points(prb_context* h, const float* xyz, const float* normals, int64_t n) {
+    if (!h || !xyz || !normals || n <= 0) { set_error("prb_set_points: bad argument"); return PRB_ERR_ARG; }
+    Context& c = h->c;
+    PRB_CUDA(cudaSetDevice(c.device));
+    release_all(c);
+    c.N = n;
+    c.launches = 0;
+    PRB_CUDA(cudaEventRecord(c.ev[0], c.stream));
+    PRB_TRY(c.rawP.alloc(3 * (size_t)n, c.stream));
+    PRB_TRY(c.rawN.alloc(3 * (size_t)n, c.stream));
+    PRB_CUDA(cudaMemcpyAsync(c.rawP.p, xyz, 12 * (size_t)n, cudaMemcpyDefault, c.stream));
+    PRB_CUDA(cudaMemcpyAsync(c.rawN.p, normals, 12 * (size_t)n, cudaMemcpyDefault, c.stream));
+    PRB_CUDA(cudaEventRecord(c.ev[1], c.stream));
+    c.stage = 1;
+    return PRB_OK;
+}
+
+int prb_build_octree(prb_context* h) {
+    if (!h) return PRB_ERR_ARG;
+    Context& c = h->c;
+    if (c.stage < 1) { set_error("prb_build_octree: no points set"); return PRB_ERR_STATE; }
+    PRB_CUDA(cudaSetDevice(c.device));
+    PRB_CUDA(cudaEventRecord(c.ev[1], c.stream));
+    PRB_TRY(stage_octree(c));
+    PRB_CUDA(cudaEventRecord(c.ev[2], c.stream));
+    c.stage = 2;
+    return PRB_OK;
+}
+int prb_splat(prb_context* h) {
+    if (!h) return PRB_ERR_ARG;
+    Context& c = h->c;
+    if (c.stage < 2) { set_error("prb_splat: octree not built"); return PRB_ERR_STATE; }
+    PRB_CUDA(cudaSetDevice(c.device));
+    PRB_CUDA(cudaEventRecord(c.ev[2], c.stream));
+    PRB_TRY(stage_splat(c));
+    PRB_CUDA(cudaEventRecord(c.ev[4], c.stream));
+    c.stage = 3;
+    return PRB_OK;
+}
+int prb_solve(prb_context* h) {
+    if (!h) return PRB_ERR_ARG;
+    Context& c = h->c;
+    if (c.stage < 3) { set_error("prb_solve: splat not done"); return PRB_ERR_STATE; }
+    PRB_CUDA(cudaSetDevice(c.device));
+    PRB_CUDA(cudaEventRecord(c.ev[4], c.stream));
+    PRB_TRY(stage_solve(c));
+    PRB_CUDA(cudaEventRecord(c.ev[5], c.stream));
+    PRB_TRY(stage_iso(c));
+    PRB_CUDA(cudaEventRecord(c.ev[6], c.stream));
+    c.stage = 4;
+    return PRB_OK;
+}
+int prb_extract(prb_context* h) {
+    if (!h) return PRB_ERR_ARG;
+    Context& c = h->c;
+    if (c.stage < 4) { set_error("prb_extract: solve not done"); return PRB_ERR_STATE; }
+    PRB_CUDA(cudaSetDevice(c.device));
+    PRB_CUDA(cudaEventRecord(c.ev[6], c.stream));
+    PRB_TRY(stage_extract(c));
+    PRB_CUDA(cudaEventRecord(c.ev[7], c.stream));
+    PRB_CUDA(cudaStreamSynchronize(c.stream));
+    c.stage = 5;
+    return PRB_OK;
+}
+int prb_run(prb_context* h) {
+    PRB_TRY(prb_build_octree(h));
+    PRB_TRY(prb_splat(h));
+    PRB_TRY(prb_solve(h));
+    PRB_TRY(prb_extract(h));
+    return PRB_OK;
+}
+
+// Debug / parity: re-run one stage on the current (possibly overwritten) intermediates.
+int prb_run_stage(prb_context* h, const char* name) {
+    if (!h || !name) return PRB_ERR_ARG;
+    Context& c = h->c;
+    PRB_CUDA(cudaSetDevice(c.device));
+    std::string s(name);
+    int need = (s == "divergence") ? 3 : (s == "solve") ? 3 : (s == "iso") ? 4 : (s == "extract") ? 4 : 99;
+    if (c.stage < need) { set_error("prb_run_stage: stage not reachable yet"); return PRB_ERR_STATE; }
+    if (s == "divergence") PRB_TRY(stage_divergence(c));
+    else if (s == "solve") PRB_TRY(stage_solve(c));
+    else if (s == "iso") PRB_TRY(stage_iso(c));
+    else if (s == "extract") { PRB_TRY(stage_extract(c)); if (c.stage < 5) c.stage = 5; }
+    PRB_CUDA(cudaStreamSynchronize(c.stream));
+    return PRB_OK;
+}
+
+int prb_get_mesh_device(prb_context* h, const float** v, int64_t* nv, const int32_t** t, int64_t* nt) {
+    if (!h) return PRB_ERR_ARG;
+    Context& c = h->c;
+    if (c.stage < 5) { set_error("prb_get_mesh: extract not done"); return PRB_ERR_STATE; }
+    if (v) *v = c.meshV.p;
+    if (nv) *nv = c.nMeshV;
+    if (t) *t = c.meshT.p;
+    if (nt) *nt = c.nMeshT;
+    return PRB_OK;
+}
+int prb_get_mesh(prb_context* h, const float** v, int64_t* nv, const int32_t** t, int64_t* nt) {
+    if (!h) return PRB_ERR_ARG;
+    Context& c = h->c;
+    if (c.stage < 5) { set_error("prb_get_mesh: extract not done"); return PRB_ERR_STATE; }
+    PRB_CUDA(cudaSetDevice(c.device));
+    if (!c.hMeshValid) {
+        c.hMeshV.resize(3 * (size_t)c.nMeshV);
+        c.hMeshT.resize(3 * (size_t)c.nMeshT);
+        if (c.nMeshV) PRB_CUDA(cudaMemcpyAsync(c.hMeshV.data(), c.meshV.p, 12 * (size_t)c.nMeshV, cudaMemcpyDeviceToHost, c.stream));
+        if (c.nMeshT) PRB_CUDA(cudaMemcpyAsync(c.hMeshT.data(), c.meshT.p, 12 * (size_t)c.nMeshT, cudaMemcpyDeviceToHost, c.stream));
+        PRB_CUDA(cudaStreamSynchronize(c.stream));
+        c.hMeshValid = true;
+    }
+    if (v) *v = c.hMeshV.data();
+    if (nv) *nv = c.nMeshV;
+    if (t) *t = c.hMeshT.data();
+    if (nt) *nt = c.nMeshT;
+    return PRB_OK;
+}
+
+int prb_get_stats(prb_context* h, prb_stats* out) {
+    if (!h || !out) return PRB_ERR_ARG;
+    Context& c = h->c;
+    PRB_CUDA(cudaSetDevice(c.device));
+    PRB_CUDA(cudaStreamSynchronize(c.stream));
+    prb_stats& s = c.stats;
+    s.n_points = c.N;
+    s.depth = c.D;
+    s.n_nodes = c.M;
+    for (int d = 0; d < 16; d++) { s.nodes_per_depth[d] = d <= c.D ? c.cnt[d] : 0; s.cg_iters[d] = d <= c.D ? c.cgIters[d] : 0; }
+    s.n_subdivide = (int)c.subdivide.size();
+    s.n_passes = (int)c.passes.size();
+    s.n_vertices = c.nMeshV;
+    s.n_triangles = c.nMeshT;
+    s.iso_value = c.iso;
+    for (int a = 0; a < 3; a++) s.center[a] = c.center[a];
+    s.scale = c.scale;
+    s.cg_row_iters = c.cgRowIters;
+    s.kernel_launches = c.launches;
+    auto el = [&](int a, int b) { float ms = 0; if (cudaEventElapsedTime(&ms, c.ev[a], c.ev[b]) != cudaSuccess) { cudaGetLastError(); ms = 0; } return ms; };
+    if (c.stage >= 1) s.ms_h2d = el(0, 1);
+    if (c.stage >= 2) s.ms_octree = el(1, 2);
+    if (c.stage >= 3) { s.ms_splat = el(2, 3); s.ms_divergence = el(3, 4); }
+    if (c.stage >= 4) { s.ms_solve = el(4, 5); s.ms_iso = el(5, 6); }
+    if (c.stage >= 5) { s.ms_extract = el(6, 7); s.ms_total = el(0, 7); }
+    *out = s;
+    return PRB_OK;
+}
+
+int64_t prb_get_array(prb_context* h, const char* name, void* dst, int64_t cap) {
+    if (!h || !name) return PRB_ERR_ARG;
+    Context& c = h->c;
+    cudaSetDevice(c.device);
+    cudaStreamSynchronize(c.stream);
+    std::string s(name);
+    const void* dev = nullptr;
+    int64_t bytes = -1;
+    std::vector<char> host;
+    auto D_ = [&](const void* p, size_t b) { dev = p; bytes = (int64_t)b; };
+    auto H_ = [&](const void* p, size_t b) { host.assign((const char*)p, (const char*)p + b); bytes = (int64_t)b; };
+    const int M = c.M, D = c.D;
+    if (s == "points") D_(c.P.p, c.P.bytes());
+    else if (s == "normals") D_(c.Nr.p, c.Nr.bytes());
+    else if (s == "sorted_idx") D_(c.sortedIdx.p, c.sortedIdx.bytes());
+    else if (s == "sorted_key") D_(c.sortedKey.p, c.sortedKey.bytes());
+    else if (s == "base") H_(c.base, sizeof(int) * (D + 2));
+    else if (s == "count") H_(c.cnt, sizeof(int) * (D + 1));
+    else if (s == "key") D_(c.key.p, c.key.bytes());
+    else if (s == "pidx") D_(c.pidx.p, c.pidx.bytes());
+    else if (s == "pnum") D_(c.pnum.p, c.pnum.bytes());
+    else if (s == "parent") D_(c.parent.p, c.parent.bytes());
+    else if (s == "didx") D_(c.didx.p, c.didx.bytes());
+    else if (s == "dnum") D_(c.dnum.p, c.dnum.bytes());
+    else if (s == "child0") D_(c.child0.p, c.child0.bytes());
+    else if (s == "neighs") D_(c.neighs.p, c.neighs.bytes());
+    else if (s == "nb_base") D_(c.nbBase.p, c.nbBase.bytes());
+    else if (s == "p2n") D_(c.p2n.p, c.p2n.bytes());
+    else if (s == "vectorfield") D_(c.V.p, c.V.bytes());
+    else if (s == "divergence") D_(c.divg.p, c.divg.bytes());
+    else if (s == "x") D_(c.x.p, c.x.bytes());
+    else if (s == "pointvalue") D_(c.pointValue.p, c.pointValue.bytes());
+    else if (s == "vvalue_slots") D_(c.vval.p, c.vval.bytes());
+    else if (s == "mesh_v") D_(c.meshV.p, 12 * (size_t)c.nMeshV);
+    else if (s == "mesh_t") D_(c.meshT.p, 12 * (size_t)c.nMeshT);
+    else if (s == "iso") H_(&c.iso, 4);
+    else if (s == "center_scale") { float v[4] = {c.center[0], c.center[1], c.center[2], c.scale}; H_(v, 16); }
+    else if (s == "cg_iters") H_(c.cgIters, sizeof(int) * (D + 1));
+    else if (s == "lap_stencil") H_(c.tab.stencil.data(), c.tab.stencil.size() * 4);
+    else if (s == "df_table") H_(c.tab.dfT.data(), c.tab.dfT.size() * 4);
+    else if (s == "passes") { std::vector<int> v; for (auto& p : c.passes) { v.push_back(p.kind); v.push_back(p.nv); v.push_back(p.nt); } H_(v.data(), v.size() * 4); }
+    else if (s == "subdivide") H_(c.subdivide.data(), c.subdivide.size() * 4);
+    else if (s == "children") {
+        // expanded [M][8] view of child0 for comparison with the reference layout
+        std::vector<int> c0(M);
+        if (M && cudaMemcpy(c0.data(), c.child0.p, sizeof(int) * (size_t)M, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("copy failed"); return PRB_ERR_CUDA; }
+        std::vector<int> ch(8 * (size_t)M);
+        for (int i = 0; i < M; i++) for (int k = 0; k < 8; k++) ch[8 * (size_t)i + k] = c0[i] < 0 ? -1 : c0[i] + k;
+        H_(ch.data(), ch.size() * 4);
+    } else { set_error("unknown array " + s); return PRB_ERR_ARG; }
+    if (dst && cap >= bytes && bytes > 0) {
+        if (dev) { if (cudaMemcpy(dst, dev, (size_t)bytes, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("copy failed"); return PRB_ERR_CUDA; } }
+        else std::memcpy(dst, host.data(), (size_t)bytes);
+    }
+    return bytes;
+}
+
+int prb_set_array(prb_context* h, const char* name, const void* src, int64_t bytes) {
+    if (!h || !name || !src) return PRB_ERR_ARG;
+    Context& c = h->c;
+    PRB_CUDA(cudaSetDevice(c.device));
+    PRB_CUDA(cudaStreamSynchronize(c.stream));
+    std::string s(name);
+    void* dst = nullptr;
+    size_t want = 0;
+    if (s == "vectorfield") { dst = c.V.p; want = c.V.bytes(); }
+    else if (s == "divergence") { dst = c.divg.p; want = c.divg.bytes(); }
+    else if (s == "x") { dst = c.x.p; want = c.x.bytes(); }
+    else if (s == "iso") { if (bytes != 4) return PRB_ERR_ARG; std::memcpy(&c.iso, src, 4); return PRB_OK; }
+    else { set_error("unknown array " + s); return PRB_ERR_ARG; }
+    if (!dst || (int64_t)want != bytes) { set_error("size mismatch for " + s); return PRB_ERR_ARG; }
+    PRB_CUDA(cudaMemcpy(dst, src, want, cudaMemcpyHostToDevice));
+    return PRB_OK;
+}
+
+}  // extern "C"
