@@ -130,6 +130,78 @@ __global__ void __launch_bounds__(256) k_divergence(const float* __restrict__ V,
     }
 }
 
+// ---- coarse depths: scatter form.  A coarse node has up to 27 * 8^(D-d) terms, far too many for
+// one thread block (the reference runs depths 0-4 as a host loop with one launch set per node,
+// main.cu:3419-3458).  Work item = (node n, chunk of <= kChunk of the depth-D slots under n);
+// every slot contributes to the <= 27 neighbours o of n, so a block accumulates 27 partial sums
+// in double, reduces them and issues at most 27 atomicAdd(double).
+constexpr int kChunk = 2048;
+__global__ void __launch_bounds__(256) k_count_items(const int* __restrict__ dnum, int nNodes, int* __restrict__ items) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nNodes; i += gridDim.x * blockDim.x) items[i] = (dnum[i] + kChunk - 1) / kChunk;
+}
+__global__ void __launch_bounds__(256) k_divergence_scatter(const float* __restrict__ V, const ushort4* __restrict__ offs, const int* __restrict__ neighs,
+                                                            const int* __restrict__ didx, const int* __restrict__ dnum, const float* __restrict__ dfT,
+                                                            const int* __restrict__ dfOffset, const int* __restrict__ itemBase, int nNodes, int baseD, int D,
+                                                            double* __restrict__ accum) {
+    __shared__ int sNode;
+    __shared__ int sNb[27];
+    __shared__ double sRed[8][27];
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = nNodes;                      // last node with itemBase <= blockIdx.x
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (itemBase[mid] <= (int)blockIdx.x) lo = mid; else hi = mid; }
+        sNode = lo;
+    }
+    __syncthreads();
+    const int n = sNode;
+    if (threadIdx.x < 27) sNb[threadIdx.x] = neighs[27 * (i64)n + threadIdx.x];
+    const ushort4 on = offs[n];
+    const int d = on.w, k = 1 << (D - d);
+    const float* row = dfT + dfOffset[d];
+    const int chunk = (int)blockIdx.x - itemBase[n];
+    const int s0 = didx[n] + chunk * kChunk;
+    const int cnt = min(kChunk, dnum[n] - chunk * kChunk);
+    double acc[27];
+#pragma unroll
+    for (int j = 0; j < 27; j++) acc[j] = 0.0;
+    const int bx = k * ((int)on.x - 1), by = k * ((int)on.y - 1), bz = k * ((int)on.z - 1);
+    for (int q = threadIdx.x; q < cnt; q += 256) {
+        int s = s0 + q;
+        ushort4 so = offs[baseD + s];
+        float v0 = V[3 * (i64)s], v1 = V[3 * (i64)s + 1], v2 = V[3 * (i64)s + 2];
+        float ux[3], uy[3], uz[3];
+#pragma unroll
+        for (int t = 0; t < 3; t++) {                 // neighbour o = n + (t-1) per axis
+            ux[t] = row[(int)so.x - bx - k * (t - 1)];
+            uy[t] = row[(int)so.y - by - k * (t - 1)];
+            uz[t] = row[(int)so.z - bz - k * (t - 1)];
+        }
+#pragma unroll
+        for (int j = 0; j < 27; j++) {
+            float dp = __fmul_rn(v0, ux[j / 9]);
+            dp = __fmaf_rn(v1, uy[(j / 3) % 3], dp);
+            dp = __fmaf_rn(v2, uz[j % 3], dp);
+            acc[j] += (double)dp;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 27; j++) {
+        double v = acc[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) sRed[threadIdx.x >> 5][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 27 && sNb[threadIdx.x] >= 0) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) v += sRed[w][threadIdx.x];
+        atomicAdd(&accum[sNb[threadIdx.x]], v);
+    }
+}
+__global__ void __launch_bounds__(256) k_divergence_finish(const double* __restrict__ accum, int n, float* __restrict__ divg) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) divg[i] = (float)accum[i];
+}
+
 int stage_splat(Context& c) {
     const int D = c.D;
     cudaStream_t st = c.stream;
@@ -146,17 +218,36 @@ int stage_splat(Context& c) {
 
 int stage_divergence(Context& c) {
     const int D = c.D;
-    for (int d = 0; d <= D; d++) {
+    cudaStream_t st = c.stream;
+    // depths with up to 8^4 slots under a node and deeper trees of slots go through the scatter
+    // kernel; the three finest depths are gathered per node (thread / warp), which for the two
+    // finest reproduces the reference's summation order exactly.
+    int dc = D - 4;                                   // last depth handled by the scatter kernel
+    if (dc >= 0) {
+        const int nCoarse = c.base[dc + 1];
+        DBuf<int> items, itemBase;
+        DBuf<double> accum;
+        PRB_TRY(items.alloc((size_t)nCoarse, st));
+        PRB_TRY(itemBase.alloc((size_t)nCoarse, st));
+        PRB_TRY(accum.alloc((size_t)nCoarse, st));
+        PRB_CUDA(cudaMemsetAsync(accum.p, 0, sizeof(double) * (size_t)nCoarse, st));
+        PRB_LAUNCH(c, k_count_items, grid_for(c, nCoarse, 256), 256, 0, c.dnum.p, nCoarse, items.p);
+        i64 nItems = 0;
+        PRB_TRY(exclusive_scan(c, items.p, itemBase.p, nCoarse, &nItems));
+        if (nItems > 0)
+            PRB_LAUNCH(c, k_divergence_scatter, (int)nItems, 256, 0, c.V.p, c.offs.p, c.neighs.p, c.didx.p, c.dnum.p, c.dDfT.p, c.dDfOffset.p, itemBase.p,
+                       nCoarse, c.base[D], D, accum.p);
+        PRB_LAUNCH(c, k_divergence_finish, grid_for(c, nCoarse, 256), 256, 0, accum.p, nCoarse, c.divg.p);
+        items.release(); itemBase.release(); accum.release();
+    }
+    for (int d = (dc >= 0 ? dc + 1 : 0); d <= D; d++) {
         int k = 1 << (D - d);
         const float* row = c.dDfT.p + c.tab.dfOffset[d];
         int n = c.cnt[d];
-        if (d >= D - 1) {
+        if (d >= D - 1)
             PRB_LAUNCH(c, k_divergence<1>, grid_for(c, n, 256), 256, 0, c.V.p, c.offs.p, c.neighs.p, c.didx.p, c.dnum.p, row, c.base[d], n, c.base[D], k, c.divg.p);
-        } else if (n >= 2048) {
+        else
             PRB_LAUNCH(c, k_divergence<32>, grid_for(c, (i64)n * 32, 256), 256, 0, c.V.p, c.offs.p, c.neighs.p, c.didx.p, c.dnum.p, row, c.base[d], n, c.base[D], k, c.divg.p);
-        } else {
-            PRB_LAUNCH(c, k_divergence<1024>, n, 256, 0, c.V.p, c.offs.p, c.neighs.p, c.didx.p, c.dnum.p, row, c.base[d], n, c.base[D], k, c.divg.p);
-        }
     }
     PRB_CUDA(cudaGetLastError());
     return PRB_OK;

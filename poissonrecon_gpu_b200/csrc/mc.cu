@@ -198,31 +198,33 @@ __global__ void __launch_bounds__(128) k_vertex_values(Topo T, int M, int D, con
                                                        const ushort4* __restrict__ offs, const float* __restrict__ x, const float* __restrict__ baseFn,
                                                        float iso, float* __restrict__ vval) {
     const int exceedTab[8] = {0, 1, 3, 2, 4, 5, 7, 6};     // childrenVertexKind, MarchingCubes.cuh:721-723 (applied as the reference does)
-    i64 total = 8 * (i64)M;
-    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
-        int i = (int)(t >> 3), j = (int)(t & 7), m;
-        if (i == 0) continue;                              // root vertices are dropped (validVertex, main.cu:1634-1638)
-        if (corner_owner(T, i, j, m) != i) continue;
+    // one thread per node, looping over the corners it owns (an interior cell owns exactly one,
+    // so all lanes stay busy; a thread per (node, corner) leaves 7 of 8 lanes idle in the walk)
+    for (int i = 1 + blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {   // root vertices are dropped (validVertex, main.cu:1634-1638)
         ushort4 o = offs[i];
-        int depth = o.w;
-        float w = 1.0f / (float)(1 << depth);
-        float pos[3] = {(float)((int)o.x + (j & 1)) * w, (float)((int)o.y + ((j >> 1) & 1)) * w, (float)((int)o.z + ((j >> 2) & 1)) * w};
-        float val = 0.f;
-        int now = i;
-        while (now != -1) {
-            accumulate_level(val, T.nbr + 27 * (i64)now, offs[now], x, baseFn, pos);
-            now = parent[now];
+        const int depth0 = o.w;
+        const float w = 1.0f / (float)(1 << depth0);
+        for (int j = 0; j < 8; j++) {
+            int m;
+            if (corner_owner(T, i, j, m) != i) continue;
+            float pos[3] = {(float)((int)o.x + (j & 1)) * w, (float)((int)o.y + ((j >> 1) & 1)) * w, (float)((int)o.z + ((j >> 2) & 1)) * w};
+            float val = 0.f;
+            int now = i;
+            while (now != -1) {
+                accumulate_level(val, T.nbr + 27 * (i64)now, offs[now], x, baseFn, pos);
+                now = parent[now];
+            }
+            now = i;
+            int ex = exceedTab[j], depth = depth0;
+            while (depth < D) {
+                ++depth;
+                int c0 = child0[now];
+                if (c0 < 0) break;
+                now = c0 + ex;
+                accumulate_level(val, T.nbr + 27 * (i64)now, offs[now], x, baseFn, pos);
+            }
+            vval[8 * (i64)i + j] = __fsub_rn(val, iso);
         }
-        now = i;
-        int ex = exceedTab[j];
-        while (depth < D) {
-            ++depth;
-            int c0 = child0[now];
-            if (c0 < 0) break;
-            now = c0 + ex;
-            accumulate_level(val, T.nbr + 27 * (i64)now, offs[now], x, baseFn, pos);
-        }
-        vval[t] = __fsub_rn(val, iso);
     }
 }
 
@@ -413,57 +415,73 @@ __global__ void __launch_bounds__(256) k_vcell_offsets(VTree V, const ushort4* _
         voffs[vl] = make_ushort4((unsigned short)ox, (unsigned short)oy, (unsigned short)oz, (unsigned short)V.D);
     }
 }
+// per virtual node: which of its 27 neighbour slots carry a solution value (a real node, or, at
+// the roots' level, a virtual root standing for the real leaf it replaces)
+__global__ void __launch_bounds__(256) k_vmask(VTree V, i64 total, const int* __restrict__ vneigh, unsigned* __restrict__ vmask) {
+    for (i64 v = (i64)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (i64)gridDim.x * blockDim.x) {
+        bool rootLevel = v < V.depthAddr[V.rd] + V.nr;
+        unsigned m = 0;
+        const int* nb = vneigh + 27 * v;
+#pragma unroll
+        for (int j = 0; j < 27; j++) {
+            int q = nb[j];
+            if (q >= 0 && (q < V.M || rootLevel)) m |= 1u << j;
+        }
+        vmask[v] = m;
+    }
+}
 // corner values of the depth-D virtual cells: only REAL nodes carry a solution; a virtual root
-// stands for the real leaf it replaces (main.cu:2328-2442)
-__global__ void __launch_bounds__(128) k_vvertex_values(VTree V, Topo T, const int* __restrict__ vneigh, const ushort4* __restrict__ voffs,
+// stands for the real leaf it replaces (main.cu:2328-2442).  One thread per cell, looping over
+// the corners it owns; virtual levels without any real neighbour are skipped via vmask.
+__global__ void __launch_bounds__(128) k_vvertex_values(VTree V, Topo T, const int* __restrict__ vneigh, const unsigned* __restrict__ vmask,
+                                                        const ushort4* __restrict__ voffs,
                                                         const int* __restrict__ neighs, const int* __restrict__ parent, const ushort4* __restrict__ offs,
                                                         const float* __restrict__ x, const float* __restrict__ baseFn, float iso, float* __restrict__ sval) {
     const int perD = vt_per(V, V.D);
-    const i64 total = 8 * (i64)T.nCells;
     const float w = 1.0f / (float)(1 << V.D);
-    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
-        int l = (int)(t >> 3), j = (int)(t & 7), m;
-        int id = T.cellBase + l;
-        if (corner_owner(T, id, j, m) != id) continue;
-        ushort4 o = voffs[l];
-        float pos[3] = {(float)((int)o.x + (j & 1)) * w, (float)((int)o.y + ((j >> 1) & 1)) * w, (float)((int)o.z + ((j >> 2) & 1)) * w};
-        float val = 0.f;
-        int r = l / perD, loc = l - r * perD;
-        // virtual levels D .. rd
-        for (int d = V.D; d >= V.rd; --d) {
-            int per = vt_per(V, d);
-            int v = V.depthAddr[d] + r * per + loc;
-            const int* nb = vneigh + 27 * (i64)v;
-            int od = V.D - d;
-            int nn = 1 << d, f0 = nn - 1;
-            int ox = (int)o.x >> od, oy = (int)o.y >> od, oz = (int)o.z >> od;
-            float vx[3], vy[3], vz[3];
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < T.nCells; l += gridDim.x * blockDim.x) {
+        const int id = T.cellBase + l;
+        const ushort4 o = voffs[l];
+        const int r = l / perD;
+        for (int j = 0; j < 8; j++) {
+            int m;
+            if (corner_owner(T, id, j, m) != id) continue;
+            float pos[3] = {(float)((int)o.x + (j & 1)) * w, (float)((int)o.y + ((j >> 1) & 1)) * w, (float)((int)o.z + ((j >> 2) & 1)) * w};
+            float val = 0.f;
+            int loc = l - r * perD;
+            for (int d = V.D; d >= V.rd; --d) {           // virtual levels D .. rd
+                int per = vt_per(V, d);
+                int v = V.depthAddr[d] + r * per + loc;
+                loc >>= 3;
+                unsigned mk = vmask[v];
+                if (!mk) continue;
+                const int* nb = vneigh + 27 * (i64)v;
+                int od = V.D - d;
+                int nn = 1 << d, f0 = nn - 1;
+                int ox = (int)o.x >> od, oy = (int)o.y >> od, oz = (int)o.z >> od;
+                float vx[3], vy[3], vz[3];
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                int ax = ox + k - 1, ay = oy + k - 1, az = oz + k - 1;
-                vx[k] = (ax >= 0 && ax < nn) ? base_value(baseFn, f0 + ax, pos[0]) : 0.f;
-                vy[k] = (ay >= 0 && ay < nn) ? base_value(baseFn, f0 + ay, pos[1]) : 0.f;
-                vz[k] = (az >= 0 && az < nn) ? base_value(baseFn, f0 + az, pos[2]) : 0.f;
-            }
-#pragma unroll
-            for (int jj = 0; jj < 27; jj++) {
-                int q = nb[jj];
-                if (q < 0) continue;
-                if (q >= V.M) {
-                    if (d != V.rd) continue;                  // virtual non-root: no solution value
-                    q = V.roots[q - V.M - V.depthAddr[V.rd]];  // virtual root -> the real leaf it replaces
+                for (int k = 0; k < 3; k++) {
+                    int ax = ox + k - 1, ay = oy + k - 1, az = oz + k - 1;
+                    vx[k] = (ax >= 0 && ax < nn) ? base_value(baseFn, f0 + ax, pos[0]) : 0.f;
+                    vy[k] = (ay >= 0 && ay < nn) ? base_value(baseFn, f0 + ay, pos[1]) : 0.f;
+                    vz[k] = (az >= 0 && az < nn) ? base_value(baseFn, f0 + az, pos[2]) : 0.f;
                 }
-                val = __fmaf_rn(__fmul_rn(__fmul_rn(x[q], vx[jj / 9]), vy[(jj / 3) % 3]), vz[jj % 3], val);
+#pragma unroll
+                for (int jj = 0; jj < 27; jj++) {
+                    if (!(mk & (1u << jj))) continue;
+                    int q = nb[jj];
+                    if (q >= V.M) q = V.roots[q - V.M - V.depthAddr[V.rd]];   // virtual root -> the real leaf it replaces
+                    val = __fmaf_rn(__fmul_rn(__fmul_rn(x[q], vx[jj / 9]), vy[(jj / 3) % 3]), vz[jj % 3], val);
+                }
             }
-            loc >>= 3;
+            int now = parent[V.roots[r]];                 // real ancestors
+            while (now != -1) {
+                accumulate_level(val, neighs + 27 * (i64)now, offs[now], x, baseFn, pos);
+                now = parent[now];
+            }
+            sval[8 * (i64)l + j] = __fsub_rn(val, iso);
         }
-        // real ancestors
-        int now = parent[V.roots[r]];
-        while (now != -1) {
-            accumulate_level(val, neighs + 27 * (i64)now, offs[now], x, baseFn, pos);
-            now = parent[now];
-        }
-        sval[t] = __fsub_rn(val, iso);
     }
 }
 __global__ void __launch_bounds__(256) k_offset_triangles(int* __restrict__ t, i64 n, int off) {
@@ -534,7 +552,10 @@ static int refine_pass(Context& c, const int* dRoots, int nr, int rd, bool singl
     PRB_TRY(voffs.alloc((size_t)nD, st));
     PRB_TRY(sval.alloc(8 * (size_t)nD, st));
     PRB_LAUNCH(c, k_vcell_offsets, grid_for(c, nD, 256), 256, 0, V, c.offs.p, voffs.p);
-    PRB_LAUNCH(c, k_vvertex_values, grid_for(c, 8 * (i64)nD, 128, 16), 128, 0, V, T, vneigh.p, voffs.p, c.neighs.p, c.parent.p, c.offs.p, c.x.p, c.dBaseFn.p, c.iso, sval.p);
+    DBuf<unsigned> vmask;
+    PRB_TRY(vmask.alloc((size_t)total, st));
+    PRB_LAUNCH(c, k_vmask, grid_for(c, total, 256), 256, 0, V, total, vneigh.p, vmask.p);
+    PRB_LAUNCH(c, k_vvertex_values, grid_for(c, nD, 128, 16), 128, 0, V, T, vneigh.p, vmask.p, voffs.p, c.neighs.p, c.parent.p, c.offs.p, c.x.p, c.dBaseFn.p, c.iso, sval.p);
     outs.emplace_back();
     PassOut& po = outs.back();
     PRB_TRY(run_mc_on_cells(c, T, sval.p, T.cellBase, voffs.p, false, nullptr, po));
@@ -544,7 +565,7 @@ static int refine_pass(Context& c, const int* dRoots, int nr, int rd, bool singl
     } else {
         c.passes.push_back({single ? 1 : 2, po.nv, po.nt});
     }
-    vneigh.release(); voffs.release(); sval.release();
+    vneigh.release(); voffs.release(); sval.release(); vmask.release();
     return PRB_OK;
 }
 
@@ -558,7 +579,7 @@ int stage_extract(Context& c) {
     Topo R;
     R.nbr = c.neighs.p; R.rowBase = 0; R.minId = 0; R.cellBase = c.base[D]; R.nCells = c.cnt[D];
     PRB_TRY(c.vval.alloc(8 * (size_t)M, st));
-    PRB_LAUNCH(c, k_vertex_values, grid_for(c, 8 * (i64)M, 128, 16), 128, 0, R, M, D, c.parent.p, c.child0.p, c.offs.p, c.x.p, c.dBaseFn.p, c.iso, c.vval.p);
+    PRB_LAUNCH(c, k_vertex_values, grid_for(c, M, 128, 16), 128, 0, R, M, D, c.parent.p, c.child0.p, c.offs.p, c.x.p, c.dBaseFn.p, c.iso, c.vval.p);
     DBuf<unsigned> fmark;
     PRB_TRY(fmark.alloc((size_t)M, st));
     PRB_CUDA(cudaMemsetAsync(fmark.p, 0, sizeof(unsigned) * (size_t)M, st));

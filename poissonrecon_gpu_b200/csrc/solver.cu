@@ -154,15 +154,19 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
                 const float beta = sBeta[d];
                 for (int t = tid; t < ng * 27; t += kCgBlock) (&sbase[0][0])[t] = P.nbBase[27 * (i64)g0 + t];
                 __syncthreads();
-                for (int v = tid; v < ng * 216; v += kCgBlock) {
-                    int g = v / 216, rem = v - g * 216;
-                    int b = sbase[g][rem >> 3];
-                    float val = 0.f;
-                    if (b >= 0) {
-                        int n = b + (rem & 7);
-                        val = __fadd_rn(P.r[n], __fmul_rn(beta, pOld[n]));
+                // stage the 27 neighbour blocks of every group: thread (g, e) walks the 27 blocks, so
+                // 8 lanes read one 32-byte sector per load and all 27 (x2) loads are independent
+                {
+                    const int g = tid >> 3, e = tid & 7;
+                    if (g < ng) {
+#pragma unroll
+                        for (int blk = 0; blk < 27; blk++) {
+                            int b = sbase[g][blk];
+                            float val = 0.f;
+                            if (b >= 0) val = __fadd_rn(P.r[b + e], __fmul_rn(beta, pOld[b + e]));
+                            sval[g][blk][e] = val;
+                        }
                     }
-                    (&sval[0][0][0])[v] = val;
                 }
                 __syncthreads();
                 double part = 0.0;
