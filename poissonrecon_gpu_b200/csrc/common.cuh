@@ -91,7 +91,8 @@ struct Context {
     DBuf<int> dDfOffset;
     // ---- fields
     DBuf<float> V;                 // [M_D][3]
-    DBuf<float> divg, x;
+    DBuf<float> divg, x;          // x is padded: node i lives at xv[i] = x.p[7 + i] (sibling blocks 32-byte aligned)
+    float* xv = nullptr;
     DBuf<float> pointValue;
     float iso = 0;
     int cgIters[kMaxDepth + 1] = {0};

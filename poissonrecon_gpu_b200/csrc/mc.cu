@@ -125,7 +125,7 @@ int stage_iso(Context& c) {
     DBuf<double> sum;
     PRB_TRY(sum.alloc(1, st));
     PRB_CUDA(cudaMemsetAsync(sum.p, 0, sizeof(double), st));
-    PRB_LAUNCH(c, k_point_values, grid_for(c, c.N, 128, 16), 128, 0, c.P.p, c.p2n.p, c.N, c.base[c.D], c.neighs.p, c.parent.p, c.offs.p, c.x.p, c.dBaseFn.p,
+    PRB_LAUNCH(c, k_point_values, grid_for(c, c.N, 128, 16), 128, 0, c.P.p, c.p2n.p, c.N, c.base[c.D], c.neighs.p, c.parent.p, c.offs.p, c.xv, c.dBaseFn.p,
                c.pointValue.p, sum.p);
     double h = 0;
     PRB_CUDA(cudaMemcpyAsync(&h, sum.p, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -555,7 +555,7 @@ static int refine_pass(Context& c, const int* dRoots, int nr, int rd, bool singl
     DBuf<unsigned> vmask;
     PRB_TRY(vmask.alloc((size_t)total, st));
     PRB_LAUNCH(c, k_vmask, grid_for(c, total, 256), 256, 0, V, total, vneigh.p, vmask.p);
-    PRB_LAUNCH(c, k_vvertex_values, grid_for(c, nD, 128, 16), 128, 0, V, T, vneigh.p, vmask.p, voffs.p, c.neighs.p, c.parent.p, c.offs.p, c.x.p, c.dBaseFn.p, c.iso, sval.p);
+    PRB_LAUNCH(c, k_vvertex_values, grid_for(c, nD, 128, 16), 128, 0, V, T, vneigh.p, vmask.p, voffs.p, c.neighs.p, c.parent.p, c.offs.p, c.xv, c.dBaseFn.p, c.iso, sval.p);
     outs.emplace_back();
     PassOut& po = outs.back();
     PRB_TRY(run_mc_on_cells(c, T, sval.p, T.cellBase, voffs.p, false, nullptr, po));
@@ -579,7 +579,7 @@ int stage_extract(Context& c) {
     Topo R;
     R.nbr = c.neighs.p; R.rowBase = 0; R.minId = 0; R.cellBase = c.base[D]; R.nCells = c.cnt[D];
     PRB_TRY(c.vval.alloc(8 * (size_t)M, st));
-    PRB_LAUNCH(c, k_vertex_values, grid_for(c, M, 128, 16), 128, 0, R, M, D, c.parent.p, c.child0.p, c.offs.p, c.x.p, c.dBaseFn.p, c.iso, c.vval.p);
+    PRB_LAUNCH(c, k_vertex_values, grid_for(c, M, 128, 16), 128, 0, R, M, D, c.parent.p, c.child0.p, c.offs.p, c.xv, c.dBaseFn.p, c.iso, c.vval.p);
     DBuf<unsigned> fmark;
     PRB_TRY(fmark.alloc((size_t)M, st));
     PRB_CUDA(cudaMemsetAsync(fmark.p, 0, sizeof(unsigned) * (size_t)M, st));

@@ -16,6 +16,7 @@ static void release_all(Context& c) {
     c.V.release(); c.divg.release(); c.x.release(); c.pointValue.release();
     c.meshV.release(); c.meshT.release(); c.vval.release();
     c.nMeshV = c.nMeshT = 0;
+    c.xv = nullptr;
     c.hMeshValid = false;
 }
 
@@ -280,7 +281,7 @@ int64_t prb_get_array(prb_context* h, const char* name, void* dst, int64_t cap) 
     else if (s == "p2n") D_(c.p2n.p, c.p2n.bytes());
     else if (s == "vectorfield") D_(c.V.p, c.V.bytes());
     else if (s == "divergence") D_(c.divg.p, c.divg.bytes());
-    else if (s == "x") D_(c.x.p, c.x.bytes());
+    else if (s == "x") D_(c.xv, c.xv ? 4 * (size_t)M : 0);
     else if (s == "pointvalue") D_(c.pointValue.p, c.pointValue.bytes());
     else if (s == "vvalue_slots") D_(c.vval.p, c.vval.bytes());
     else if (s == "mesh_v") D_(c.meshV.p, 12 * (size_t)c.nMeshV);
@@ -317,7 +318,7 @@ int prb_set_array(prb_context* h, const char* name, const void* src, int64_t byt
     size_t want = 0;
     if (s == "vectorfield") { dst = c.V.p; want = c.V.bytes(); }
     else if (s == "divergence") { dst = c.divg.p; want = c.divg.bytes(); }
-    else if (s == "x") { dst = c.x.p; want = c.x.bytes(); }
+    else if (s == "x") { dst = c.xv; want = c.xv ? 4 * (size_t)c.M : 0; }
     else if (s == "iso") { if (bytes != 4) return PRB_ERR_ARG; std::memcpy(&c.iso, src, 4); return PRB_OK; }
     else { set_error("unknown array " + s); return PRB_ERR_ARG; }
     if (!dst || (int64_t)want != bytes) { set_error("size mismatch for " + s); return PRB_ERR_ARG; }

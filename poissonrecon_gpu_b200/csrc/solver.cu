@@ -6,18 +6,21 @@
 // memory, 7 grid syncs per iteration and host loops over managed arrays around the launch.
 // Here:
 //   * the matrix is never formed: rows are the translation-invariant 27-point stencil
-//     (4 distinct values per depth, stencil[d][27]) applied through the sibling-block table
-//     nbBase[group][27] (13.5 B/row instead of 216 B/row of CSR);
+//     (4 distinct values per depth) applied through the sibling-block table nbBase[group][27]
+//     (13.5 B/row instead of 216 B/row of CSR);
 //   * the depths are independent, so they all iterate in lock-step inside one
 //     launch: one iteration of the kernel = one CG iteration of every still-active depth, with
 //     per-depth alpha / beta / residual and per-depth stopping.  Grid syncs per solve drop from
-//     7 * sum_d iters_d to 2 * max_d iters_d;
-//   * p = r + beta*p is recomputed on the fly while the neighbour blocks are staged into shared
-//     memory (double-buffered p), which removes the third pass and its sync;
-//   * the row sum runs over present neighbours in slot order j = 0..26 with FMAs, exactly the
-//     reference's CSR order, so A*p is bit-identical; dots are float products accumulated in
-//     double (CG_CUDA.cuh:217-220); alpha, beta are float.
-// Algorithmic bytes per row per iteration: 57.5 B.
+//     7 * sum_d iters_d to 3 * max_d iters_d;
+//   * SpMV is warp-centric: a warp owns 4 sibling groups (32 rows), stages their 27 neighbour
+//     blocks with 128-bit loads (a sibling block of 8 floats is one aligned 32-byte sector) into
+//     a 6x6x6 shared-memory cube per group, and every row then reads its 3x3x3 window at
+//     compile-time offsets from one base address (bank-conflict free) -- no block barriers;
+//   * the row sum runs over the neighbour slots in order j = 0..26 with FMAs, exactly the
+//     reference's CSR order (absent neighbours contribute an exact +0), so A*p is bit-identical;
+//     dots are float products accumulated in double (CG_CUDA.cuh:217-220); alpha, beta are float.
+// Algorithmic bytes per row per iteration: 57.5 B
+//   (p=r+beta*p: 12, SpMV: 13.5 + 4 + 4, x/r update: 24).
 #include "common.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
@@ -25,7 +28,8 @@ namespace cg = cooperative_groups;
 namespace prb {
 
 constexpr int kCgBlock = 256;
-constexpr int kGroupsPerTile = kCgBlock / 8;      // 32 sibling groups = 256 rows per tile
+constexpr int kCgWarps = kCgBlock / 32;
+constexpr int kGroupsPerWarp = 4;                 // 32 rows per warp tile
 
 struct CgParams {
     int D;
@@ -33,10 +37,10 @@ struct CgParams {
     const int* nbBase;
     const float* stencil;          // [D+1][27]
     const float* b;                // divergence
+    // vectors indexed by node id; node 1 sits on a 32-byte boundary (pointer = allocation + 7)
     float* x;
     float* r;
-    float* p0;
-    float* p1;
+    float* p;
     float* Ap;
     double* dots;                  // [2 buffers][2 kinds][16] + [16] for the initial r.r
     int* itersOut;                 // [D+1]
@@ -45,36 +49,31 @@ struct CgParams {
     int maxIter;
 };
 
-__device__ __forceinline__ double block_sum(double v, double* red) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        v = threadIdx.x < (kCgBlock >> 5) ? red[threadIdx.x] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    }
-    return v;   // valid in thread 0
-}
+// (blk, half) -> offset inside the 6x6x6 cube of the first of the 4 floats of that half block
+__constant__ unsigned short cCubeOff[54];
 
 __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ float sval[kGroupsPerTile][27][8];
-    __shared__ int sbase[kGroupsPerTile][27];
-    __shared__ float sSt[kMaxDepth + 1][27];
-    __shared__ double red[32];
-    __shared__ float sR1[kMaxDepth + 1], sR0[kMaxDepth + 1], sAlpha[kMaxDepth + 1], sBeta[kMaxDepth + 1];
+    __shared__ __align__(16) float sCube[kCgWarps][kGroupsPerWarp][216];
+    __shared__ float sSt[kMaxDepth + 1][4];
+    __shared__ double sAcc[kMaxDepth + 1];
+    __shared__ float sR1[kMaxDepth + 1], sAlpha[kMaxDepth + 1], sBeta[kMaxDepth + 1];
     __shared__ int sActive[kMaxDepth + 1], sIter[kMaxDepth + 1];
-    __shared__ int sTileStart[kMaxDepth + 2];     // prefix of tiles over active depths
-    const int D = P.D, tid = threadIdx.x;
-    for (int t = tid; t < (D + 1) * 27; t += kCgBlock) sSt[t / 27][t % 27] = P.stencil[t];
+    __shared__ int sTileStart[kMaxDepth + 2];     // prefix of warp tiles over active depths
+    __shared__ int sGrpStart[kMaxDepth + 2];      // prefix of sibling groups over active depths
+    const int D = P.D, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gwarp = blockIdx.x * kCgWarps + warp, nwarps = gridDim.x * kCgWarps;
+    if (tid < (D + 1) * 4) {
+        // one representative per number of off-centre axes: j = 13, 14, 17, 26
+        const int rep[4] = {13, 14, 17, 26};
+        sSt[tid >> 2][tid & 3] = P.stencil[(tid >> 2) * 27 + rep[tid & 3]];
+    }
+    if (tid <= D) sAcc[tid] = 0.0;
     __syncthreads();
 
     // ---- depth 0: a 1x1 system, solved by one thread with the same recurrences
     if (blockIdx.x == 0 && tid == 0) {
-        float a00 = sSt[0][13];
+        float a00 = sSt[0][0];
         float x0 = 0.f, r = P.b[0], p = 0.f, r0 = 0.f;
         float r1 = (float)(double)(r * r);
         int k = 1;
@@ -97,16 +96,13 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
     {
         double acc = 0.0;
         int curD = -1;
-        __shared__ double sAcc[kMaxDepth + 1];
-        if (tid <= D) sAcc[tid] = 0.0;
-        __syncthreads();
-        int totalRows = 8 * P.gbase[D + 1];
+        const int totalRows = 8 * P.gbase[D + 1];
         for (int rowi = blockIdx.x * kCgBlock + tid; rowi < totalRows; rowi += gridDim.x * kCgBlock) {
             int i = 1 + rowi, G = rowi >> 3, d = 1;
             while (G >= P.gbase[d + 1]) d++;
             if (d != curD) { if (curD >= 0) atomicAdd(&sAcc[curD], acc); acc = 0.0; curD = d; }
             float bv = P.b[i];
-            P.x[i] = 0.f; P.r[i] = bv; P.p0[i] = 0.f; P.p1[i] = 0.f;
+            P.x[i] = 0.f; P.r[i] = bv; P.p[i] = 0.f;
             acc += (double)(bv * bv);
         }
         if (curD >= 0) atomicAdd(&sAcc[curD], acc);
@@ -116,113 +112,184 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
     grid.sync();
     if (tid >= 1 && tid <= D) {
         float r1 = (float)P.dots[64 + tid];
-        sR1[tid] = r1; sR0[tid] = 0.f; sIter[tid] = 1; sBeta[tid] = 0.f; sAlpha[tid] = 0.f;
+        sR1[tid] = r1; sIter[tid] = 1; sBeta[tid] = 0.f; sAlpha[tid] = 0.f;
         sActive[tid] = (r1 > P.tol2 && 1 <= P.maxIter) ? 1 : 0;
     }
     __syncthreads();
 
+    const int gi = lane >> 3, cc = lane & 7;
+    const int cubeBase = (2 + ((cc >> 2) & 1)) * 36 + (2 + ((cc >> 1) & 1)) * 6 + (2 + (cc & 1));
+    float* myCube = &sCube[warp][0][0];
+    // staging task t = lane + 32k handles half-block (blk = t>>1, half = t&1); its cube offset
+    // depends on the lane only, so it is computed once (a __constant__ table indexed by lane would
+    // serialise: the constant cache serves one address per cycle)
+    int cubeOff[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        int t = lane + 32 * k, blk = t >> 1, half = t & 1;
+        cubeOff[k] = (2 * (blk / 9) + half) * 36 + (2 * ((blk / 3) % 3)) * 6 + 2 * (blk % 3);
+    }
+
     for (int it = 1;; it++) {
         // every block derives the same schedule from the same per-depth state
-        int anyActive = 0;
         if (tid == 0) {
-            int acc = 0;
+            int acc = 0, accG = 0;
             for (int d = 1; d <= D; d++) {
                 sTileStart[d] = acc;
-                if (sActive[d]) acc += (P.gbase[d + 1] - P.gbase[d] + kGroupsPerTile - 1) / kGroupsPerTile;
+                sGrpStart[d] = accG;
+                if (sActive[d]) { acc += (P.gbase[d + 1] - P.gbase[d] + kGroupsPerWarp - 1) / kGroupsPerWarp; accG += P.gbase[d + 1] - P.gbase[d]; }
             }
             sTileStart[D + 1] = acc;
+            sGrpStart[D + 1] = accG;
         }
+        if (tid <= D) sAcc[tid] = 0.0;
         __syncthreads();
         const int nTiles = sTileStart[D + 1];
-        anyActive = nTiles > 0;
-        if (!anyActive) break;
+        if (nTiles == 0) break;
         const int cur = it & 1, nxt = cur ^ 1;
         double* dPAp = P.dots + cur * 32;         // kind 0
         double* dRRn = P.dots + cur * 32 + 16;    // kind 1 (this iteration's new r.r)
-        const float* pOld = (it & 1) ? P.p0 : P.p1;
-        float* pNew = (it & 1) ? P.p1 : P.p0;
-        // ---------------- phase A: p = r + beta p ; Ap = A p ; p.Ap
+
+        // ---------------- phase C: p = r + beta p   (beta = 0 and p = 0 in the first iteration)
+        // streaming over the active depth slabs, 4 rows (one 128-bit access) per thread
         {
-            __shared__ double sAcc[kMaxDepth + 1];
-            if (tid <= D) sAcc[tid] = 0.0;
-            __syncthreads();
-            for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
-                int d = 1;
-                while (!(sActive[d] && tile >= sTileStart[d] && tile < sTileStart[d + 1])) d++;
-                const int g0 = P.gbase[d] + (tile - sTileStart[d]) * kGroupsPerTile;
-                const int ng = min(kGroupsPerTile, P.gbase[d + 1] - g0);
-                const float beta = sBeta[d];
-                for (int t = tid; t < ng * 27; t += kCgBlock) (&sbase[0][0])[t] = P.nbBase[27 * (i64)g0 + t];
-                __syncthreads();
-                // stage the 27 neighbour blocks of every group: thread (g, e) walks the 27 blocks, so
-                // 8 lanes read one 32-byte sector per load and all 27 (x2) loads are independent
-                {
-                    const int g = tid >> 3, e = tid & 7;
-                    if (g < ng) {
-#pragma unroll
-                        for (int blk = 0; blk < 27; blk++) {
-                            int b = sbase[g][blk];
-                            float val = 0.f;
-                            if (b >= 0) val = __fadd_rn(P.r[b + e], __fmul_rn(beta, pOld[b + e]));
-                            sval[g][blk][e] = val;
-                        }
-                    }
+            const int nQuads = 2 * sGrpStart[D + 1];
+            int d = 0, lo = 0, hi = 0, gb = 0;
+            float be = 0.f;
+            for (int q = blockIdx.x * kCgBlock + tid; q < nQuads; q += gridDim.x * kCgBlock) {
+                int ag = q >> 1;
+                while (ag >= hi) { d++; lo = sGrpStart[d]; hi = sGrpStart[d + 1]; gb = P.gbase[d]; be = sBeta[d]; }   // inactive depths have lo == hi
+                int i = 1 + 8 * (gb + ag - lo) + 4 * (q & 1);
+                float4 rv = *reinterpret_cast<const float4*>(P.r + i);
+                float4 pv = *reinterpret_cast<const float4*>(P.p + i);
+                pv.x = __fadd_rn(rv.x, __fmul_rn(be, pv.x));
+                pv.y = __fadd_rn(rv.y, __fmul_rn(be, pv.y));
+                pv.z = __fadd_rn(rv.z, __fmul_rn(be, pv.z));
+                pv.w = __fadd_rn(rv.w, __fmul_rn(be, pv.w));
+                *reinterpret_cast<float4*>(P.p + i) = pv;
+            }
+        }
+        grid.sync();
+        // ---------------- phase A: Ap = A p ; p.Ap
+        {
+            double part = 0.0;
+            int curD = -1;
+            int d = 0, lo = 0, hi = 0, gb = 0, ge = 0;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            for (int tile = gwarp; tile < nTiles; tile += nwarps) {
+                while (tile >= hi) {
+                    d++; lo = sTileStart[d]; hi = sTileStart[d + 1]; gb = P.gbase[d]; ge = P.gbase[d + 1];
+                    s0 = sSt[d][0]; s1 = sSt[d][1]; s2 = sSt[d][2]; s3 = sSt[d][3];
                 }
-                __syncthreads();
-                double part = 0.0;
-                int g = tid >> 3, c = tid & 7;
-                if (g < ng) {
-                    const int cx = (c >> 2) & 1, cy = (c >> 1) & 1, cz = c & 1;
+                const int g0 = gb + (tile - lo) * kGroupsPerWarp;
+                const int ng = min(kGroupsPerWarp, ge - g0);
+                if (d != curD) {
+                    if (curD >= 0) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+                        if (lane == 0) atomicAdd(&sAcc[curD], part);
+                    }
+                    part = 0.0;
+                    curD = d;
+                }
+                __syncwarp();
+                {
+                    // all 8 base loads first, then all 8 128-bit value loads, then the stores:
+                    // 8 independent requests in flight per lane instead of a base->value chain per group
+                    const int* nbp = P.nbBase + 27 * (i64)g0;
+                    int bb[kGroupsPerWarp][2];
+#pragma unroll
+                    for (int g = 0; g < kGroupsPerWarp; g++)
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            int t = lane + 32 * k;
+                            bb[g][k] = (g < ng && t < 54) ? nbp[27 * g + (t >> 1)] : -1;
+                        }
+                    float4 vv[kGroupsPerWarp][2];
+#pragma unroll
+                    for (int g = 0; g < kGroupsPerWarp; g++)
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            vv[g][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (bb[g][k] >= 0) vv[g][k] = *reinterpret_cast<const float4*>(P.p + bb[g][k] + 4 * (lane & 1));
+                        }
+#pragma unroll
+                    for (int g = 0; g < kGroupsPerWarp; g++)
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            int t = lane + 32 * k;
+                            if (g < ng && t < 54) {
+                                int off = cubeOff[k];
+                                float* cube = myCube + g * 216;
+                                *reinterpret_cast<float2*>(cube + off) = make_float2(vv[g][k].x, vv[g][k].y);
+                                *reinterpret_cast<float2*>(cube + off + 6) = make_float2(vv[g][k].z, vv[g][k].w);
+                            }
+                        }
+                }
+                __syncwarp();
+                if (gi < ng) {
+                    const float* cb = myCube + gi * 216 + cubeBase;
                     float acc = 0.f;
 #pragma unroll
                     for (int j = 0; j < 27; j++) {
-                        const int tx = cx + j / 9 - 1, ty = cy + (j / 3) % 3 - 1, tz = cz + j % 3 - 1;
-                        const int blk = (tx < 0 ? 0 : (tx > 1 ? 2 : 1)) * 9 + (ty < 0 ? 0 : (ty > 1 ? 2 : 1)) * 3 + (tz < 0 ? 0 : (tz > 1 ? 2 : 1));
-                        const int e = ((tx & 1) << 2) | ((ty & 1) << 1) | (tz & 1);
-                        if (sbase[g][blk] >= 0) acc = __fmaf_rn(sSt[d][j], sval[g][blk][e], acc);
+                        const int dx = j / 9 - 1, dy = (j / 3) % 3 - 1, dz = j % 3 - 1;
+                        const int ty = (dx != 0) + (dy != 0) + (dz != 0);
+                        const float sv = ty == 0 ? s0 : (ty == 1 ? s1 : (ty == 2 ? s2 : s3));
+                        acc = __fmaf_rn(sv, cb[dx * 36 + dy * 6 + dz], acc);
                     }
-                    int i = 1 + 8 * (g0 + g) + c;
-                    float pv = sval[g][13][c];
+                    int i = 1 + 8 * (g0 + gi) + cc;
                     P.Ap[i] = acc;
-                    pNew[i] = pv;
-                    part = (double)(pv * acc);
+                    part += (double)(cb[0] * acc);
                 }
-                double tot = block_sum(part, red);
-                if (tid == 0) sAcc[d] += tot;
-                __syncthreads();
+            }
+            if (curD >= 0) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+                if (lane == 0) atomicAdd(&sAcc[curD], part);
             }
             __syncthreads();
             if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&dPAp[tid], sAcc[tid]);
         }
         grid.sync();
         // both accumulators of the NEXT iteration are zeroed here: every block has passed this
-        // iteration's first sync, hence finished reading them after the previous iteration's syncs
+        // iteration's syncs, hence finished reading them after the previous iteration's syncs
         if (blockIdx.x == 0 && tid < 32) P.dots[nxt * 32 + tid] = 0.0;
+        if (tid <= D) sAcc[tid] = 0.0;
         if (tid >= 1 && tid <= D && sActive[tid]) sAlpha[tid] = (float)((double)sR1[tid] / dPAp[tid]);
         __syncthreads();
         // ---------------- phase B: x += alpha p ; r -= alpha Ap ; r.r
         {
-            __shared__ double sAcc[kMaxDepth + 1];
-            if (tid <= D) sAcc[tid] = 0.0;
-            __syncthreads();
-            for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
-                int d = 1;
-                while (!(sActive[d] && tile >= sTileStart[d] && tile < sTileStart[d + 1])) d++;
-                const int g0 = P.gbase[d] + (tile - sTileStart[d]) * kGroupsPerTile;
-                const int ng = min(kGroupsPerTile, P.gbase[d + 1] - g0);
-                const float al = sAlpha[d];
-                double part = 0.0;
-                if (tid < ng * 8) {
-                    int i = 1 + 8 * g0 + tid;
-                    float pv = pNew[i], av = P.Ap[i];
-                    P.x[i] = __fmaf_rn(al, pv, P.x[i]);
-                    float rv = __fmaf_rn(-al, av, P.r[i]);
-                    P.r[i] = rv;
-                    part = (double)(rv * rv);
-                }
-                double tot = block_sum(part, red);
-                if (tid == 0) sAcc[d] += tot;
-                __syncthreads();
+            double part = 0.0;
+            int curD = -1;
+            const int nQuads = 2 * sGrpStart[D + 1];
+            int d = 0, lo = 0, hi = 0, gb = 0;
+            float al = 0.f;
+            for (int q = blockIdx.x * kCgBlock + tid; q < nQuads; q += gridDim.x * kCgBlock) {
+                int ag = q >> 1;
+                while (ag >= hi) { d++; lo = sGrpStart[d]; hi = sGrpStart[d + 1]; gb = P.gbase[d]; al = sAlpha[d]; }
+                if (d != curD) { if (curD >= 0) atomicAdd(&sAcc[curD], part); part = 0.0; curD = d; }
+                int i = 1 + 8 * (gb + ag - lo) + 4 * (q & 1);
+                float4 pv = *reinterpret_cast<const float4*>(P.p + i);
+                float4 av = *reinterpret_cast<const float4*>(P.Ap + i);
+                float4 xv = *reinterpret_cast<const float4*>(P.x + i);
+                float4 rv = *reinterpret_cast<const float4*>(P.r + i);
+                xv.x = __fmaf_rn(al, pv.x, xv.x); xv.y = __fmaf_rn(al, pv.y, xv.y); xv.z = __fmaf_rn(al, pv.z, xv.z); xv.w = __fmaf_rn(al, pv.w, xv.w);
+                rv.x = __fmaf_rn(-al, av.x, rv.x); rv.y = __fmaf_rn(-al, av.y, rv.y); rv.z = __fmaf_rn(-al, av.z, rv.z); rv.w = __fmaf_rn(-al, av.w, rv.w);
+                *reinterpret_cast<float4*>(P.x + i) = xv;
+                *reinterpret_cast<float4*>(P.r + i) = rv;
+                part += (double)(rv.x * rv.x);
+                part += (double)(rv.y * rv.y);
+                part += (double)(rv.z * rv.z);
+                part += (double)(rv.w * rv.w);
+            }
+            {
+                // one shared-memory atomic per warp when the whole warp ended in the same depth
+                int d0 = __shfl_sync(0xffffffffu, curD, 0);
+                if (__all_sync(0xffffffffu, curD == d0)) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+                    if (lane == 0 && d0 >= 0) atomicAdd(&sAcc[d0], part);
+                } else if (curD >= 0) atomicAdd(&sAcc[curD], part);
             }
             __syncthreads();
             if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&dRRn[tid], sAcc[tid]);
@@ -230,7 +297,7 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
         grid.sync();
         if (tid >= 1 && tid <= D && sActive[tid]) {
             float r0 = sR1[tid], r1 = (float)dRRn[tid];
-            sR0[tid] = r0; sR1[tid] = r1;
+            sR1[tid] = r1;
             int k = sIter[tid] + 1;
             sIter[tid] = k;
             sBeta[tid] = r1 / r0;
@@ -241,17 +308,31 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
     if (blockIdx.x == 0 && tid >= 1 && tid <= D) { P.itersOut[tid] = sIter[tid] - 1; P.resOut[tid] = sR1[tid]; }
 }
 
+static bool g_cubeReady = false;
+
 int stage_solve(Context& c) {
     const int D = c.D, M = c.M;
     cudaStream_t st = c.stream;
-    PRB_TRY(c.x.alloc((size_t)M, st));
-    DBuf<float> r, p0, p1, Ap, resOut;
+    if (!g_cubeReady) {
+        unsigned short h[54];
+        for (int t = 0; t < 54; t++) {
+            int blk = t >> 1, half = t & 1;
+            int bx = blk / 9, by = (blk / 3) % 3, bz = blk % 3;
+            h[t] = (unsigned short)((2 * bx + half) * 36 + (2 * by) * 6 + 2 * bz);
+        }
+        PRB_CUDA(cudaMemcpyToSymbol(cCubeOff, h, sizeof(h)));
+        g_cubeReady = true;
+    }
+    // vectors are padded by 7 floats so that node 1 (the first sibling block) is 32-byte aligned
+    const size_t padN = (size_t)M + 8;
+    PRB_TRY(c.x.alloc(padN, st));
+    c.xv = c.x.p + 7;
+    DBuf<float> r, p, Ap, resOut;
     DBuf<double> dots;
     DBuf<int> itersOut;
-    PRB_TRY(r.alloc((size_t)M, st));
-    PRB_TRY(p0.alloc((size_t)M, st));
-    PRB_TRY(p1.alloc((size_t)M, st));
-    PRB_TRY(Ap.alloc((size_t)M, st));
+    PRB_TRY(r.alloc(padN, st));
+    PRB_TRY(p.alloc(padN, st));
+    PRB_TRY(Ap.alloc(padN, st));
     PRB_TRY(dots.alloc(96, st));
     PRB_TRY(itersOut.alloc(16, st));
     PRB_TRY(resOut.alloc(16, st));
@@ -261,7 +342,8 @@ int stage_solve(Context& c) {
     P.D = D;
     for (int d = 1; d <= D + 1; d++) P.gbase[d] = (c.base[d] - 1) / 8;
     P.gbase[0] = 0;
-    P.nbBase = c.nbBase.p; P.stencil = c.dStencil.p; P.b = c.divg.p; P.x = c.x.p; P.r = r.p; P.p0 = p0.p; P.p1 = p1.p; P.Ap = Ap.p;
+    P.nbBase = c.nbBase.p; P.stencil = c.dStencil.p; P.b = c.divg.p;
+    P.x = c.xv; P.r = r.p + 7; P.p = p.p + 7; P.Ap = Ap.p + 7;
     P.dots = dots.p; P.itersOut = itersOut.p; P.resOut = resOut.p;
     float tol = (float)c.cgTol;
     P.tol2 = tol * tol;
@@ -270,9 +352,10 @@ int stage_solve(Context& c) {
     PRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_cg_all_depths, kCgBlock, 0));
     if (perSM < 1) { set_error("CG kernel does not fit on an SM"); return PRB_ERR_CUDA; }
     int gridSize = c.smCount * perSM;
-    int maxTiles = 0;
-    for (int d = 1; d <= D; d++) maxTiles += (P.gbase[d + 1] - P.gbase[d] + kGroupsPerTile - 1) / kGroupsPerTile;
-    if (gridSize > maxTiles) gridSize = ((maxTiles + c.smCount - 1) / c.smCount) * c.smCount;   // small problems: fewer CTAs, cheaper grid syncs
+    i64 maxTiles = 0;
+    for (int d = 1; d <= D; d++) maxTiles += (P.gbase[d + 1] - P.gbase[d] + kGroupsPerWarp - 1) / kGroupsPerWarp;
+    i64 needBlocks = (maxTiles + kCgWarps - 1) / kCgWarps;
+    if (gridSize > needBlocks) gridSize = (int)(((needBlocks + c.smCount - 1) / c.smCount) * c.smCount);   // small problems: fewer CTAs, cheaper grid syncs
     if (gridSize > c.smCount * perSM) gridSize = c.smCount * perSM;
     if (gridSize < 1) gridSize = 1;
     void* args[] = {(void*)&P};
@@ -283,7 +366,7 @@ int stage_solve(Context& c) {
     PRB_CUDA(cudaStreamSynchronize(st));
     c.cgRowIters = 0;
     for (int d = 0; d <= D; d++) { c.cgIters[d] = hIters[d]; c.cgRowIters += (i64)c.cnt[d] * hIters[d]; }
-    r.release(); p0.release(); p1.release(); Ap.release(); dots.release(); itersOut.release(); resOut.release();
+    r.release(); p.release(); Ap.release(); dots.release(); itersOut.release(); resOut.release();
     return PRB_OK;
 }
 
