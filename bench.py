@@ -1,0 +1,341 @@
+#!/usr/bin/env python3
+"""Headline benchmark: M points/s end to end (octree + solve + marching cubes) at depth 10.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+A *step* is one complete reconstruction (prb_set_points + prb_run: octree, splat, divergence,
+CG solve, iso value, marching cubes + refinement passes) of one synthetic oriented point cloud:
+BASELINE.json configs[2], the non-uniform scan, 5 M points, maxDepth 10 (the configuration the
+metric is quoted on; it fits one B200).  `value` is measured with the samples already resident
+in HBM (device pointers into prb_set_points), `e2e` with pinned HOST buffers in and the mesh
+copied back to the host, both through the C ABI (include/prb.h) and both timed with CUDA events
+on the library's own stream.  N > 1: one process per GPU, every rank reconstructs its own
+cloud (same generator, different seed) -- weak scaling, no data-path collective
+(DESIGN.md "multi-GPU").  The CG kernel's roofline line uses the algorithmic 57.5 B per row
+per iteration of SURVEY.md 8(d) and the CUDA-event duration of the solve stage.
+
+`--impl reference`: the reference has no CPU path and its CUDA build stops at depth 9
+(SURVEY.md fact 3), so this arm times the CPU oracle port (oracle/) on a bounded sample of the
+workload with all host threads, as the tier contract asks.  The reference's own CUDA binary
+(oracle/_ref/ref_poisson_d8, harness-patched build of /root/reference) is timed on its own
+runnable config next to ours and reported under "reference_cuda" when it is present.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+B_ITER = 57.5     # algorithmic bytes per row per CG iteration
+CPU_SAMPLE = dict(n=100_000, depth=8)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.path = tempfile.mktemp(prefix="prb_clocks_", suffix=".csv")
+        self.proc = None
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.device)],
+                                         stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm), reasons=sorted(reasons))
+        return out
+
+
+def make_cloud(workload, rank):
+    from poissonrecon_gpu_b200 import synth
+    c = synth.CONFIGS[workload]
+    if rank == 0:
+        p, n = c["gen"](c["n"])
+    else:
+        p, n = c["gen"](c["n"], seed=100 + rank)
+    return p, n, c["depth"]
+
+
+def cpu_oracle_rate(workload, steps=1):
+    """CPU oracle (port of the reference pipeline) on a bounded sample; returns (Mpts/s, seconds, cores, sample text)."""
+    from poissonrecon_gpu_b200 import synth
+    from tests.oracle_binding import Oracle
+    gen = synth.CONFIGS[workload]["gen"]
+    p, n = gen(CPU_SAMPLE["n"])
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    times = []
+    for _ in range(steps):
+        o = Oracle()
+        t0 = time.perf_counter()
+        o.run(p, n, CPU_SAMPLE["depth"], 4)
+        times.append(time.perf_counter() - t0)
+        del o
+    sec = statistics.median(times)
+    sample = (f"{synth.CONFIGS[workload]['gen'].__name__} generator, {CPU_SAMPLE['n']} points, depth {CPU_SAMPLE['depth']}, full pipeline "
+              f"(oracle/poisson_oracle.cpp, OpenMP in its data-parallel loops); the full {workload} job is hours on the CPU port")
+    return CPU_SAMPLE["n"] / sec / 1e6, sec, cores, sample
+
+
+def run_reference_arm(a, rank, world):
+    if rank != 0:
+        return
+    t_all = time.perf_counter()
+    rates = []
+    for _ in range(max(0, a.warmup > 0)):     # one warm-up pass is enough for a CPU code
+        cpu_oracle_rate(a.workload, 1)
+    secs = []
+    for _ in range(a.steps):
+        r, s, cores, sample = cpu_oracle_rate(a.workload, 1)
+        rates.append(r); secs.append(s)
+    v = statistics.median(rates)
+    from poissonrecon_gpu_b200 import synth
+    line = {"impl": "reference", "metric": "M points/s end-to-end (octree+solve+MC)", "value": v, "unit": "Mpoints/s", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * statistics.median(secs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": a.workload, "points": synth.CONFIGS[a.workload]["n"], "depth": synth.CONFIGS[a.workload]["depth"],
+                       "note": "reference has no CPU path and its CUDA build is limited to depth<=9: CPU oracle port on a bounded sample"},
+            "cpu_baseline": {"value": v, "unit": "Mpoints/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t_all}
+    print(json.dumps(line), flush=True)
+
+
+def reference_cuda_context(device):
+    """Times the reference's own CUDA build (harness-patched, sm_100) on config 1 next to ours."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_poisson_d8")
+    if not os.path.exists(exe):
+        return None
+    from poissonrecon_gpu_b200 import PoissonRecon, plyio, synth
+    p, n, D = synth.make("sphere100k_d8")
+    with tempfile.TemporaryDirectory() as td:
+        inp, out = os.path.join(td, "in.ply"), os.path.join(td, "out.ply")
+        plyio.write_points_ply(inp, p, n)
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(device))
+        walls = []
+        txt = ""
+        for _ in range(2):
+            t0 = time.perf_counter()
+            r = subprocess.run([exe, inp, out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=300)
+            walls.append(time.perf_counter() - t0)
+            txt = r.stdout
+            if r.returncode != 0:
+                return {"config": "sphere100k_d8", "error": f"reference binary exited {r.returncode}"}
+    import re
+    tot = re.search(r"The whole project takes ([0-9.]+)s", txt)
+    rd = re.search(r"Read takes:([0-9.]+)s", txt)
+    wr = re.search(r"Output ply files takes ([0-9.]+)s", txt)
+    ref_total = float(tot.group(1)) if tot else min(walls)
+    ref_compute = ref_total - (float(rd.group(1)) if rd else 0) - (float(wr.group(1)) if wr else 0)
+    pr = PoissonRecon(D, device=0)
+    ours = []
+    for _ in range(4):
+        t0 = time.perf_counter()
+        pr.set_points(p, n); pr.run(); pr.mesh()
+        ours.append(time.perf_counter() - t0)
+    pr.close()
+    o = statistics.median(ours[1:])
+    return {"config": "sphere100k_d8 (BASELINE configs[0]; the reference's depth cap is 9)", "ref_total_s_incl_io": ref_total, "ref_compute_s": ref_compute,
+            "ref_mpoints_s": p.shape[0] / ref_compute / 1e6, "ours_compute_s_host_in_mesh_out": o, "ours_mpoints_s": p.shape[0] / o / 1e6,
+            "speedup": ref_compute / o, "how": "oracle/_ref/ref_poisson_d8 = unmodified reference kernels, argv/depth harness patch, nvcc -arch=sm_100; wall of the same process minus its own read/write timers"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="scan5m_d10")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference_arm(a, rank, world)
+        return
+    if a.warmup < 3:
+        a.warmup = 3     # timing rule: at least 3 warm-up steps
+
+    import torch
+    import torch.distributed as dist
+    from poissonrecon_gpu_b200 import PoissonRecon
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    p, n, D = make_cloud(a.workload, rank)
+    N = p.shape[0]
+    hp, hn = torch.from_numpy(p).pin_memory(), torch.from_numpy(n).pin_memory()
+    dp, dn = hp.cuda(), hn.cuda()
+    pr = PoissonRecon(D, device=local)
+    stream = torch.cuda.ExternalStream(pr.stream(), device=local)
+
+    def step_resident():
+        pr.set_points(dp.data_ptr(), dn.data_ptr(), N)
+        pr.run()
+
+    def step_e2e():
+        pr.set_points(hp.data_ptr(), hn.data_ptr(), N)      # pinned host -> device inside the step
+        pr.run()
+        return pr.mesh_host_view()                           # device -> host read of the result
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(a.warmup):
+        step_resident()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    stage_ms = {}
+    launches = 0
+    cg_ms, cg_row_iters = [], []
+
+    def step_resident_recorded():
+        nonlocal launches
+        step_resident()
+        st = pr.stats()
+        launches += st["kernel_launches"]
+        cg_ms.append(st["ms_solve"]); cg_row_iters.append(st["cg_row_iters"])
+        for k, v in st.items():
+            if k.startswith("ms_"):
+                stage_ms.setdefault(k, []).append(v)
+
+    ms_total = timed(step_resident_recorded, a.steps)
+    st = pr.stats()
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, a.steps)
+    nv, nt = pr.mesh_device_size()
+    clk = clocks.stop() if rank == 0 else None
+
+    units = N * world
+    value = units * a.steps / (ms_total * 1e-3) / 1e6
+    e2e = units * a.steps / (ms_e2e * 1e-3) / 1e6
+    peak, peak_src = measured_peaks()
+    cg_t = statistics.mean(cg_ms)
+    achieved = B_ITER * statistics.mean(cg_row_iters) / (cg_t * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "cg_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(a.workload)
+        except Exception:
+            traffic = None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": "M points/s end-to-end (octree+solve+MC) at depth 10; CG SpMV HBM GB/s vs peak",
+        "value": value, "unit": "Mpoints/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": a.workload, "points_per_gpu": N, "depth": D, "nodes": st["n_nodes"], "mesh_vertices": nv, "mesh_triangles": nt,
+                   "cg_iters": st["cg_iters"][: D + 1], "parallelism": f"replicas x{world} (one cloud per GPU, no collective)" if world > 1 else "1 GPU",
+                   "l2": "no flush: every step streams > 3 GB of samples, node slabs and vectors, far beyond the 126 MB L2"},
+        "e2e": {"value": e2e, "unit": "Mpoints/s", "h2d_bytes_per_step": 24 * N, "d2h_bytes_per_step": 12 * (nv + nt), "ms_per_step": ms_e2e / a.steps,
+                "api": "prb_set_points(pinned host) + prb_run + prb_get_mesh (C ABI, include/prb.h)"},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "k_cg_all_depths (matrix-free 27-point stencil CG, all depths in one persistent launch)", "bound": "hbm",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "algorithmic_bytes_per_row_iteration": B_ITER, "row_iterations_per_launch": statistics.mean(cg_row_iters),
+                     "launch_ms": cg_t},
+        "stages_ms": {k: statistics.mean(v) for k, v in stage_ms.items()},
+        "clocks": clk,
+    }
+    if not a.no_cpu_baseline and world == 1:
+        r, s, cores, sample = cpu_oracle_rate(a.workload, 1)
+        line["cpu_baseline"] = {"value": r, "unit": "Mpoints/s", "cores": cores, "kind": "port", "sample": sample, "seconds": s}
+    if not a.no_reference_cuda and world == 1:
+        try:
+            rc = reference_cuda_context(local)
+        except Exception as e:  # the comparator must never take the bench line down
+            rc = {"error": repr(e)}
+        if rc:
+            line["reference_cuda"] = rc
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

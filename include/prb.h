@@ -88,6 +88,10 @@ int prb_get_mesh_device(prb_context* ctx, const float** d_vertices, int64_t* nv,
 
 int prb_get_stats(prb_context* ctx, prb_stats* out);
 
+/* The context's internal CUDA stream (a cudaStream_t), so that a caller can order its own work
+ * or record its own events around the stages (bench.py times steps with events on it). */
+int prb_get_stream(prb_context* ctx, void** stream);
+
 /* Parity / debug getters: copies a named intermediate array to host memory `dst` (if non-null
  * and cap_bytes is large enough) and returns its size in bytes, or a negative error.  Names:
  *   points normals sorted_idx sorted_key base count key pidx pnum parent didx dnum children
@@ -104,6 +108,14 @@ int prb_run_stage(prb_context* ctx, const char* name);
 /* Options: "cg_tol" (default 1e-5, CG_CUDA.cuh:347), "cg_max_iter" (10000, CG_CUDA.cuh:263),
  * "refine" (1 = run the refinement passes, main.cu:3799-4564). */
 int prb_set_option(prb_context* ctx, const char* key, double value);
+
+/* Host-side B-spline precompute (replaces FunctionData<2,double>::set / setDotTables,
+ * FunctionData.inl:112-215, and the table uploads of main.cu:3308-3359).  Needs no GPU: copies
+ * the named table for `depth` to `dst` and returns its size in bytes.  Names: gauss (4x4 f32),
+ * max_depth_fn (4x4 f32), base_fn (res x 4 x 5 f32), df_table (f32), df_offset (i32, depth+2),
+ * stencil ((depth+1) x 27 f32), ff0 ff1 d20 d21 (f64 per depth: same-depth 1-D <F,F> and
+ * <F',F'> at centre distance 0 and 1). */
+int64_t prb_host_tables(int depth, const char* name, void* dst, int64_t cap_bytes);
 
 #ifdef __cplusplus
 }

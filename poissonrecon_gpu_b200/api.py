@@ -74,13 +74,16 @@ def load_library():
     lib.prb_set_array.argtypes = [vp, ctypes.c_char_p, vp, cll]
     lib.prb_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_double]
     lib.prb_run_stage.argtypes = [vp, ctypes.c_char_p]
+    lib.prb_get_stream.argtypes = [vp, ctypes.POINTER(vp)]
+    lib.prb_host_tables.argtypes = [ci, ctypes.c_char_p, vp, cll]
+    lib.prb_host_tables.restype = cll
     _lib = lib
     return lib
 
 
 EXPORTS = ["prb_create", "prb_destroy", "prb_last_error", "prb_set_points", "prb_build_octree", "prb_splat", "prb_solve",
            "prb_extract", "prb_run", "prb_get_mesh", "prb_get_mesh_device", "prb_get_stats", "prb_get_array", "prb_set_array",
-           "prb_set_option", "prb_run_stage"]
+           "prb_set_option", "prb_run_stage", "prb_get_stream", "prb_host_tables"]
 
 
 class PoissonRecon:
@@ -140,6 +143,12 @@ class PoissonRecon:
     def set_option(self, key: str, value: float):
         self._check(self.lib.prb_set_option(self.h, key.encode(), float(value)))
 
+    def stream(self) -> int:
+        """The context's cudaStream_t as an integer (wrap with torch.cuda.ExternalStream)."""
+        p = ctypes.c_void_p()
+        self._check(self.lib.prb_get_stream(self.h, ctypes.byref(p)))
+        return int(p.value or 0)
+
     def stats(self) -> dict:
         s = PrbStats()
         self._check(self.lib.prb_get_stats(self.h, ctypes.byref(s)))
@@ -152,6 +161,16 @@ class PoissonRecon:
         self._check(self.lib.prb_get_mesh(self.h, ctypes.byref(pv), ctypes.byref(nv), ctypes.byref(pt), ctypes.byref(nt)))
         v = np.ctypeslib.as_array(ctypes.cast(pv, ctypes.POINTER(ctypes.c_float)), (nv.value, 3)).copy() if nv.value else np.zeros((0, 3), np.float32)
         t = np.ctypeslib.as_array(ctypes.cast(pt, ctypes.POINTER(ctypes.c_int32)), (nt.value, 3)).copy() if nt.value else np.zeros((0, 3), np.int32)
+        return v, t
+
+    def mesh_host_view(self):
+        """Like mesh() but returns views of the context's pinned host buffers (valid until the next
+        prb_set_points / prb_extract): the device -> host copy without a second host copy."""
+        pv, pt = ctypes.c_void_p(), ctypes.c_void_p()
+        nv, nt = ctypes.c_int64(), ctypes.c_int64()
+        self._check(self.lib.prb_get_mesh(self.h, ctypes.byref(pv), ctypes.byref(nv), ctypes.byref(pt), ctypes.byref(nt)))
+        v = np.ctypeslib.as_array(ctypes.cast(pv, ctypes.POINTER(ctypes.c_float)), (nv.value, 3)) if nv.value else np.zeros((0, 3), np.float32)
+        t = np.ctypeslib.as_array(ctypes.cast(pt, ctypes.POINTER(ctypes.c_int32)), (nt.value, 3)) if nt.value else np.zeros((0, 3), np.int32)
         return v, t
 
     def mesh_device_size(self):

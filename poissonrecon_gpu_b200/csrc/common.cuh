@@ -55,6 +55,28 @@ struct DBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
+// Growable pinned host buffer (D2H target of the mesh: pageable memory would halve PCIe throughput).
+template <class T>
+struct HBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t count) {
+        if (count <= cap) return PRB_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = count + count / 4 + 1024;
+        PRB_CUDA(cudaMallocHost((void**)&p, want * sizeof(T)));
+        cap = want;
+        return PRB_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
 // One pass (the main depth-D pass or a refinement pass) of mesh output.
 struct PassRecord { int kind, nv, nt; };   // kind: 0 main, 1 coarse (single root), 2 batched per depth
 
@@ -101,8 +123,8 @@ struct Context {
     DBuf<float> meshV;             // device
     DBuf<int> meshT;
     i64 nMeshV = 0, nMeshT = 0;
-    std::vector<float> hMeshV;
-    std::vector<int> hMeshT;
+    HBuf<float> hMeshV;            // pinned host copies (prb_get_mesh)
+    HBuf<int> hMeshT;
     bool hMeshValid = false;
     std::vector<PassRecord> passes;
     std::vector<int> subdivide;    // host copy of the refined leaves (node ids)

@@ -89,6 +89,7 @@ void prb_destroy(prb_context* h) {
     release_all(c);
     c.dMaxDepthFn.release(); c.dBaseFn.release(); c.dDfT.release(); c.dDfOffset.release(); c.dStencil.release();
     cudaStreamSynchronize(c.stream);
+    c.hMeshV.release(); c.hMeshT.release();
     for (auto& e : c.ev) cudaEventDestroy(e);
     cudaStreamDestroy(c.stream);
     delete h;
@@ -208,17 +209,23 @@ int prb_get_mesh(prb_context* h, const float** v, int64_t* nv, const int32_t** t
     if (c.stage < 5) { set_error("prb_get_mesh: extract not done"); return PRB_ERR_STATE; }
     PRB_CUDA(cudaSetDevice(c.device));
     if (!c.hMeshValid) {
-        c.hMeshV.resize(3 * (size_t)c.nMeshV);
-        c.hMeshT.resize(3 * (size_t)c.nMeshT);
-        if (c.nMeshV) PRB_CUDA(cudaMemcpyAsync(c.hMeshV.data(), c.meshV.p, 12 * (size_t)c.nMeshV, cudaMemcpyDeviceToHost, c.stream));
-        if (c.nMeshT) PRB_CUDA(cudaMemcpyAsync(c.hMeshT.data(), c.meshT.p, 12 * (size_t)c.nMeshT, cudaMemcpyDeviceToHost, c.stream));
+        PRB_TRY(c.hMeshV.reserve(3 * (size_t)c.nMeshV + 1));
+        PRB_TRY(c.hMeshT.reserve(3 * (size_t)c.nMeshT + 1));
+        if (c.nMeshV) PRB_CUDA(cudaMemcpyAsync(c.hMeshV.p, c.meshV.p, 12 * (size_t)c.nMeshV, cudaMemcpyDeviceToHost, c.stream));
+        if (c.nMeshT) PRB_CUDA(cudaMemcpyAsync(c.hMeshT.p, c.meshT.p, 12 * (size_t)c.nMeshT, cudaMemcpyDeviceToHost, c.stream));
         PRB_CUDA(cudaStreamSynchronize(c.stream));
         c.hMeshValid = true;
     }
-    if (v) *v = c.hMeshV.data();
+    if (v) *v = c.hMeshV.p;
     if (nv) *nv = c.nMeshV;
-    if (t) *t = c.hMeshT.data();
+    if (t) *t = c.hMeshT.p;
     if (nt) *nt = c.nMeshT;
+    return PRB_OK;
+}
+
+int prb_get_stream(prb_context* h, void** stream) {
+    if (!h || !stream) { set_error("prb_get_stream: null argument"); return PRB_ERR_ARG; }
+    *stream = (void*)h->c.stream;
     return PRB_OK;
 }
 
@@ -306,6 +313,28 @@ int64_t prb_get_array(prb_context* h, const char* name, void* dst, int64_t cap) 
         else std::memcpy(dst, host.data(), (size_t)bytes);
     }
     return bytes;
+}
+
+int64_t prb_host_tables(int depth, const char* name, void* dst, int64_t cap) {
+    if (!name || depth < 0 || depth > kMaxDepth) { set_error("prb_host_tables: bad argument"); return PRB_ERR_ARG; }
+    BSplineTables t;
+    build_bspline_tables(depth, t);
+    std::string s(name);
+    const void* src = nullptr;
+    size_t bytes = 0;
+    if (s == "gauss") { src = t.gauss; bytes = sizeof(t.gauss); }
+    else if (s == "max_depth_fn") { src = t.maxDepthFn; bytes = sizeof(t.maxDepthFn); }
+    else if (s == "base_fn") { src = t.baseFn.data(); bytes = t.baseFn.size() * 4; }
+    else if (s == "df_table") { src = t.dfT.data(); bytes = t.dfT.size() * 4; }
+    else if (s == "df_offset") { src = t.dfOffset.data(); bytes = t.dfOffset.size() * 4; }
+    else if (s == "stencil") { src = t.stencil.data(); bytes = t.stencil.size() * 4; }
+    else if (s == "ff0") { src = t.ff0.data(); bytes = t.ff0.size() * 8; }
+    else if (s == "ff1") { src = t.ff1.data(); bytes = t.ff1.size() * 8; }
+    else if (s == "d20") { src = t.d20.data(); bytes = t.d20.size() * 8; }
+    else if (s == "d21") { src = t.d21.data(); bytes = t.d21.size() * 8; }
+    else { set_error("unknown table " + s); return PRB_ERR_ARG; }
+    if (dst && cap >= (int64_t)bytes && bytes) std::memcpy(dst, src, bytes);
+    return (int64_t)bytes;
 }
 
 int prb_set_array(prb_context* h, const char* name, const void* src, int64_t bytes) {
