@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 B_ITER = 57.5     # algorithmic bytes per row per CG iteration
-CPU_SAMPLE = dict(n=100_000, depth=8)
+CPU_SAMPLE = dict(n=400_000, depth=8)
 
 
 def measured_peaks():
