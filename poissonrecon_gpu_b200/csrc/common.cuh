@@ -89,7 +89,9 @@ struct Context {
     double cgTol = 1e-5;
     int cgMaxIter = 10000;
     int doRefine = 1;
+    int refineImplicit = 1;        // 0: materialised virtual subtrees for every pass (debug / cross-check)
     int smCount = kSMs;
+    size_t deviceMemBytes = 0;
     // ---- samples
     i64 N = 0;
     DBuf<float> rawP, rawN;        // file coordinates, [N][3]

@@ -13,6 +13,7 @@
 // triangles by cell then case-table order), so meshes compare index by index.
 #include "common.cuh"
 #include "mc_case_table.h"
+#include "scan.cuh"
 
 namespace prb {
 
@@ -488,6 +489,375 @@ __global__ void __launch_bounds__(256) k_offset_triangles(int* __restrict__ t, i
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) t[i] += off;
 }
 
+// ================================================================== refinement, implicit form
+// Passes whose roots lie at least 3 levels above D (n = 2^(D-rd) >= 8 cells per side, up to
+// 8^(D-rd) cells per root) never materialise the virtual subtree: a virtual depth-D cell is
+// (root r, local Morton code l), its neighbours, the owners of its corners and edges and the
+// real nodes next to it all follow from arithmetic on (r, l) plus one 27-entry table per ROOT.
+// Values: the corner (+,+,+) of a cell is always owned by that cell (it is the lowest of the 8
+// incident cells in Morton = id order), so one float per cell (val7) holds every grid value
+// except those on the lower faces of a root without a virtual neighbour there (kept in `low`).
+// A block evaluates one 8x8x8 brick: the real nodes next to the brick's ancestors are found once
+// per brick by descending the real tree, the per-axis base-function values once per
+// coordinate, and every cell then sums its levels D..0 in the reference's order
+// (main.cu:2328-2442) from shared memory.
+struct RGeom {
+    int M, D, rd, lv, n, nr;
+    unsigned per;                 // n^3
+    const int* roots;             // [nr] real node ids of the pass, ascending
+    const int* rootNb;            // [nr][27] depth-rd neighbours: real id, M + r' (virtual root r') or -1
+    const float* rootX;           // [nr][rd+1][27] solution at the 27 neighbours of the root (level rd) and of its ancestors (0 = absent)
+    const ushort4* offs;
+    const int* child0;
+    const float* x;
+    const float* baseFn;
+    float iso;
+    float* val7;                  // [nr * per]
+    float* low;                   // [nr][3][(n+1)^2]
+};
+
+__device__ __forceinline__ unsigned spread3(unsigned v) {   // bit s -> bit 3s (10 bits)
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__device__ __forceinline__ unsigned compact3(unsigned v) {  // bit 3s -> bit s
+    v &= 0x09249249u;
+    v = (v ^ (v >> 2)) & 0x030C30C3u;
+    v = (v ^ (v >> 4)) & 0x0300F00Fu;
+    v = (v ^ (v >> 8)) & 0x030000FFu;
+    v = (v ^ (v >> 16)) & 0x000003FFu;
+    return v;
+}
+// local Morton code of a cell: octal digit per level, digit = x<<2|y<<1|z (child code)
+__device__ __forceinline__ unsigned rv_morton(int x, int y, int z) { return (spread3((unsigned)x) << 2) | (spread3((unsigned)y) << 1) | spread3((unsigned)z); }
+
+__global__ void __launch_bounds__(256) k_rv_roots(int nr, int rd, int M, const int* __restrict__ roots, const int* __restrict__ rootMap,
+                                                  const int* __restrict__ neighs, const int* __restrict__ parent, const float* __restrict__ x,
+                                                  int* __restrict__ rootNb, float* __restrict__ rootX) {
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= nr || lane >= 27) return;
+    int root = roots[w];
+    int q = neighs[27 * (i64)root + lane];
+    int nb = -1;
+    float xv = 0.f;
+    if (q >= 0) { int vm = rootMap[q]; nb = vm >= 0 ? M + vm : q; xv = x[q]; }   // a virtual root stands for the real leaf it replaces
+    rootNb[27 * w + lane] = nb;
+    float* X = rootX + (i64)w * (rd + 1) * 27;
+    X[rd * 27 + lane] = xv;
+    int now = parent[root];
+    for (int l = rd - 1; l >= 0; --l) {
+        int q2 = neighs[27 * (i64)now + lane];
+        X[l * 27 + lane] = q2 >= 0 ? x[q2] : 0.f;
+        now = parent[now];
+    }
+}
+
+#define RV_ACC27(val, X, vx, vy, vz)                                                                                      \
+    _Pragma("unroll") for (int j_ = 0; j_ < 27; j_++)                                                                     \
+        val = __fmaf_rn(__fmul_rn(__fmul_rn((X)[j_], (vx)[j_ / 9]), (vy)[(j_ / 3) % 3]), (vz)[j_ % 3], val)
+
+__global__ void __launch_bounds__(512) k_rv_brick_values(RGeom G) {
+    __shared__ float sX[kMaxDepth + 1][27];
+    __shared__ float sBv[3][kMaxDepth + 1][3][8];
+    __shared__ int sIds[27];
+    __shared__ int sAny[kMaxDepth + 1];
+    __shared__ int sNeedFine;
+    const int tid = threadIdx.x;
+    const i64 cell0 = (i64)blockIdx.x * 512;
+    const int r = (int)(cell0 / G.per);
+    const unsigned l0 = (unsigned)(cell0 - (i64)r * G.per);
+    const int L = G.D - 3;                                   // level of the brick
+    const ushort4 ro = G.offs[G.roots[r]];
+    const int bx = ((int)ro.x << G.lv) + (int)compact3(l0 >> 2), by = ((int)ro.y << G.lv) + (int)compact3(l0 >> 1), bz = ((int)ro.z << G.lv) + (int)compact3(l0);
+    const float w = 1.0f / (float)(1 << G.D);
+    for (int t = tid; t < (G.rd + 1) * 27; t += 512) sX[t / 27][t % 27] = G.rootX[(i64)r * (G.rd + 1) * 27 + t];
+    if (tid <= G.rd) sAny[tid] = 1;   // levels rd+1..L are written by the descending warp below
+    if (tid >= 32 && tid < 64) {
+        // one warp descends the REAL tree along the brick's path, levels rd+1 .. L: the 27
+        // neighbours of the brick's ancestor at every level (virtual ones carry no solution)
+        const int lane = tid - 32;
+        int cur = -1;
+        if (lane < 27) { int q = G.rootNb[27 * r + lane]; cur = (q >= 0 && q < G.M) ? q : -1; }
+        for (int d = G.rd + 1; d <= L; d++) {
+            int c = (int)((l0 >> (3 * (G.D - d))) & 7u), pj = 0, cc = 0;
+            if (lane < 27) lut_parent_child(c, lane, pj, cc);
+            int p = __shfl_sync(0xffffffffu, cur, pj);
+            int nxt = -1;
+            if (lane < 27 && p >= 0) { int c0 = G.child0[p]; if (c0 >= 0) nxt = c0 + cc; }
+            unsigned any = __ballot_sync(0xffffffffu, nxt >= 0);
+            if (lane < 27) sX[d][lane] = nxt >= 0 ? G.x[nxt] : 0.f;
+            if (lane == 0) sAny[d] = any != 0u;
+            cur = nxt;
+        }
+        bool kids = lane < 27 && cur >= 0 && G.child0[cur] >= 0;
+        unsigned anyKids = __ballot_sync(0xffffffffu, kids);
+        if (lane < 27) sIds[lane] = kids ? cur : -1;
+        if (lane == 0) sNeedFine = anyKids != 0u;
+    }
+    for (int t = tid; t < 3 * (G.D + 1) * 24; t += 512) {
+        int ci = t & 7, k = (t >> 3) % 3, l = (t / 24) % (G.D + 1), a = t / (24 * (G.D + 1));
+        int gc = (a == 0 ? bx : (a == 1 ? by : bz)) + ci;
+        float pos = (float)(gc + 1) * w;
+        int nn = 1 << l, ao = (gc >> (G.D - l)) + k - 1;
+        sBv[a][l][k][ci] = (ao >= 0 && ao < nn) ? base_value(G.baseFn, nn - 1 + ao, pos) : 0.f;
+    }
+    __syncthreads();
+    const unsigned l = l0 + (unsigned)tid;
+    const int cx = (int)compact3((unsigned)tid >> 2), cy = (int)compact3((unsigned)tid >> 1), cz = (int)compact3((unsigned)tid);
+    float val = 0.f;
+    if (sNeedFine) {
+        int ids[3][27];
+#pragma unroll 1
+        for (int s = 0; s < 3; s++) {
+            int c = (int)((l >> (3 * (2 - s))) & 7u);
+#pragma unroll 1
+            for (int j = 0; j < 27; j++) {
+                int pj, cc;
+                lut_parent_child(c, j, pj, cc);
+                int p = s == 0 ? sIds[pj] : ids[s - 1][pj];
+                int nxt = -1;
+                if (p >= 0) { int c0 = G.child0[p]; if (c0 >= 0) nxt = c0 + cc; }
+                ids[s][j] = nxt;
+            }
+        }
+#pragma unroll 1
+        for (int s = 2; s >= 0; --s) {
+            int lvl = L + 1 + s;
+            float vx[3], vy[3], vz[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) { vx[k] = sBv[0][lvl][k][cx]; vy[k] = sBv[1][lvl][k][cy]; vz[k] = sBv[2][lvl][k][cz]; }
+#pragma unroll 1
+            for (int j = 0; j < 27; j++) {
+                int q = ids[s][j];
+                if (q >= 0) val = __fmaf_rn(__fmul_rn(__fmul_rn(G.x[q], vx[j / 9]), vy[(j / 3) % 3]), vz[j % 3], val);
+            }
+        }
+    }
+    for (int lvl = L; lvl >= 0; --lvl) {
+        if (!sAny[lvl]) continue;
+        float vx[3], vy[3], vz[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { vx[k] = sBv[0][lvl][k][cx]; vy[k] = sBv[1][lvl][k][cy]; vz[k] = sBv[2][lvl][k][cz]; }
+        RV_ACC27(val, sX[lvl], vx, vy, vz);
+    }
+    G.val7[cell0 + tid] = __fsub_rn(val, G.iso);
+}
+
+// virtual cell at root-local coordinates (x,y,z), each in [-1, n]: which root of the pass holds
+// it (false: the cell is not virtual), coordinates wrapped into that root
+__device__ __forceinline__ bool rv_locate(const RGeom& G, int r, int& x, int& y, int& z, int& r2) {
+    int dx = x < 0 ? -1 : (x >= G.n ? 1 : 0), dy = y < 0 ? -1 : (y >= G.n ? 1 : 0), dz = z < 0 ? -1 : (z >= G.n ? 1 : 0);
+    if ((dx | dy | dz) == 0) { r2 = r; return true; }
+    int q = G.rootNb[27 * r + 9 * (dx + 1) + 3 * (dy + 1) + (dz + 1)];
+    if (q < G.M) return false;
+    r2 = q - G.M;
+    x -= dx * G.n; y -= dy * G.n; z -= dz * G.n;
+    return true;
+}
+// owner of the grid point g (root-local, each in [0,n]) of root r: the incident virtual cell with
+// the smallest id = (root, Morton) (main.cu:1474-1484 "min key"); jb = corner bits of g in that cell
+__device__ __forceinline__ void rv_point_owner(const RGeom& G, int r, int gx, int gy, int gz, int& r2, int& ox, int& oy, int& oz, int& jb) {
+    unsigned long long best = ~0ull;
+    r2 = -1;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        int x = gx - 1 + (q & 1), y = gy - 1 + ((q >> 1) & 1), z = gz - 1 + ((q >> 2) & 1), rr;
+        if (!rv_locate(G, r, x, y, z, rr)) continue;
+        unsigned long long key = ((unsigned long long)rr << 32) | rv_morton(x, y, z);
+        if (key < best) { best = key; r2 = rr; ox = x; oy = y; oz = z; jb = 7 ^ q; }
+    }
+}
+__device__ __forceinline__ i64 rv_low_index(const RGeom& G, int r, int gx, int gy, int gz) {
+    int a = gx == 0 ? 0 : (gy == 0 ? 1 : 2);
+    int u = a == 0 ? gy : gx, v = a == 2 ? gy : gz;
+    const int n1 = G.n + 1;
+    return ((i64)r * 3 + a) * n1 * n1 + (i64)u * n1 + v;
+}
+// value at grid point g of root r
+__device__ __forceinline__ float rv_point_value(const RGeom& G, int r, int gx, int gy, int gz) {
+    if (gx >= 1 && gy >= 1 && gz >= 1) return G.val7[(i64)r * G.per + rv_morton(gx - 1, gy - 1, gz - 1)];
+    int r2, ox, oy, oz, jb;
+    rv_point_owner(G, r, gx, gy, gz, r2, ox, oy, oz, jb);
+    if (jb == 7) return G.val7[(i64)r2 * G.per + rv_morton(ox, oy, oz)];
+    return G.low[rv_low_index(G, r2, ox + (jb & 1), oy + ((jb >> 1) & 1), oz + ((jb >> 2) & 1))];
+}
+// corner jb of virtual cell (r, c) evaluated by one thread (lower faces of the pass region only)
+__device__ float rv_eval_slow(const RGeom& G, int r, int cx, int cy, int cz, int jb) {
+    const ushort4 ro = G.offs[G.roots[r]];
+    const int g[3] = {((int)ro.x << G.lv) + cx, ((int)ro.y << G.lv) + cy, ((int)ro.z << G.lv) + cz};
+    const float w = 1.0f / (float)(1 << G.D);
+    const float pos[3] = {(float)(g[0] + (jb & 1)) * w, (float)(g[1] + ((jb >> 1) & 1)) * w, (float)(g[2] + ((jb >> 2) & 1)) * w};
+    const unsigned l = rv_morton(cx, cy, cz);
+    int ids[kMaxDepth][27];
+    int deepest = G.rd;
+    {
+        int cur[27];
+        for (int j = 0; j < 27; j++) { int q = G.rootNb[27 * r + j]; cur[j] = (q >= 0 && q < G.M) ? q : -1; }
+        for (int d = G.rd + 1; d <= G.D; d++) {
+            int c = (int)((l >> (3 * (G.D - d))) & 7u);
+            bool any = false;
+            for (int j = 0; j < 27; j++) {
+                int pj, cc;
+                lut_parent_child(c, j, pj, cc);
+                int p = cur[pj], nxt = -1;
+                if (p >= 0) { int c0 = G.child0[p]; if (c0 >= 0) nxt = c0 + cc; }
+                ids[d - G.rd - 1][j] = nxt;
+                any |= nxt >= 0;
+            }
+            if (!any) break;
+            deepest = d;
+            for (int j = 0; j < 27; j++) cur[j] = ids[d - G.rd - 1][j];
+        }
+    }
+    float val = 0.f;
+    for (int d = deepest; d >= 0; --d) {
+        const int nn = 1 << d;
+        float v[3][3];
+        for (int a = 0; a < 3; a++)
+            for (int k = 0; k < 3; k++) {
+                int ao = (g[a] >> (G.D - d)) + k - 1;
+                v[a][k] = (ao >= 0 && ao < nn) ? base_value(G.baseFn, nn - 1 + ao, pos[a]) : 0.f;
+            }
+        if (d > G.rd) {
+            for (int j = 0; j < 27; j++) {
+                int q = ids[d - G.rd - 1][j];
+                if (q >= 0) val = __fmaf_rn(__fmul_rn(__fmul_rn(G.x[q], v[0][j / 9]), v[1][(j / 3) % 3]), v[2][j % 3], val);
+            }
+        } else {
+            const float* X = G.rootX + ((i64)r * (G.rd + 1) + d) * 27;
+            for (int j = 0; j < 27; j++) val = __fmaf_rn(__fmul_rn(__fmul_rn(X[j], v[0][j / 9]), v[1][(j / 3) % 3]), v[2][j % 3], val);
+        }
+    }
+    return __fsub_rn(val, G.iso);
+}
+// grid points on the lower faces of every root: evaluated here when this root owns them
+__global__ void __launch_bounds__(128) k_rv_low_values(RGeom G) {
+    const int n1 = G.n + 1;
+    const i64 total = (i64)G.nr * 3 * n1 * n1;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        int v = (int)(t % n1), u = (int)((t / n1) % n1), a = (int)((t / ((i64)n1 * n1)) % 3), r = (int)(t / ((i64)3 * n1 * n1));
+        int gx = a == 0 ? 0 : u, gy = a == 0 ? u : (a == 1 ? 0 : v), gz = a == 2 ? 0 : v;
+        if ((a >= 1 && gx == 0) || (a == 2 && gy == 0)) continue;   // stored under the lowest zero axis
+        int r2, ox, oy, oz, jb;
+        rv_point_owner(G, r, gx, gy, gz, r2, ox, oy, oz, jb);
+        if (r2 != r || jb == 7) continue;
+        G.low[t] = rv_eval_slow(G, r, ox, oy, oz, jb);
+    }
+}
+// owner of edge e of cell (r, c): (flat owner cell index, edge kind in the owner's frame)
+__device__ __forceinline__ i64 rv_edge_owner(const RGeom& G, int r, int cx, int cy, int cz, int e, int& e2) {
+    const int o = e >> 2;
+    int a0, a1;
+    other_axes(o, a0, a1);
+    const int s0 = (e & 1) ? 1 : -1, s1 = (e & 2) ? 1 : -1;
+    int c[3] = {cx, cy, cz};
+    int bm;
+    i64 owner;
+    if ((s0 > 0 || c[a0] >= 1) && (s1 > 0 || c[a1] >= 1)) {
+        bm = (s0 < 0 ? 1 : 0) | (s1 < 0 ? 2 : 0);
+        if (s0 < 0) c[a0] -= 1;
+        if (s1 < 0) c[a1] -= 1;
+        owner = (i64)r * G.per + rv_morton(c[0], c[1], c[2]);
+    } else {
+        unsigned long long best = ~0ull;
+        bm = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            int d[3] = {cx, cy, cz}, rr;
+            if (q & 1) d[a0] += s0;
+            if (q & 2) d[a1] += s1;
+            if (!rv_locate(G, r, d[0], d[1], d[2], rr)) continue;
+            unsigned long long key = ((unsigned long long)rr << 32) | rv_morton(d[0], d[1], d[2]);
+            if (key < best) { best = key; bm = q; }
+        }
+        owner = (i64)(best >> 32) * G.per + (unsigned)(best & 0xffffffffu);
+    }
+    e2 = (o << 2) | ((e & 1) ^ (bm & 1)) | ((((e >> 1) & 1) ^ ((bm >> 1) & 1)) << 1);
+    return owner;
+}
+__device__ __forceinline__ void rv_cell_values(const RGeom& G, int r, int cx, int cy, int cz, float v[8]) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        int j = ring_to_bits(q);
+        v[q] = rv_point_value(G, r, cx + (j & 1), cy + ((j >> 1) & 1), cz + ((j >> 2) & 1));
+    }
+}
+__global__ void __launch_bounds__(256) k_rv_classify(RGeom G, unsigned char* __restrict__ cat, unsigned char* __restrict__ ntri, unsigned short* __restrict__ emask) {
+    const i64 total = (i64)G.nr * G.per;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        const int r = (int)(t / G.per);
+        const unsigned l = (unsigned)(t - (i64)r * G.per);
+        const int cx = (int)compact3(l >> 2), cy = (int)compact3(l >> 1), cz = (int)compact3(l);
+        float v[8];
+        rv_cell_values(G, r, cx, cy, cz, v);
+        int c = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) if (v[q] < 0.f) c |= 1 << q;
+        unsigned m = 0;
+#pragma unroll
+        for (int e = 0; e < 12; e++) {
+            if (__fmul_rn(v[cEdgeVertex[e][0]], v[cEdgeVertex[e][1]]) <= 0.f) {
+                int e2;
+                if (rv_edge_owner(G, r, cx, cy, cz, e, e2) == t) m |= 1u << e;
+            }
+        }
+        cat[t] = (unsigned char)c;
+        ntri[t] = cMcCount[c];
+        emask[t] = (unsigned short)m;
+    }
+}
+__global__ void __launch_bounds__(256) k_rv_emit_vertices(RGeom G, const unsigned short* __restrict__ emask, const int* __restrict__ vbase, float* __restrict__ outV) {
+    const float w = 1.0f / (float)(1 << G.D);
+    const i64 total = (i64)G.nr * G.per;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        unsigned m = emask[t];
+        if (!m) continue;
+        const int r = (int)(t / G.per);
+        const unsigned l = (unsigned)(t - (i64)r * G.per);
+        const int cx = (int)compact3(l >> 2), cy = (int)compact3(l >> 1), cz = (int)compact3(l);
+        float v[8];
+        rv_cell_values(G, r, cx, cy, cz, v);
+        const ushort4 ro = G.offs[G.roots[r]];
+        const int ox = ((int)ro.x << G.lv) + cx, oy = ((int)ro.y << G.lv) + cy, oz = ((int)ro.z << G.lv) + cz;
+        int k = 0;
+        for (int e = 0; e < 12; e++) {
+            if (!(m & (1u << e))) continue;
+            int r1 = cEdgeVertex[e][0], r2 = cEdgeVertex[e][1], dim = e >> 2;
+            int b1 = ring_to_bits(r1), b2 = ring_to_bits(r2);
+            float p1[3] = {(float)(ox + (b1 & 1)) * w, (float)(oy + ((b1 >> 1) & 1)) * w, (float)(oz + ((b1 >> 2) & 1)) * w};
+            float p2d = (float)((dim == 0 ? ox + (b2 & 1) : (dim == 1 ? oy + ((b2 >> 1) & 1) : oz + ((b2 >> 2) & 1)))) * w;
+            float f1 = v[r1], f2 = v[r2];
+            float pivot = __fdiv_rn(f1, __fsub_rn(f1, f2));
+            float another = __fsub_rn(1.0f, pivot);
+            float out[3] = {p1[0], p1[1], p1[2]};
+            out[dim] = __fmaf_rn(p2d, pivot, __fmul_rn(p1[dim], another));
+            i64 a = 3 * (i64)(vbase[t] + k);
+            outV[a] = out[0]; outV[a + 1] = out[1]; outV[a + 2] = out[2];
+            k++;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_rv_emit_triangles(RGeom G, const unsigned char* __restrict__ cat, const unsigned char* __restrict__ ntri, const int* __restrict__ tbase,
+                                                           const unsigned short* __restrict__ emask, const int* __restrict__ vbase, int* __restrict__ outT) {
+    const i64 total = (i64)G.nr * G.per;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        int nt = ntri[t];
+        if (!nt) continue;
+        const int r = (int)(t / G.per);
+        const unsigned l = (unsigned)(t - (i64)r * G.per);
+        const int cx = (int)compact3(l >> 2), cy = (int)compact3(l >> 1), cz = (int)compact3(l);
+        const int c = cat[t];
+        for (int j = 0; j < 3 * nt; j++) {
+            int e = cMcTri[c][j], e2;
+            i64 ow = rv_edge_owner(G, r, cx, cy, cz, e, e2);
+            outT[3 * (i64)tbase[t] + j] = vbase[ow] + __popc((unsigned)emask[ow] & ((1u << e2) - 1u));
+        }
+    }
+}
+
 struct PassOut {
     DBuf<float> v;
     DBuf<int> t;
@@ -523,6 +893,59 @@ static int run_mc_on_cells(Context& c, const Topo& T, const float* vals, int val
     return PRB_OK;
 }
 
+// refinement pass over roots at depth rd <= D-3 (implicit virtual subtrees, see RGeom)
+static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, bool single, DBuf<int>& rootMap, std::vector<PassOut>& outs) {
+    cudaStream_t st = c.stream;
+    const int D = c.D, lv = D - rd;
+    if (lv > 10) { set_error("refinement pass too large (root more than 10 levels above maxDepth)"); return PRB_ERR_NOMEM; }
+    const int n = 1 << lv, n1 = n + 1;
+    const unsigned per = 1u << (3 * lv);
+    const i64 total = (i64)nr * per;
+    if ((double)total * 20.0 > (double)c.deviceMemBytes * 0.8) { set_error("refinement pass too large for device memory"); return PRB_ERR_NOMEM; }
+    DBuf<int> rootNb, vbase, tbase;
+    DBuf<float> rootX, val7, low;
+    DBuf<unsigned char> cat, ntri;
+    DBuf<unsigned short> emask;
+    PRB_TRY(rootNb.alloc(27 * (size_t)nr, st));
+    PRB_TRY(rootX.alloc((size_t)nr * (rd + 1) * 27, st));
+    PRB_TRY(val7.alloc((size_t)total, st));
+    PRB_TRY(low.alloc((size_t)nr * 3 * n1 * n1, st));
+    PRB_LAUNCH(c, k_set_rootmap, grid_for(c, nr, 256), 256, 0, dRoots, nr, 0, 0, rootMap.p);
+    PRB_LAUNCH(c, k_rv_roots, div_up((i64)nr * 32, 256), 256, 0, nr, rd, c.M, dRoots, rootMap.p, c.neighs.p, c.parent.p, c.xv, rootNb.p, rootX.p);
+    PRB_LAUNCH(c, k_set_rootmap, grid_for(c, nr, 256), 256, 0, dRoots, nr, 0, -1, rootMap.p);
+    RGeom G;
+    G.M = c.M; G.D = D; G.rd = rd; G.lv = lv; G.n = n; G.nr = nr; G.per = per;
+    G.roots = dRoots; G.rootNb = rootNb.p; G.rootX = rootX.p; G.offs = c.offs.p; G.child0 = c.child0.p; G.x = c.xv; G.baseFn = c.dBaseFn.p;
+    G.iso = c.iso; G.val7 = val7.p; G.low = low.p;
+    PRB_LAUNCH(c, k_rv_brick_values, (unsigned)(total / 512), 512, 0, G);
+    PRB_LAUNCH(c, k_rv_low_values, grid_for(c, (i64)nr * 3 * n1 * n1, 128, 16), 128, 0, G);
+    PRB_TRY(cat.alloc((size_t)total, st));
+    PRB_TRY(ntri.alloc((size_t)total, st));
+    PRB_TRY(emask.alloc((size_t)total, st));
+    PRB_TRY(vbase.alloc((size_t)total, st));
+    PRB_TRY(tbase.alloc((size_t)total, st));
+    PRB_LAUNCH(c, k_rv_classify, grid_for(c, total, 256, 8), 256, 0, G, cat.p, ntri.p, emask.p);
+    i64 totV = 0, totT = 0;
+    PRB_TRY(exclusive_scan_op(c, ScanLoadPopc16{emask.p}, vbase.p, total, &totV));
+    PRB_TRY(exclusive_scan_op(c, ScanLoadU8{ntri.p}, tbase.p, total, &totT));
+    outs.emplace_back();
+    PassOut& po = outs.back();
+    po.nv = (int)totV;
+    po.nt = (int)totT;
+    PRB_TRY(po.v.alloc(3 * (size_t)totV, st));
+    PRB_TRY(po.t.alloc(3 * (size_t)totT, st));
+    if (totV) PRB_LAUNCH(c, k_rv_emit_vertices, grid_for(c, total, 256, 8), 256, 0, G, emask.p, vbase.p, po.v.p);
+    if (totT) PRB_LAUNCH(c, k_rv_emit_triangles, grid_for(c, total, 256, 8), 256, 0, G, cat.p, ntri.p, tbase.p, emask.p, vbase.p, po.t.p);
+    if (single && po.nv == 0) {      // main.cu:4095-4103: nothing is inserted for a coarse root without crossings
+        po.v.release(); po.t.release();
+        outs.pop_back();
+    } else {
+        c.passes.push_back({single ? 1 : 2, po.nv, po.nt});
+    }
+    rootNb.release(); rootX.release(); val7.release(); low.release(); cat.release(); ntri.release(); emask.release(); vbase.release(); tbase.release();
+    return PRB_OK;
+}
+
 static int refine_pass(Context& c, const int* dRoots, int nr, int rd, bool single, DBuf<int>& rootMap, std::vector<PassOut>& outs) {
     cudaStream_t st = c.stream;
     const int D = c.D, M = c.M;
@@ -530,6 +953,7 @@ static int refine_pass(Context& c, const int* dRoots, int nr, int rd, bool singl
         if (!single) { c.passes.push_back({2, 0, 0}); }
         return PRB_OK;
     }
+    if (D - rd >= 3 && c.refineImplicit) return refine_pass_implicit(c, dRoots, nr, rd, single, rootMap, outs);
     VTree V;
     V.M = M; V.D = D; V.rd = rd; V.nr = nr; V.roots = dRoots;
     i64 total = 0;

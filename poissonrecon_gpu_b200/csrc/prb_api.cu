@@ -69,6 +69,7 @@ int prb_create(int device, int depth, prb_context** out) {
     c.device = device;
     c.D = depth;
     c.smCount = prop.multiProcessorCount;
+    c.deviceMemBytes = prop.totalGlobalMem;
     PRB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     for (auto& e : c.ev) PRB_CUDA(cudaEventCreate(&e));
     cudaMemPool_t pool;
@@ -101,6 +102,7 @@ int prb_set_option(prb_context* h, const char* key, double value) {
     if (k == "cg_tol") h->c.cgTol = value;
     else if (k == "cg_max_iter") h->c.cgMaxIter = (int)value;
     else if (k == "refine") h->c.doRefine = (int)value;
+    else if (k == "refine_implicit") h->c.refineImplicit = (int)value;
     else { set_error("unknown option " + k); return PRB_ERR_ARG; }
     return PRB_OK;
 }

@@ -241,6 +241,14 @@ def test_full_size_properties(config):
     pr.run()
     v2, t2 = pr.mesh()
     assert np.array_equal(t, t2) and np.array_equal(v, v2)
+    # the implicit (arithmetic-topology) refinement passes equal the materialised virtual subtrees
+    pr.set_option("refine_implicit", 0)
+    pr.set_points(p, n)
+    pr.run()
+    v3, t3 = pr.mesh()
+    assert pr.get("passes", "<i4").tolist() == pr.get("passes", "<i4").tolist()
+    assert np.array_equal(t, t3) and np.array_equal(v, v3)
+    pr.set_option("refine_implicit", 1)
     # the reconstructed surface interpolates the samples: vertices lie near the sampled shape
     c, s = np.array(st["center"], np.float32), np.float32(st["scale"])
     w = v * s + c
