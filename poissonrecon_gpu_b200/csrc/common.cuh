@@ -51,6 +51,21 @@ struct DBuf {
         if (p) cudaFreeAsync(p, s);
         p = nullptr;
         n = 0;
+        cap = 0;
+    }
+    // grow-only reuse (workspace buffers kept by the context between passes and runs: repeated
+    // multi-hundred-MB alloc/free cycles of varying sizes fragment the stream-ordered pool and
+    // occasionally stall a run on fresh device allocations)
+    size_t cap = 0;
+    int ensure(size_t count, cudaStream_t st) {
+        if (p && count <= cap) { n = count; return PRB_OK; }
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+        s = st;
+        cap = count + count / 8 + 256;
+        n = count;
+        PRB_CUDA(cudaMallocAsync((void**)&p, cap * sizeof(T), st));
+        return PRB_OK;
     }
     size_t bytes() const { return n * sizeof(T); }
 };
@@ -108,7 +123,8 @@ struct Context {
     DBuf<int> parent, child0, pidx, pnum, didx, dnum;
     DBuf<int> neighs;              // [M][27]
     DBuf<ushort4> offs;            // per node (ox, oy, oz, depth)
-    DBuf<int> nbBase;              // [M/8 groups][27] child-block bases for the sibling-block SpMV (group 0 = root pad)
+    DBuf<int> sgTab;               // [nSg][64] super-group table of the stencil SpMV (octree.cu k_sg_table)
+    int nSg = 0;
     // ---- tables
     BSplineTables tab;
     DBuf<float> dMaxDepthFn, dBaseFn, dDfT, dStencil;
@@ -131,6 +147,11 @@ struct Context {
     std::vector<PassRecord> passes;
     std::vector<int> subdivide;    // host copy of the refined leaves (node ids)
     DBuf<float> vval;              // [M][8] corner values (valid at the owner's slot)
+    // grow-only workspace of the refinement passes (kept across runs)
+    DBuf<float> wsVal7, wsLow;
+    DBuf<unsigned char> wsCat, wsNtri;
+    DBuf<unsigned short> wsEmask;
+    DBuf<int> wsVbase, wsTbase;
     prb_stats stats;
 };
 

@@ -96,6 +96,10 @@ __device__ __forceinline__ void accumulate_level(float& val, const int* __restri
     }
 }
 
+#define RV_ACC27(val, X, vx, vy, vz)                                                                                      \
+    _Pragma("unroll") for (int j_ = 0; j_ < 27; j_++)                                                                     \
+        val = __fmaf_rn(__fmul_rn(__fmul_rn((X)[j_], (vx)[j_ / 9]), (vy)[(j_ / 3) % 3]), (vz)[j_ % 3], val)
+
 // ------------------------------------------------------------------ A11 iso value
 __global__ void __launch_bounds__(128) k_point_values(const float* __restrict__ P, const int* __restrict__ p2n, i64 N, int baseD,
                                                       const int* __restrict__ neighs, const int* __restrict__ parent, const ushort4* __restrict__ offs,
@@ -225,6 +229,79 @@ __global__ void __launch_bounds__(128) k_vertex_values(Topo T, int M, int D, con
                 accumulate_level(val, T.nbr + 27 * (i64)now, offs[now], x, baseFn, pos);
             }
             vval[8 * (i64)i + j] = __fsub_rn(val, iso);
+        }
+    }
+}
+
+// Same values, one WARP per sibling group: the 8 siblings share every ancestor, so the 27
+// neighbour values and the per-axis base-function values of the ancestor levels are fetched once
+// per group into shared memory and reused by all the corners the group owns (the 27 points of
+// the 3x3x3 corner grid of the group, one lane each; a point is evaluated by the group that holds
+// its owner cell).  Each lane still adds its terms in the reference's order: own level, parents
+// up to the root, then the finer nodes at that corner (main.cu:2277-2322).
+constexpr int kVvWarps = 8;
+__global__ void __launch_bounds__(kVvWarps * 32) k_vertex_values_grouped(Topo T, int nGroups, int D, const int* __restrict__ parent, const int* __restrict__ child0,
+                                                                         const ushort4* __restrict__ offs, const float* __restrict__ x,
+                                                                         const float* __restrict__ baseFn, float iso, float* __restrict__ vval) {
+    __shared__ float sX[kVvWarps][27];
+    __shared__ float sB[kVvWarps][3][3][3];      // [axis][point coordinate 0..2][k]
+    const int exceedTab[8] = {0, 1, 3, 2, 4, 5, 7, 6};     // childrenVertexKind, MarchingCubes.cuh:721-723 (applied as the reference does)
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    for (int g = blockIdx.x * kVvWarps + wp; g < nGroups; g += gridDim.x * kVvWarps) {
+        const int gb = 1 + 8 * g;                // first sibling (root vertices are dropped, main.cu:1634-1638)
+        const ushort4 o0 = offs[gb];
+        const int d0 = o0.w;
+        const float w = 1.0f / (float)(1 << d0);
+        // lane -> point (px,py,pz) of the group's corner grid
+        const int px = lane / 9, py = (lane / 3) % 3, pz = lane % 3;
+        bool mine = false;
+        int owner = -1, jo = 0;
+        if (lane < 27) {
+            const int sx = (px + 1) >> 1, sy = (py + 1) >> 1, sz = (pz + 1) >> 1;
+            const int id = gb + ((sx << 2) | (sy << 1) | sz);
+            const int j = (px - sx) | ((py - sy) << 1) | ((pz - sz) << 2);
+            int m;
+            owner = corner_owner(T, id, j, m);
+            mine = owner >= gb && owner < gb + 8;
+            jo = j ^ m;
+        }
+        const float pos[3] = {(float)((int)o0.x + px) * w, (float)((int)o0.y + py) * w, (float)((int)o0.z + pz) * w};
+        float val = 0.f;
+        if (mine) accumulate_level(val, T.nbr + 27 * (i64)owner, offs[owner], x, baseFn, pos);
+        // shared ancestor levels d0-1 .. 0
+        int anc = parent[gb];
+        for (int l = d0 - 1; l >= 0; --l) {
+            const ushort4 oa = offs[anc];
+            __syncwarp();
+            if (lane < 27) {
+                int q = T.nbr[27 * (i64)anc + lane];
+                sX[wp][lane] = q >= 0 ? x[q] : 0.f;
+                // lane -> (axis a, point coordinate pc, k)
+                const int a = lane / 9, pc = (lane / 3) % 3, k = lane % 3;
+                const int nn = 1 << l, ao = (a == 0 ? (int)oa.x : (a == 1 ? (int)oa.y : (int)oa.z)) + k - 1;
+                const float pp = (float)((a == 0 ? (int)o0.x : (a == 1 ? (int)o0.y : (int)o0.z)) + pc) * w;
+                sB[wp][a][pc][k] = (ao >= 0 && ao < nn) ? base_value(baseFn, nn - 1 + ao, pp) : 0.f;
+            }
+            __syncwarp();
+            if (mine) {
+                float vx[3], vy[3], vz[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) { vx[k] = sB[wp][0][px][k]; vy[k] = sB[wp][1][py][k]; vz[k] = sB[wp][2][pz][k]; }
+                RV_ACC27(val, sX[wp], vx, vy, vz);
+            }
+            anc = parent[anc];
+        }
+        if (mine) {
+            int now = owner, depth = d0;
+            const int ex = exceedTab[jo];
+            while (depth < D) {
+                ++depth;
+                int c0 = child0[now];
+                if (c0 < 0) break;
+                now = c0 + ex;
+                accumulate_level(val, T.nbr + 27 * (i64)now, offs[now], x, baseFn, pos);
+            }
+            vval[8 * (i64)owner + jo] = __fsub_rn(val, iso);
         }
     }
 }
@@ -555,9 +632,6 @@ __global__ void __launch_bounds__(256) k_rv_roots(int nr, int rd, int M, const i
     }
 }
 
-#define RV_ACC27(val, X, vx, vy, vz)                                                                                      \
-    _Pragma("unroll") for (int j_ = 0; j_ < 27; j_++)                                                                     \
-        val = __fmaf_rn(__fmul_rn(__fmul_rn((X)[j_], (vx)[j_ / 9]), (vy)[(j_ / 3) % 3]), (vz)[j_ % 3], val)
 
 __global__ void __launch_bounds__(512) k_rv_brick_values(RGeom G) {
     __shared__ float sX[kMaxDepth + 1][27];
@@ -809,6 +883,49 @@ __global__ void __launch_bounds__(256) k_rv_classify(RGeom G, unsigned char* __r
         emask[t] = (unsigned short)m;
     }
 }
+// brick form of the classification: the 9x9x9 grid values of a brick are staged in shared memory
+// (own corner-7 values + the 217 points of its three lower faces), every cell then reads its 8
+// corners from there
+__global__ void __launch_bounds__(512) k_rv_classify_brick(RGeom G, unsigned char* __restrict__ cat, unsigned char* __restrict__ ntri, unsigned short* __restrict__ emask) {
+    __shared__ float sV[9 * 9 * 9];
+    const int tid = threadIdx.x;
+    const i64 cell0 = (i64)blockIdx.x * 512;
+    const int r = (int)(cell0 / G.per);
+    const unsigned l0 = (unsigned)(cell0 - (i64)r * G.per);
+    const int bx = (int)compact3(l0 >> 2), by = (int)compact3(l0 >> 1), bz = (int)compact3(l0);   // root-local origin of the brick
+    const int cx = (int)compact3((unsigned)tid >> 2), cy = (int)compact3((unsigned)tid >> 1), cz = (int)compact3((unsigned)tid);
+    sV[(cx + 1) * 81 + (cy + 1) * 9 + (cz + 1)] = G.val7[cell0 + tid];
+    if (tid < 217) {
+        // points with a zero brick-local coordinate: 81 with x = 0, 72 with y = 0 (x >= 1), 64 with z = 0 (x, y >= 1)
+        int gx, gy, gz;
+        if (tid < 81) { gx = 0; gy = tid / 9; gz = tid % 9; }
+        else if (tid < 153) { int t = tid - 81; gx = 1 + t / 9; gy = 0; gz = t % 9; }
+        else { int t = tid - 153; gx = 1 + t / 8; gy = 1 + t % 8; gz = 0; }
+        sV[gx * 81 + gy * 9 + gz] = rv_point_value(G, r, bx + gx, by + gy, bz + gz);
+    }
+    __syncthreads();
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const int j = ring_to_bits(q);
+        v[q] = sV[(cx + (j & 1)) * 81 + (cy + ((j >> 1) & 1)) * 9 + (cz + ((j >> 2) & 1))];
+    }
+    int c = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) if (v[q] < 0.f) c |= 1 << q;
+    unsigned m = 0;
+    const i64 t = cell0 + tid;
+#pragma unroll
+    for (int e = 0; e < 12; e++) {
+        if (__fmul_rn(v[cEdgeVertex[e][0]], v[cEdgeVertex[e][1]]) <= 0.f) {
+            int e2;
+            if (rv_edge_owner(G, r, bx + cx, by + cy, bz + cz, e, e2) == t) m |= 1u << e;
+        }
+    }
+    cat[t] = (unsigned char)c;
+    ntri[t] = cMcCount[c];
+    emask[t] = (unsigned short)m;
+}
 __global__ void __launch_bounds__(256) k_rv_emit_vertices(RGeom G, const unsigned short* __restrict__ emask, const int* __restrict__ vbase, float* __restrict__ outV) {
     const float w = 1.0f / (float)(1 << G.D);
     const i64 total = (i64)G.nr * G.per;
@@ -902,14 +1019,16 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     const unsigned per = 1u << (3 * lv);
     const i64 total = (i64)nr * per;
     if ((double)total * 20.0 > (double)c.deviceMemBytes * 0.8) { set_error("refinement pass too large for device memory"); return PRB_ERR_NOMEM; }
-    DBuf<int> rootNb, vbase, tbase;
-    DBuf<float> rootX, val7, low;
-    DBuf<unsigned char> cat, ntri;
-    DBuf<unsigned short> emask;
+    DBuf<int> rootNb;
+    DBuf<float> rootX;
+    DBuf<int>&vbase = c.wsVbase, &tbase = c.wsTbase;
+    DBuf<float>&val7 = c.wsVal7, &low = c.wsLow;
+    DBuf<unsigned char>&cat = c.wsCat, &ntri = c.wsNtri;
+    DBuf<unsigned short>& emask = c.wsEmask;
     PRB_TRY(rootNb.alloc(27 * (size_t)nr, st));
     PRB_TRY(rootX.alloc((size_t)nr * (rd + 1) * 27, st));
-    PRB_TRY(val7.alloc((size_t)total, st));
-    PRB_TRY(low.alloc((size_t)nr * 3 * n1 * n1, st));
+    PRB_TRY(val7.ensure((size_t)total, st));
+    PRB_TRY(low.ensure((size_t)nr * 3 * n1 * n1, st));
     PRB_LAUNCH(c, k_set_rootmap, grid_for(c, nr, 256), 256, 0, dRoots, nr, 0, 0, rootMap.p);
     PRB_LAUNCH(c, k_rv_roots, div_up((i64)nr * 32, 256), 256, 0, nr, rd, c.M, dRoots, rootMap.p, c.neighs.p, c.parent.p, c.xv, rootNb.p, rootX.p);
     PRB_LAUNCH(c, k_set_rootmap, grid_for(c, nr, 256), 256, 0, dRoots, nr, 0, -1, rootMap.p);
@@ -919,12 +1038,12 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     G.iso = c.iso; G.val7 = val7.p; G.low = low.p;
     PRB_LAUNCH(c, k_rv_brick_values, (unsigned)(total / 512), 512, 0, G);
     PRB_LAUNCH(c, k_rv_low_values, grid_for(c, (i64)nr * 3 * n1 * n1, 128, 16), 128, 0, G);
-    PRB_TRY(cat.alloc((size_t)total, st));
-    PRB_TRY(ntri.alloc((size_t)total, st));
-    PRB_TRY(emask.alloc((size_t)total, st));
-    PRB_TRY(vbase.alloc((size_t)total, st));
-    PRB_TRY(tbase.alloc((size_t)total, st));
-    PRB_LAUNCH(c, k_rv_classify, grid_for(c, total, 256, 8), 256, 0, G, cat.p, ntri.p, emask.p);
+    PRB_TRY(cat.ensure((size_t)total, st));
+    PRB_TRY(ntri.ensure((size_t)total, st));
+    PRB_TRY(emask.ensure((size_t)total, st));
+    PRB_TRY(vbase.ensure((size_t)total, st));
+    PRB_TRY(tbase.ensure((size_t)total, st));
+    PRB_LAUNCH(c, k_rv_classify_brick, (unsigned)(total / 512), 512, 0, G, cat.p, ntri.p, emask.p);
     i64 totV = 0, totT = 0;
     PRB_TRY(exclusive_scan_op(c, ScanLoadPopc16{emask.p}, vbase.p, total, &totV));
     PRB_TRY(exclusive_scan_op(c, ScanLoadU8{ntri.p}, tbase.p, total, &totT));
@@ -942,7 +1061,7 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     } else {
         c.passes.push_back({single ? 1 : 2, po.nv, po.nt});
     }
-    rootNb.release(); rootX.release(); val7.release(); low.release(); cat.release(); ntri.release(); emask.release(); vbase.release(); tbase.release();
+    rootNb.release(); rootX.release();
     return PRB_OK;
 }
 
@@ -1003,7 +1122,12 @@ int stage_extract(Context& c) {
     Topo R;
     R.nbr = c.neighs.p; R.rowBase = 0; R.minId = 0; R.cellBase = c.base[D]; R.nCells = c.cnt[D];
     PRB_TRY(c.vval.alloc(8 * (size_t)M, st));
-    PRB_LAUNCH(c, k_vertex_values, grid_for(c, M, 128, 16), 128, 0, R, M, D, c.parent.p, c.child0.p, c.offs.p, c.xv, c.dBaseFn.p, c.iso, c.vval.p);
+    {
+        const int nGroups = (M - 1) / 8;
+        if (nGroups > 0)
+            PRB_LAUNCH(c, k_vertex_values_grouped, grid_for(c, (i64)nGroups * 32, kVvWarps * 32, 8), kVvWarps * 32, 0, R, nGroups, D, c.parent.p, c.child0.p, c.offs.p, c.xv,
+                       c.dBaseFn.p, c.iso, c.vval.p);
+    }
     DBuf<unsigned> fmark;
     PRB_TRY(fmark.alloc((size_t)M, st));
     PRB_CUDA(cudaMemsetAsync(fmark.p, 0, sizeof(unsigned) * (size_t)M, st));

@@ -208,14 +208,31 @@ __global__ void k_root_neighbours(int* __restrict__ neighs) {
     int j = threadIdx.x;
     if (j < 27) neighs[j] = (j == 13) ? 0 : -1;
 }
-// child-block bases per sibling group: group G covers nodes 1+8G .. 8+8G
-__global__ void __launch_bounds__(256) k_group_bases(const int* __restrict__ parent, const int* __restrict__ child0, const int* __restrict__ neighs,
-                                                     int nGroups, int* __restrict__ nbBase) {
-    i64 total = (i64)nGroups * 27;
+// Super-group table of the stencil SpMV (solver.cu).  Super-group 1+G' = the (up to 8) sibling
+// groups whose parents P_k are the 8 nodes of group G' (children of one node Q); entry u =
+// ux*16+uy*4+uz (each in 0..3) is the first child of the node at offset 2*off(Q) + u - 1 in the
+// P-level grid (-1: absent or childless), i.e. the 4x4x4 cube of 8-row blocks that holds every
+// neighbour of every row under Q.  The interior entries (u in {1,2}^3) are the row bases of the
+// super-group's own groups.  Super-group 0 is depth 1 (the root's children).
+__global__ void __launch_bounds__(256) k_sg_table(const int* __restrict__ parent, const int* __restrict__ child0, const int* __restrict__ neighs,
+                                                  int nSg, int* __restrict__ sgTab) {
+    i64 total = (i64)nSg * 64;
     for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
-        int G = (int)(t / 27), j = (int)(t - (i64)G * 27);
-        int np = neighs[27 * (i64)parent[1 + 8 * G] + j];
-        nbBase[t] = np >= 0 ? child0[np] : -1;
+        int sg = (int)(t >> 6), u = (int)(t & 63);
+        int ux = u >> 4, uy = (u >> 2) & 3, uz = u & 3;
+        int out = -1;
+        if (sg == 0) {
+            if (u == 21) out = child0[0];
+        } else {
+            int Q = parent[1 + 8 * (sg - 1)];
+            int j = 9 * ((ux + 1) >> 1) + 3 * ((uy + 1) >> 1) + ((uz + 1) >> 1);
+            int np = neighs[27 * (i64)Q + j];
+            if (np >= 0) {
+                int b = child0[np];
+                if (b >= 0) out = child0[b + ((((ux + 1) & 1) << 2) | (((uy + 1) & 1) << 1) | ((uz + 1) & 1))];
+            }
+        }
+        sgTab[t] = out;
     }
 }
 __global__ void __launch_bounds__(256) k_point_to_leaf(const int* __restrict__ flag, const int* __restrict__ excl, const int* __restrict__ slotD, i64 n, int* __restrict__ p2n) {
@@ -348,10 +365,10 @@ int stage_octree(Context& c) {
     PRB_LAUNCH(c, k_root_neighbours, 1, 32, 0, c.neighs.p);
     for (int d = 1; d <= D; d++)
         PRB_LAUNCH(c, k_neighbours, grid_for(c, (i64)c.cnt[d] * 27, 256), 256, 0, c.parent.p, c.child0.p, c.neighs.p, c.base[d], c.cnt[d]);
-    int nGroups = (M - 1) / 8;
-    PRB_TRY(c.nbBase.alloc(27 * (size_t)(nGroups > 0 ? nGroups : 1), st));
-    if (nGroups > 0)
-        PRB_LAUNCH(c, k_group_bases, grid_for(c, (i64)nGroups * 27, 256), 256, 0, c.parent.p, c.child0.p, c.neighs.p, nGroups, c.nbBase.p);
+    // super-groups: depth 1, then one per sibling group of depths 1..D-1
+    c.nSg = 1 + (c.base[D] - 1) / 8;
+    PRB_TRY(c.sgTab.alloc(64 * (size_t)c.nSg, st));
+    PRB_LAUNCH(c, k_sg_table, grid_for(c, (i64)c.nSg * 64, 256), 256, 0, c.parent.p, c.child0.p, c.neighs.p, c.nSg, c.sgTab.p);
     flagN.release(); exclN.release();
     for (int d = 0; d <= D; d++) { lkey[d].release(); fp[d].release(); fc[d].release(); fdm1[d].release(); prank[d].release(); slot[d].release(); }
     PRB_CUDA(cudaGetLastError());

@@ -12,7 +12,7 @@ void set_error(const std::string& msg) { g_lastError = msg; }
 static void release_all(Context& c) {
     c.rawP.release(); c.rawN.release(); c.P.release(); c.Nr.release(); c.sortedKey.release(); c.sortedIdx.release(); c.p2n.release();
     c.dBase.release(); c.key.release(); c.parent.release(); c.child0.release(); c.pidx.release(); c.pnum.release(); c.didx.release(); c.dnum.release();
-    c.neighs.release(); c.offs.release(); c.nbBase.release();
+    c.neighs.release(); c.offs.release(); c.sgTab.release();
     c.V.release(); c.divg.release(); c.x.release(); c.pointValue.release();
     c.meshV.release(); c.meshT.release(); c.vval.release();
     c.nMeshV = c.nMeshT = 0;
@@ -88,6 +88,7 @@ void prb_destroy(prb_context* h) {
     Context& c = h->c;
     cudaSetDevice(c.device);
     release_all(c);
+    c.wsVal7.release(); c.wsLow.release(); c.wsCat.release(); c.wsNtri.release(); c.wsEmask.release(); c.wsVbase.release(); c.wsTbase.release();
     c.dMaxDepthFn.release(); c.dBaseFn.release(); c.dDfT.release(); c.dDfOffset.release(); c.dStencil.release();
     cudaStreamSynchronize(c.stream);
     c.hMeshV.release(); c.hMeshT.release();
@@ -286,7 +287,7 @@ int64_t prb_get_array(prb_context* h, const char* name, void* dst, int64_t cap) 
     else if (s == "dnum") D_(c.dnum.p, c.dnum.bytes());
     else if (s == "child0") D_(c.child0.p, c.child0.bytes());
     else if (s == "neighs") D_(c.neighs.p, c.neighs.bytes());
-    else if (s == "nb_base") D_(c.nbBase.p, c.nbBase.bytes());
+    else if (s == "sg_table") D_(c.sgTab.p, c.sgTab.bytes());
     else if (s == "p2n") D_(c.p2n.p, c.p2n.bytes());
     else if (s == "vectorfield") D_(c.V.p, c.V.bytes());
     else if (s == "divergence") D_(c.divg.p, c.divg.bytes());

@@ -6,20 +6,24 @@
 // memory, 7 grid syncs per iteration and host loops over managed arrays around the launch.
 // Here:
 //   * the matrix is never formed: rows are the translation-invariant 27-point stencil
-//     (4 distinct values per depth) applied through the sibling-block table nbBase[group][27]
-//     (13.5 B/row instead of 216 B/row of CSR);
+//     (4 distinct values per depth) applied through the super-group table sgTab[sg][64]
+//     (octree.cu k_sg_table): the up to 64 rows under one node Q (8 sibling groups) and all
+//     their neighbours live in the 4x4x4 cube of 8-row blocks around Q's children
+//     (256 B of topology per <= 64 rows instead of 216 B per ROW of CSR);
 //   * the depths are independent, so they all iterate in lock-step inside one
 //     launch: one iteration of the kernel = one CG iteration of every still-active depth, with
 //     per-depth alpha / beta / residual and per-depth stopping.  Grid syncs per solve drop from
 //     7 * sum_d iters_d to 3 * max_d iters_d;
-//   * SpMV is warp-centric: a warp owns 4 sibling groups (32 rows), stages their 27 neighbour
-//     blocks with 128-bit loads (a sibling block of 8 floats is one aligned 32-byte sector) into
-//     a 6x6x6 shared-memory cube per group, and every row then reads its 3x3x3 window at
-//     compile-time offsets from one base address (bank-conflict free) -- no block barriers;
+//   * SpMV: a warp owns a super-group per step.  The 64 blocks (an 8x8x8 cube of p values, 2 KB)
+//     are copied global -> shared with 16-byte cp.async into a double buffer, one tile ahead of
+//     the compute, and the table two tiles ahead, so the gather latency is off the critical path;
+//     every lane then produces two rows (a z pair) from a 3x3x4 register window read with
+//     conflict-free LDS (padded block-major layout; the two half-warps walk z in opposite
+//     directions so that they always hit different banks);
 //   * the row sum runs over the neighbour slots in order j = 0..26 with FMAs, exactly the
 //     reference's CSR order (absent neighbours contribute an exact +0), so A*p is bit-identical;
 //     dots are float products accumulated in double (CG_CUDA.cuh:217-220); alpha, beta are float.
-// Algorithmic bytes per row per iteration (SURVEY.md §8d): 57.5 B
+// Algorithmic bytes per row per iteration (SURVEY.md 8d): 57.5 B
 //   (p=r+beta*p: 12, SpMV: 13.5 + 4 + 4, x/r update: 24).
 #include "common.cuh"
 #include <cooperative_groups.h>
@@ -29,12 +33,16 @@ namespace prb {
 
 constexpr int kCgBlock = 256;
 constexpr int kCgWarps = kCgBlock / 32;
-constexpr int kGroupsPerWarp = 4;                 // 32 rows per warp tile
+// shared cube of one super-group: block (bx,by,bz) at bx*kSX + by*kSY + bz*8 floats, 8 floats per
+// block in child-code order; the paddings make both the 16-byte staging stores and the
+// per-lane window loads bank-conflict free (see k_cg_all_depths)
+constexpr int kSX = 200, kSY = 48, kCube = 4 * kSX;
 
 struct CgParams {
     int D;
-    int gbase[kMaxDepth + 2];     // first group of depth d (groups cover nodes 1..M-1), gbase[D+1] = total
-    const int* nbBase;
+    int gbase[kMaxDepth + 2];     // first sibling group of depth d (groups cover nodes 1..M-1), gbase[D+1] = total
+    int sgStart[kMaxDepth + 2];   // first super-group of depth d (d = 1..D), sgStart[D+1] = total
+    const int* sgTab;
     const float* stencil;          // [D+1][27]
     const float* b;                // divergence
     // vectors indexed by node id; node 1 sits on a 32-byte boundary (pointer = allocation + 7)
@@ -49,20 +57,31 @@ struct CgParams {
     int maxIter;
 };
 
-// (blk, half) -> offset inside the 6x6x6 cube of the first of the 4 floats of that half block
-__constant__ unsigned short cCubeOff[54];
+__device__ __forceinline__ void cp_async16(unsigned smemAddr, const void* gptr, int srcBytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smemAddr), "l"(gptr), "r"(srcBytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// warp-level: sum `part` over the warp and add it to the block accumulator of depth d
+__device__ __forceinline__ void warp_add(double part, double* sAcc, int d, int lane) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+    if (lane == 0 && part != 0.0) atomicAdd(&sAcc[d], part);
+}
+
+extern __shared__ __align__(16) float sDyn[];   // [kCgWarps][2][kCube]
 
 __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ __align__(16) float sCube[kCgWarps][kGroupsPerWarp][216];
     __shared__ float sSt[kMaxDepth + 1][4];
     __shared__ double sAcc[kMaxDepth + 1];
     __shared__ float sR1[kMaxDepth + 1], sAlpha[kMaxDepth + 1], sBeta[kMaxDepth + 1];
     __shared__ int sActive[kMaxDepth + 1], sIter[kMaxDepth + 1];
-    __shared__ int sTileStart[kMaxDepth + 2];     // prefix of warp tiles over active depths
-    __shared__ int sGrpStart[kMaxDepth + 2];      // prefix of sibling groups over active depths
     const int D = P.D, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gwarp = blockIdx.x * kCgWarps + warp, nwarps = gridDim.x * kCgWarps;
+    const int gthread = blockIdx.x * kCgBlock + tid, nthreads = gridDim.x * kCgBlock;
     if (tid < (D + 1) * 4) {
         // one representative per number of off-centre axes: j = 13, 14, 17, 26
         const int rep[4] = {13, 14, 17, 26};
@@ -94,18 +113,17 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
     }
     // ---- init: x = 0, r = b, p = 0, r1 = r.r per depth
     {
-        double acc = 0.0;
-        int curD = -1;
-        const int totalRows = 8 * P.gbase[D + 1];
-        for (int rowi = blockIdx.x * kCgBlock + tid; rowi < totalRows; rowi += gridDim.x * kCgBlock) {
-            int i = 1 + rowi, G = rowi >> 3, d = 1;
-            while (G >= P.gbase[d + 1]) d++;
-            if (d != curD) { if (curD >= 0) atomicAdd(&sAcc[curD], acc); acc = 0.0; curD = d; }
-            float bv = P.b[i];
-            P.x[i] = 0.f; P.r[i] = bv; P.p[i] = 0.f;
-            acc += (double)(bv * bv);
+        // b (the divergence) is an unpadded array, so its quads are not 16-byte aligned: scalar loads
+        for (int d = 1; d <= D; d++) {
+            const int i0 = 1 + 8 * P.gbase[d], i1 = 1 + 8 * P.gbase[d + 1];
+            double part = 0.0;
+            for (int i = i0 + gthread; i < i1; i += nthreads) {
+                float bv = P.b[i];
+                P.x[i] = 0.f; P.r[i] = bv; P.p[i] = 0.f;
+                part += (double)(bv * bv);
+            }
+            warp_add(part, sAcc, d, lane);
         }
-        if (curD >= 0) atomicAdd(&sAcc[curD], acc);
         __syncthreads();
         if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&P.dots[64 + tid], sAcc[tid]);   // dedicated init buffer
     }
@@ -117,49 +135,52 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
     }
     __syncthreads();
 
-    const int gi = lane >> 3, cc = lane & 7;
-    const int cubeBase = (2 + ((cc >> 2) & 1)) * 36 + (2 + ((cc >> 1) & 1)) * 6 + (2 + (cc & 1));
-    float* myCube = &sCube[warp][0][0];
-    // staging task t = lane + 32k handles half-block (blk = t>>1, half = t&1); its cube offset
-    // depends on the lane only, so it is computed once (a __constant__ table indexed by lane would
-    // serialise: the constant cache serves one address per cycle)
-    int cubeOff[2];
+    // ---- per-lane constants of the SpMV
+    float* const cube0 = sDyn + (size_t)warp * 2 * kCube;
+    const unsigned cubeS = (unsigned)__cvta_generic_to_shared(cube0);
+    // staging: copy task t = lane + 32k (k = 0..3) moves half-block (blk = t>>1, half = t&1)
+    int stOff[4];
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < 4; k++) {
         int t = lane + 32 * k, blk = t >> 1, half = t & 1;
-        cubeOff[k] = (2 * (blk / 9) + half) * 36 + (2 * ((blk / 3) % 3)) * 6 + 2 * (blk % 3);
+        stOff[k] = (blk >> 4) * kSX + ((blk >> 2) & 3) * kSY + (blk & 3) * 8 + half * 4;
+    }
+    // compute: lane -> (kz, X, Y); it produces the rows at cube node (2+X, 2+Y, 2+2kz + {0,1})
+    const int kz = lane >> 4, X = (lane >> 2) & 3, Y = lane & 3;
+    const int pb = (1 + (X >> 1)) * 16 + (1 + (Y >> 1)) * 4 + (1 + kz);      // cube block of the rows' parent
+    const int rowIn = ((X & 1) << 2) | ((Y & 1) << 1);                         // child code of the z pair's first row
+    int ax[3], ay[3], zo[4];
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+        int xx = 1 + X + t, yy = 1 + Y + t;
+        ax[t] = (xx >> 1) * kSX + ((xx & 1) << 2);
+        ay[t] = (yy >> 1) * kSY + ((yy & 1) << 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        // half-warp 0 reads z = z0-1 .. z0+2 upwards, half-warp 1 downwards: at every step the two
+        // halves touch z of opposite parity, i.e. different banks
+        int z = kz ? (2 + 2 * kz + 2 - i) : (1 + i);
+        zo[i] = (z >> 1) * 8 + (z & 1);
     }
 
     for (int it = 1;; it++) {
-        // every block derives the same schedule from the same per-depth state
-        if (tid == 0) {
-            int acc = 0, accG = 0;
-            for (int d = 1; d <= D; d++) {
-                sTileStart[d] = acc;
-                sGrpStart[d] = accG;
-                if (sActive[d]) { acc += (P.gbase[d + 1] - P.gbase[d] + kGroupsPerWarp - 1) / kGroupsPerWarp; accG += P.gbase[d + 1] - P.gbase[d]; }
-            }
-            sTileStart[D + 1] = acc;
-            sGrpStart[D + 1] = accG;
-        }
+        int anyActive = 0;
+        for (int d = 1; d <= D; d++) anyActive |= sActive[d];
+        if (!anyActive) break;
         if (tid <= D) sAcc[tid] = 0.0;
         __syncthreads();
-        const int nTiles = sTileStart[D + 1];
-        if (nTiles == 0) break;
         const int cur = it & 1, nxt = cur ^ 1;
         double* dPAp = P.dots + cur * 32;         // kind 0
         double* dRRn = P.dots + cur * 32 + 16;    // kind 1 (this iteration's new r.r)
 
         // ---------------- phase C: p = r + beta p   (beta = 0 and p = 0 in the first iteration)
-        // streaming over the active depth slabs, 4 rows (one 128-bit access) per thread
-        {
-            const int nQuads = 2 * sGrpStart[D + 1];
-            int d = 0, lo = 0, hi = 0, gb = 0;
-            float be = 0.f;
-            for (int q = blockIdx.x * kCgBlock + tid; q < nQuads; q += gridDim.x * kCgBlock) {
-                int ag = q >> 1;
-                while (ag >= hi) { d++; lo = sGrpStart[d]; hi = sGrpStart[d + 1]; gb = P.gbase[d]; be = sBeta[d]; }   // inactive depths have lo == hi
-                int i = 1 + 8 * (gb + ag - lo) + 4 * (q & 1);
+        for (int d = 1; d <= D; d++) {
+            if (!sActive[d]) continue;
+            const float be = sBeta[d];
+            const int q1 = 2 * P.gbase[d + 1];
+            for (int q = 2 * P.gbase[d] + gthread; q < q1; q += nthreads) {
+                const int i = 1 + 4 * q;
                 float4 rv = *reinterpret_cast<const float4*>(P.r + i);
                 float4 pv = *reinterpret_cast<const float4*>(P.p + i);
                 pv.x = __fadd_rn(rv.x, __fmul_rn(be, pv.x));
@@ -171,85 +192,71 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
         }
         grid.sync();
         // ---------------- phase A: Ap = A p ; p.Ap
-        {
+        for (int d = 1; d <= D; d++) {
+            if (!sActive[d]) continue;
+            const float s0 = sSt[d][0], s1 = sSt[d][1], s2 = sSt[d][2], s3 = sSt[d][3];
+            const int t1 = P.sgStart[d + 1];
+            int t = P.sgStart[d] + gwarp;
             double part = 0.0;
-            int curD = -1;
-            int d = 0, lo = 0, hi = 0, gb = 0, ge = 0;
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-            for (int tile = gwarp; tile < nTiles; tile += nwarps) {
-                while (tile >= hi) {
-                    d++; lo = sTileStart[d]; hi = sTileStart[d + 1]; gb = P.gbase[d]; ge = P.gbase[d + 1];
-                    s0 = sSt[d][0]; s1 = sSt[d][1]; s2 = sSt[d][2]; s3 = sSt[d][3];
-                }
-                const int g0 = gb + (tile - lo) * kGroupsPerWarp;
-                const int ng = min(kGroupsPerWarp, ge - g0);
-                if (d != curD) {
-                    if (curD >= 0) {
+            // table registers of the current tile (A), the next (B) and the one after (C)
+            int a0 = -1, a1 = -1, b0 = -1, b1 = -1;
+            if (t < t1) { a0 = P.sgTab[64 * (i64)t + lane]; a1 = P.sgTab[64 * (i64)t + 32 + lane]; }
+            if (t + nwarps < t1) { b0 = P.sgTab[64 * (i64)(t + nwarps) + lane]; b1 = P.sgTab[64 * (i64)(t + nwarps) + 32 + lane]; }
+            int buf = 0;
+            if (t < t1) {
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
-                        if (lane == 0) atomicAdd(&sAcc[curD], part);
-                    }
-                    part = 0.0;
-                    curD = d;
-                }
-                __syncwarp();
-                {
-                    // all 8 base loads first, then all 8 128-bit value loads, then the stores:
-                    // 8 independent requests in flight per lane instead of a base->value chain per group
-                    const int* nbp = P.nbBase + 27 * (i64)g0;
-                    int bb[kGroupsPerWarp][2];
-#pragma unroll
-                    for (int g = 0; g < kGroupsPerWarp; g++)
-#pragma unroll
-                        for (int k = 0; k < 2; k++) {
-                            int t = lane + 32 * k;
-                            bb[g][k] = (g < ng && t < 54) ? nbp[27 * g + (t >> 1)] : -1;
-                        }
-                    float4 vv[kGroupsPerWarp][2];
-#pragma unroll
-                    for (int g = 0; g < kGroupsPerWarp; g++)
-#pragma unroll
-                        for (int k = 0; k < 2; k++) {
-                            vv[g][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (bb[g][k] >= 0) vv[g][k] = *reinterpret_cast<const float4*>(P.p + bb[g][k] + 4 * (lane & 1));
-                        }
-#pragma unroll
-                    for (int g = 0; g < kGroupsPerWarp; g++)
-#pragma unroll
-                        for (int k = 0; k < 2; k++) {
-                            int t = lane + 32 * k;
-                            if (g < ng && t < 54) {
-                                int off = cubeOff[k];
-                                float* cube = myCube + g * 216;
-                                *reinterpret_cast<float2*>(cube + off) = make_float2(vv[g][k].x, vv[g][k].y);
-                                *reinterpret_cast<float2*>(cube + off + 6) = make_float2(vv[g][k].z, vv[g][k].w);
-                            }
-                        }
-                }
-                __syncwarp();
-                if (gi < ng) {
-                    const float* cb = myCube + gi * 216 + cubeBase;
-                    float acc = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 27; j++) {
-                        const int dx = j / 9 - 1, dy = (j / 3) % 3 - 1, dz = j % 3 - 1;
-                        const int ty = (dx != 0) + (dy != 0) + (dz != 0);
-                        const float sv = ty == 0 ? s0 : (ty == 1 ? s1 : (ty == 2 ? s2 : s3));
-                        acc = __fmaf_rn(sv, cb[dx * 36 + dy * 6 + dz], acc);
-                    }
-                    int i = 1 + 8 * (g0 + gi) + cc;
-                    P.Ap[i] = acc;
-                    part += (double)(cb[0] * acc);
+                for (int k = 0; k < 4; k++) {
+                    int base = __shfl_sync(0xffffffffu, k < 2 ? a0 : a1, ((lane >> 1) + 16 * k) & 31);
+                    cp_async16(cubeS + 4u * (unsigned)stOff[k], base >= 0 ? (const void*)(P.p + base + 4 * (lane & 1)) : (const void*)(P.p + 1), base >= 0 ? 16 : 0);
                 }
             }
-            if (curD >= 0) {
+            cp_async_commit();
+            for (; t < t1; t += nwarps, buf ^= 1) {
+                // next tile's copies into the other buffer, the table of the tile after that into registers
+                int c0 = -1, c1 = -1;
+                if (t + nwarps < t1) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
-                if (lane == 0) atomicAdd(&sAcc[curD], part);
+                    for (int k = 0; k < 4; k++) {
+                        int base = __shfl_sync(0xffffffffu, k < 2 ? b0 : b1, ((lane >> 1) + 16 * k) & 31);
+                        cp_async16(cubeS + 4u * (unsigned)((buf ^ 1) * kCube + stOff[k]), base >= 0 ? (const void*)(P.p + base + 4 * (lane & 1)) : (const void*)(P.p + 1),
+                                   base >= 0 ? 16 : 0);
+                    }
+                    if (t + 2 * nwarps < t1) { c0 = P.sgTab[64 * (i64)(t + 2 * nwarps) + lane]; c1 = P.sgTab[64 * (i64)(t + 2 * nwarps) + 32 + lane]; }
+                }
+                cp_async_commit();
+                cp_async_wait<1>();
+                __syncwarp();
+                const int r0 = __shfl_sync(0xffffffffu, a0, pb & 31), r1 = __shfl_sync(0xffffffffu, a1, pb & 31);
+                const int rowBase = pb < 32 ? r0 : r1;
+                if (rowBase >= 0) {
+                    const float* cb = cube0 + buf * kCube;
+                    float acc0 = 0.f, acc1 = 0.f, pc0 = 0.f, pc1 = 0.f;
+#pragma unroll
+                    for (int dx = 0; dx < 3; dx++)
+#pragma unroll
+                        for (int dy = 0; dy < 3; dy++) {
+                            const float* q = cb + ax[dx] + ay[dy];
+                            float t0 = q[zo[0]], t1v = q[zo[1]], t2 = q[zo[2]], t3 = q[zo[3]];
+                            const float w0 = kz ? t3 : t0, w1 = kz ? t2 : t1v, w2 = kz ? t1v : t2, w3 = kz ? t0 : t3;
+                            const int ty = (dx != 1) + (dy != 1);
+                            const float se = ty == 0 ? s1 : (ty == 1 ? s2 : s3);     // dz != 0
+                            const float sc = ty == 0 ? s0 : (ty == 1 ? s1 : s2);     // dz == 0
+                            acc0 = __fmaf_rn(se, w0, acc0); acc0 = __fmaf_rn(sc, w1, acc0); acc0 = __fmaf_rn(se, w2, acc0);
+                            acc1 = __fmaf_rn(se, w1, acc1); acc1 = __fmaf_rn(sc, w2, acc1); acc1 = __fmaf_rn(se, w3, acc1);
+                            if (dx == 1 && dy == 1) { pc0 = w1; pc1 = w2; }
+                        }
+                    *reinterpret_cast<float2*>(P.Ap + rowBase + rowIn) = make_float2(acc0, acc1);
+                    part += (double)(pc0 * acc0);
+                    part += (double)(pc1 * acc1);
+                }
+                __syncwarp();      // all lanes are done with this buffer before the next copies land in it
+                a0 = b0; a1 = b1; b0 = c0; b1 = c1;
             }
-            __syncthreads();
-            if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&dPAp[tid], sAcc[tid]);
+            cp_async_wait<0>();
+            warp_add(part, sAcc, d, lane);
         }
+        __syncthreads();
+        if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&dPAp[tid], sAcc[tid]);
         grid.sync();
         // both accumulators of the NEXT iteration are zeroed here: every block has passed this
         // iteration's syncs, hence finished reading them after the previous iteration's syncs
@@ -258,17 +265,13 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
         if (tid >= 1 && tid <= D && sActive[tid]) sAlpha[tid] = (float)((double)sR1[tid] / dPAp[tid]);
         __syncthreads();
         // ---------------- phase B: x += alpha p ; r -= alpha Ap ; r.r
-        {
+        for (int d = 1; d <= D; d++) {
+            if (!sActive[d]) continue;
+            const float al = sAlpha[d];
+            const int q1 = 2 * P.gbase[d + 1];
             double part = 0.0;
-            int curD = -1;
-            const int nQuads = 2 * sGrpStart[D + 1];
-            int d = 0, lo = 0, hi = 0, gb = 0;
-            float al = 0.f;
-            for (int q = blockIdx.x * kCgBlock + tid; q < nQuads; q += gridDim.x * kCgBlock) {
-                int ag = q >> 1;
-                while (ag >= hi) { d++; lo = sGrpStart[d]; hi = sGrpStart[d + 1]; gb = P.gbase[d]; al = sAlpha[d]; }
-                if (d != curD) { if (curD >= 0) atomicAdd(&sAcc[curD], part); part = 0.0; curD = d; }
-                int i = 1 + 8 * (gb + ag - lo) + 4 * (q & 1);
+            for (int q = 2 * P.gbase[d] + gthread; q < q1; q += nthreads) {
+                const int i = 1 + 4 * q;
                 float4 pv = *reinterpret_cast<const float4*>(P.p + i);
                 float4 av = *reinterpret_cast<const float4*>(P.Ap + i);
                 float4 xv = *reinterpret_cast<const float4*>(P.x + i);
@@ -282,18 +285,10 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
                 part += (double)(rv.z * rv.z);
                 part += (double)(rv.w * rv.w);
             }
-            {
-                // one shared-memory atomic per warp when the whole warp ended in the same depth
-                int d0 = __shfl_sync(0xffffffffu, curD, 0);
-                if (__all_sync(0xffffffffu, curD == d0)) {
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
-                    if (lane == 0 && d0 >= 0) atomicAdd(&sAcc[d0], part);
-                } else if (curD >= 0) atomicAdd(&sAcc[curD], part);
-            }
-            __syncthreads();
-            if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&dRRn[tid], sAcc[tid]);
+            warp_add(part, sAcc, d, lane);
         }
+        __syncthreads();
+        if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&dRRn[tid], sAcc[tid]);
         grid.sync();
         if (tid >= 1 && tid <= D && sActive[tid]) {
             float r0 = sR1[tid], r1 = (float)dRRn[tid];
@@ -308,21 +303,9 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
     if (blockIdx.x == 0 && tid >= 1 && tid <= D) { P.itersOut[tid] = sIter[tid] - 1; P.resOut[tid] = sR1[tid]; }
 }
 
-static bool g_cubeReady = false;
-
 int stage_solve(Context& c) {
     const int D = c.D, M = c.M;
     cudaStream_t st = c.stream;
-    if (!g_cubeReady) {
-        unsigned short h[54];
-        for (int t = 0; t < 54; t++) {
-            int blk = t >> 1, half = t & 1;
-            int bx = blk / 9, by = (blk / 3) % 3, bz = blk % 3;
-            h[t] = (unsigned short)((2 * bx + half) * 36 + (2 * by) * 6 + 2 * bz);
-        }
-        PRB_CUDA(cudaMemcpyToSymbol(cCubeOff, h, sizeof(h)));
-        g_cubeReady = true;
-    }
     // vectors are padded by 7 floats so that node 1 (the first sibling block) is 32-byte aligned
     const size_t padN = (size_t)M + 8;
     PRB_TRY(c.x.alloc(padN, st));
@@ -342,24 +325,30 @@ int stage_solve(Context& c) {
     P.D = D;
     for (int d = 1; d <= D + 1; d++) P.gbase[d] = (c.base[d] - 1) / 8;
     P.gbase[0] = 0;
-    P.nbBase = c.nbBase.p; P.stencil = c.dStencil.p; P.b = c.divg.p;
+    // super-groups: sg 0 = depth 1; depth d >= 2 owns the super-groups 1 + (sibling groups of depth d-1)
+    P.sgStart[0] = 0;
+    P.sgStart[1] = 0;
+    for (int d = 2; d <= D + 1; d++) P.sgStart[d] = 1 + P.gbase[d - 1];
+    P.sgTab = c.sgTab.p; P.stencil = c.dStencil.p; P.b = c.divg.p;
     P.x = c.xv; P.r = r.p + 7; P.p = p.p + 7; P.Ap = Ap.p + 7;
     P.dots = dots.p; P.itersOut = itersOut.p; P.resOut = resOut.p;
     float tol = (float)c.cgTol;
     P.tol2 = tol * tol;
     P.maxIter = c.cgMaxIter;
+    const size_t dynSmem = (size_t)kCgWarps * 2 * kCube * sizeof(float);
+    PRB_CUDA(cudaFuncSetAttribute(k_cg_all_depths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynSmem));
+    PRB_CUDA(cudaFuncSetAttribute(k_cg_all_depths, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int perSM = 0;
-    PRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_cg_all_depths, kCgBlock, 0));
+    PRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_cg_all_depths, kCgBlock, dynSmem));
     if (perSM < 1) { set_error("CG kernel does not fit on an SM"); return PRB_ERR_CUDA; }
     int gridSize = c.smCount * perSM;
-    i64 maxTiles = 0;
-    for (int d = 1; d <= D; d++) maxTiles += (P.gbase[d + 1] - P.gbase[d] + kGroupsPerWarp - 1) / kGroupsPerWarp;
+    i64 maxTiles = P.sgStart[D + 1];
     i64 needBlocks = (maxTiles + kCgWarps - 1) / kCgWarps;
     if (gridSize > needBlocks) gridSize = (int)(((needBlocks + c.smCount - 1) / c.smCount) * c.smCount);   // small problems: fewer CTAs, cheaper grid syncs
     if (gridSize > c.smCount * perSM) gridSize = c.smCount * perSM;
     if (gridSize < 1) gridSize = 1;
     void* args[] = {(void*)&P};
-    PRB_CUDA(cudaLaunchCooperativeKernel((void*)k_cg_all_depths, dim3(gridSize), dim3(kCgBlock), args, 0, st));
+    PRB_CUDA(cudaLaunchCooperativeKernel((void*)k_cg_all_depths, dim3(gridSize), dim3(kCgBlock), args, dynSmem, st));
     c.launches++;
     int hIters[16];
     PRB_CUDA(cudaMemcpyAsync(hIters, itersOut.p, sizeof(hIters), cudaMemcpyDeviceToHost, st));
