@@ -45,31 +45,49 @@ __device__ __forceinline__ float shifted_bspline(const float* __restrict__ fn, f
     return res;
 }
 
-__global__ void __launch_bounds__(128) k_splat(const float* __restrict__ fn, const float* __restrict__ P, const float* __restrict__ Nr,
-                                               const int* __restrict__ neighs, const int* __restrict__ pidx, const int* __restrict__ pnum,
-                                               const ushort4* __restrict__ offs, int baseD, int countD, float width, float* __restrict__ V) {
+// per-sample weights: W[q][axis][t] = B-hat evaluated for the slot whose offset along `axis` is
+// (offset of q's leaf) + t - 1.  A sample is seen by up to 27 slots; the shifted-polynomial
+// evaluation (divisions included) is done once per sample and axis instead of once per pair.
+__global__ void __launch_bounds__(128) k_splat_weights(const float* __restrict__ fn, const float* __restrict__ P, const int* __restrict__ p2n,
+                                                       const ushort4* __restrict__ offsD, i64 N, float width, float* __restrict__ W) {
     __shared__ float sfn[16];
     if (threadIdx.x < 16) sfn[threadIdx.x] = fn[threadIdx.x];
     __syncthreads();
+    for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += (i64)gridDim.x * blockDim.x) {
+        const ushort4 o = offsD[p2n[q]];
+        const int oo[3] = {(int)o.x, (int)o.y, (int)o.z};
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const float pa = P[3 * q + a];
+#pragma unroll
+            for (int t = 0; t < 3; t++) {
+                float oc = (float)((0.5 + (double)(oo[a] + t - 1)) * (double)width);
+                W[9 * q + 3 * a + t] = shifted_bspline(sfn, pa, oc);
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(128) k_splat(const float* __restrict__ W, const float* __restrict__ Nr,
+                                               const int* __restrict__ neighs, const int* __restrict__ pidx, const int* __restrict__ pnum,
+                                               int baseD, int countD, float* __restrict__ V) {
     for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < countD; l += gridDim.x * blockDim.x) {
         int i = baseD + l;
-        ushort4 o = offs[i];
-        float oc[3] = {(float)((0.5 + o.x) * (double)width), (float)((0.5 + o.y) * (double)width), (float)((0.5 + o.z) * (double)width)};
         float val[3] = {0.f, 0.f, 0.f};
         const int* nb = neighs + 27 * (i64)i;
+#pragma unroll
         for (int j = 0; j < 27; j++) {
             int n = nb[j];
             if (n < 0) continue;
             int p0 = pidx[n], pn = pnum[n];
+            // the slot lies at direction -d_j of the sample's leaf: weight index t = 2 - (digit of j)
+            const int tx = 2 - j / 9, ty = 2 - (j / 3) % 3, tz = 2 - j % 3;
             for (int k = 0; k < pn; k++) {
-                i64 q = 3 * (i64)(p0 + k);
-                float wx = shifted_bspline(sfn, P[q], oc[0]);
-                float wy = shifted_bspline(sfn, P[q + 1], oc[1]);
-                float wz = shifted_bspline(sfn, P[q + 2], oc[2]);
-                float w = __fmul_rn(__fmul_rn(wx, wy), wz);
-                val[0] = __fmaf_rn(w, Nr[q], val[0]);
-                val[1] = __fmaf_rn(w, Nr[q + 1], val[1]);
-                val[2] = __fmaf_rn(w, Nr[q + 2], val[2]);
+                i64 q = p0 + k;
+                const float* wq = W + 9 * q;
+                float w = __fmul_rn(__fmul_rn(wq[tx], wq[3 + ty]), wq[6 + tz]);
+                val[0] = __fmaf_rn(w, Nr[3 * q], val[0]);
+                val[1] = __fmaf_rn(w, Nr[3 * q + 1], val[1]);
+                val[2] = __fmaf_rn(w, Nr[3 * q + 2], val[2]);
             }
         }
         V[3 * (i64)l] = val[0];
@@ -127,6 +145,63 @@ __global__ void __launch_bounds__(256) k_divergence(const float* __restrict__ V,
             }
         }
         if (lane == 0 && l < count) divg[base + l] = (float)val;
+    }
+}
+
+// The two finest depths without the slot indirections: at depth D a neighbour IS its slot and the
+// table index is the neighbour direction; at depth D-1 the slots of a neighbour are its 8
+// children (one aligned 96-byte record of V) and the index is 2*(direction+1) + child bit.
+// Same terms, same order, same arithmetic as k_divergence<1>.
+__global__ void __launch_bounds__(256) k_divergence_leaf(const float* __restrict__ V, const int* __restrict__ neighs, const float* __restrict__ dfRow,
+                                                         int baseD, int count, float* __restrict__ divg) {
+    const float r0 = dfRow[0], r1 = dfRow[1], r2 = dfRow[2];
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < count; l += gridDim.x * blockDim.x) {
+        const int* nb = neighs + 27 * (i64)(baseD + l);
+        double val = 0.0;
+#pragma unroll
+        for (int j = 0; j < 27; j++) {
+            int n = nb[j];
+            if (n < 0) continue;
+            const float* v = V + 3 * (i64)(n - baseD);
+            const float u0 = (j / 9) == 0 ? r0 : ((j / 9) == 1 ? r1 : r2);
+            const float u1 = ((j / 3) % 3) == 0 ? r0 : (((j / 3) % 3) == 1 ? r1 : r2);
+            const float u2 = (j % 3) == 0 ? r0 : ((j % 3) == 1 ? r1 : r2);
+            float dp = __fmul_rn(v[0], u0);
+            dp = __fmaf_rn(v[1], u1, dp);
+            dp = __fmaf_rn(v[2], u2, dp);
+            val += (double)dp;
+        }
+        divg[baseD + l] = (float)val;
+    }
+}
+__global__ void __launch_bounds__(256) k_divergence_dm1(const float* __restrict__ V, const int* __restrict__ neighs, const int* __restrict__ child0,
+                                                        const float* __restrict__ dfRow, int base, int count, int baseD, float* __restrict__ divg) {
+    float row[6];
+#pragma unroll
+    for (int t = 0; t < 6; t++) row[t] = dfRow[t];
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < count; l += gridDim.x * blockDim.x) {
+        const int* nb = neighs + 27 * (i64)(base + l);
+        double val = 0.0;
+#pragma unroll
+        for (int j = 0; j < 27; j++) {
+            int n = nb[j];
+            if (n < 0) continue;
+            int c0 = child0[n];
+            if (c0 < 0) continue;
+            const float4* v4 = reinterpret_cast<const float4*>(V + 3 * (i64)(c0 - baseD));
+            float v[24];
+#pragma unroll
+            for (int t = 0; t < 6; t++) { float4 a = v4[t]; v[4 * t] = a.x; v[4 * t + 1] = a.y; v[4 * t + 2] = a.z; v[4 * t + 3] = a.w; }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const float u0 = row[2 * (j / 9) + (q >> 2)], u1 = row[2 * ((j / 3) % 3) + ((q >> 1) & 1)], u2 = row[2 * (j % 3) + (q & 1)];
+                float dp = __fmul_rn(v[3 * q], u0);
+                dp = __fmaf_rn(v[3 * q + 1], u1, dp);
+                dp = __fmaf_rn(v[3 * q + 2], u2, dp);
+                val += (double)dp;
+            }
+        }
+        divg[base + l] = (float)val;
     }
 }
 
@@ -208,8 +283,13 @@ int stage_splat(Context& c) {
     PRB_TRY(c.V.alloc(3 * (size_t)c.cnt[D], st));
     PRB_TRY(c.divg.alloc((size_t)c.M, st));
     float width = (float)(1.0 / (1 << D));
-    PRB_LAUNCH(c, k_splat, grid_for(c, c.cnt[D], 128, 16), 128, 0, c.dMaxDepthFn.p, c.P.p, c.Nr.p, c.neighs.p, c.pidx.p, c.pnum.p, c.offs.p,
-               c.base[D], c.cnt[D], width, c.V.p);
+    {
+        DBuf<float> W;
+        PRB_TRY(W.alloc(9 * (size_t)c.N, st));
+        PRB_LAUNCH(c, k_splat_weights, grid_for(c, c.N, 128, 16), 128, 0, c.dMaxDepthFn.p, c.P.p, c.p2n.p, c.offs.p + c.base[D], c.N, width, W.p);
+        PRB_LAUNCH(c, k_splat, grid_for(c, c.cnt[D], 128, 16), 128, 0, W.p, c.Nr.p, c.neighs.p, c.pidx.p, c.pnum.p, c.base[D], c.cnt[D], c.V.p);
+        W.release();
+    }
     PRB_CUDA(cudaEventRecord(c.ev[3], st));
     PRB_TRY(stage_divergence(c));
     PRB_CUDA(cudaGetLastError());
@@ -244,7 +324,11 @@ int stage_divergence(Context& c) {
         int k = 1 << (D - d);
         const float* row = c.dDfT.p + c.tab.dfOffset[d];
         int n = c.cnt[d];
-        if (d >= D - 1)
+        if (d == D)
+            PRB_LAUNCH(c, k_divergence_leaf, grid_for(c, n, 256), 256, 0, c.V.p, c.neighs.p, row, c.base[D], n, c.divg.p);
+        else if (d == D - 1)
+            PRB_LAUNCH(c, k_divergence_dm1, grid_for(c, n, 256), 256, 0, c.V.p, c.neighs.p, c.child0.p, row, c.base[d], n, c.base[D], c.divg.p);
+        else if (d >= D - 1)
             PRB_LAUNCH(c, k_divergence<1>, grid_for(c, n, 256), 256, 0, c.V.p, c.offs.p, c.neighs.p, c.didx.p, c.dnum.p, row, c.base[d], n, c.base[D], k, c.divg.p);
         else
             PRB_LAUNCH(c, k_divergence<32>, grid_for(c, (i64)n * 32, 256), 256, 0, c.V.p, c.offs.p, c.neighs.p, c.didx.p, c.dnum.p, row, c.base[d], n, c.base[D], k, c.divg.p);

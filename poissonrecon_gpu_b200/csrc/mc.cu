@@ -245,6 +245,8 @@ __global__ void __launch_bounds__(kVvWarps * 32) k_vertex_values_grouped(Topo T,
                                                                          const float* __restrict__ baseFn, float iso, float* __restrict__ vval) {
     __shared__ float sX[kVvWarps][27];
     __shared__ float sB[kVvWarps][3][3][3];      // [axis][point coordinate 0..2][k]
+    __shared__ float sXc[kVvWarps][64];          // solution on the 4x4x4 node cube around the group (own level)
+    __shared__ float sB0[kVvWarps][3][3][4];     // own level: [axis][point coordinate][cube coordinate]
     const int exceedTab[8] = {0, 1, 3, 2, 4, 5, 7, 6};     // childrenVertexKind, MarchingCubes.cuh:721-723 (applied as the reference does)
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     for (int g = blockIdx.x * kVvWarps + wp; g < nGroups; g += gridDim.x * kVvWarps) {
@@ -267,7 +269,33 @@ __global__ void __launch_bounds__(kVvWarps * 32) k_vertex_values_grouped(Topo T,
         }
         const float pos[3] = {(float)((int)o0.x + px) * w, (float)((int)o0.y + py) * w, (float)((int)o0.z + pz) * w};
         float val = 0.f;
-        if (mine) accumulate_level(val, T.nbr + 27 * (i64)owner, offs[owner], x, baseFn, pos);
+        // own level: every neighbour of every sibling lies in the 4x4x4 cube around the group
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int e = lane + 32 * h, ux = e >> 4, uy = (e >> 2) & 3, uz = e & 3;
+            const int sx = ux >> 1, sy = uy >> 1, sz = uz >> 1;
+            const int j = 9 * (ux - sx) + 3 * (uy - sy) + (uz - sz);          // 9(dx+1)+3(dy+1)+(dz+1) with d = u - 1 - s
+            const int q = T.nbr[27 * (i64)(gb + ((sx << 2) | (sy << 1) | sz)) + j];
+            sXc[wp][e] = q >= 0 ? x[q] : 0.f;
+        }
+        for (int e = lane; e < 36; e += 32) {
+            const int a = e / 12, pc = (e >> 2) % 3, cu = e & 3;
+            const int nn = 1 << d0, ao = (a == 0 ? (int)o0.x : (a == 1 ? (int)o0.y : (int)o0.z)) + cu - 1;
+            const float pp = (float)((a == 0 ? (int)o0.x : (a == 1 ? (int)o0.y : (int)o0.z)) + pc) * w;
+            sB0[wp][a][pc][cu] = (ao >= 0 && ao < nn) ? base_value(baseFn, nn - 1 + ao, pp) : 0.f;
+        }
+        __syncwarp();
+        if (mine) {
+            const int k = owner - gb, sox = (k >> 2) & 1, soy = (k >> 1) & 1, soz = k & 1;
+            float vx[3], vy[3], vz[3];
+#pragma unroll
+            for (int t = 0; t < 3; t++) { vx[t] = sB0[wp][0][px][sox + t]; vy[t] = sB0[wp][1][py][soy + t]; vz[t] = sB0[wp][2][pz][soz + t]; }
+            const float* xc = &sXc[wp][sox * 16 + soy * 4 + soz];
+#pragma unroll
+            for (int j = 0; j < 27; j++)
+                val = __fmaf_rn(__fmul_rn(__fmul_rn(xc[(j / 9) * 16 + ((j / 3) % 3) * 4 + (j % 3)], vx[j / 9]), vy[(j / 3) % 3]), vz[j % 3], val);
+        }
         // shared ancestor levels d0-1 .. 0
         int anc = parent[gb];
         for (int l = d0 - 1; l >= 0; --l) {
