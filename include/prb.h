@@ -109,6 +109,25 @@ int prb_run_stage(prb_context* ctx, const char* name);
  * "refine" (1 = run the refinement passes, main.cu:3799-4564). */
 int prb_set_option(prb_context* ctx, const char* key, double value);
 
+/* ---- Multi-GPU (new: the reference is single-GPU, devID = 0 hard-coded at CG_CUDA.cuh:356).
+ * One process and one context per GPU of one NVLink box, 2..8 ranks.  Every rank is given the SAME
+ * samples and builds the same octree; the divergence, the CG solve and the iso value are sharded
+ * by Morton range (depths with fewer than 65536 nodes stay replicated) and exchange data through
+ * a peer-mapped arena: kernels read the other ranks' halo blocks over NVLink directly, phase
+ * boundaries are epoch flags in that arena (no host round trip).  Every rank ends with the
+ * complete solution and extracts the complete mesh.
+ *   prb_mg_init      allocates this rank's arena (cudaMalloc, `arena_bytes`; 8*(nodes+8) bytes
+ *                    + 16 KiB are needed per run) and returns its 64-byte CUDA IPC handle;
+ *   prb_mg_set_peer  opens the arena of another rank from its handle (exchange the handles with
+ *                    any host-side transport, e.g. torch.distributed.all_gather_object);
+ *   prb_mg_barrier   box-wide barrier through the arena flags (all ranks must call it);
+ *   prb_mg_plan      host-only helper: the contiguous split of `count` units over `world` ranks
+ *                    used for every sharded range (out[world + 1]). */
+int prb_mg_init(prb_context* ctx, int rank, int world, int64_t arena_bytes, void* ipc_handle_out_64_bytes);
+int prb_mg_set_peer(prb_context* ctx, int peer_rank, const void* ipc_handle_64_bytes);
+int prb_mg_barrier(prb_context* ctx);
+int prb_mg_plan(int64_t count, int world, int64_t* out);
+
 /* Host-side B-spline precompute (replaces FunctionData<2,double>::set / setDotTables,
  * FunctionData.inl:112-215, and the table uploads of main.cu:3308-3359).  Needs no GPU: copies
  * the named table for `depth` to `dst` and returns its size in bytes.  Names: gauss (4x4 f32),

@@ -42,6 +42,16 @@ class PrbStats(ctypes.Structure):
         return d
 
 
+def shard_plan(count: int, world: int):
+    """Contiguous split of `count` units over `world` ranks (prb_mg_plan; host only, no GPU)."""
+    lib = load_library()
+    out = (ctypes.c_int64 * (world + 1))()
+    rc = lib.prb_mg_plan(int(count), int(world), out)
+    if rc != 0:
+        raise PrbError(f"prb_mg_plan: {lib.prb_last_error().decode()}")
+    return list(out)
+
+
 def lib_path() -> str:
     return os.path.join(_HERE, "libprb.so")
 
@@ -75,6 +85,10 @@ def load_library():
     lib.prb_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_double]
     lib.prb_run_stage.argtypes = [vp, ctypes.c_char_p]
     lib.prb_get_stream.argtypes = [vp, ctypes.POINTER(vp)]
+    lib.prb_mg_init.argtypes = [vp, ci, ci, cll, vp]
+    lib.prb_mg_set_peer.argtypes = [vp, ci, vp]
+    lib.prb_mg_barrier.argtypes = [vp]
+    lib.prb_mg_plan.argtypes = [cll, ci, ctypes.POINTER(cll)]
     lib.prb_host_tables.argtypes = [ci, ctypes.c_char_p, vp, cll]
     lib.prb_host_tables.restype = cll
     _lib = lib
@@ -83,7 +97,8 @@ def load_library():
 
 EXPORTS = ["prb_create", "prb_destroy", "prb_last_error", "prb_set_points", "prb_build_octree", "prb_splat", "prb_solve",
            "prb_extract", "prb_run", "prb_get_mesh", "prb_get_mesh_device", "prb_get_stats", "prb_get_array", "prb_set_array",
-           "prb_set_option", "prb_run_stage", "prb_get_stream", "prb_host_tables"]
+           "prb_set_option", "prb_run_stage", "prb_get_stream", "prb_host_tables", "prb_mg_init", "prb_mg_set_peer", "prb_mg_barrier",
+           "prb_mg_plan"]
 
 
 class PoissonRecon:
@@ -142,6 +157,34 @@ class PoissonRecon:
 
     def set_option(self, key: str, value: float):
         self._check(self.lib.prb_set_option(self.h, key.encode(), float(value)))
+
+    # ---- multi-GPU (one process per GPU; see include/prb.h)
+    def mg_init(self, rank: int, world: int, arena_bytes: int) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        self._check(self.lib.prb_mg_init(self.h, rank, world, int(arena_bytes), buf))
+        return bytes(buf.raw)
+
+    def mg_set_peer(self, peer_rank: int, handle: bytes):
+        buf = ctypes.create_string_buffer(handle, 64)
+        self._check(self.lib.prb_mg_set_peer(self.h, peer_rank, buf))
+
+    def mg_barrier(self):
+        self._check(self.lib.prb_mg_barrier(self.h))
+
+    def mg_setup(self, arena_bytes: int, group=None):
+        """Allocate this rank's arena, exchange the IPC handles over torch.distributed (the plumbing
+        backend: NCCL or gloo) and open every peer.  All ranks of the group must call it."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        mine = self.mg_init(rank, world, arena_bytes)
+        handles = [None] * world
+        dist.all_gather_object(handles, mine, group=group)
+        for r, hd in enumerate(handles):
+            if r != rank:
+                self.mg_set_peer(r, hd)
+        dist.barrier(group)
+        self.mg_barrier()
+        return rank, world
 
     def stream(self) -> int:
         """The context's cudaStream_t as an integer (wrap with torch.cuda.ExternalStream)."""

@@ -92,6 +92,54 @@ struct HBuf {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU (one process per GPU, all GPUs of one NVLink/NVSwitch box).  The octree topology is
+// replicated on every rank (it is built from the same samples, bit-identically); the heavy field
+// stages are sharded by Morton range and exchange data through a PEER-MAPPED ARENA: one
+// cudaMalloc block per rank, exported with cudaIpcGetMemHandle and opened by every other rank,
+// in which all ranks make the same sequence of sub-allocations (same sizes -> same offsets), so
+// `peerArena[r] + offset` addresses rank r's copy of a buffer.  Kernels read halo data with plain
+// loads / cp.async on those peer pointers (NVLink), and ranks synchronise with epoch flags in
+// the arena header -- no host round trip, no NCCL call on the data path.
+constexpr int kMaxRanks = 8;
+constexpr size_t kMgHeaderBytes = 16384;     // flags + dot-product slots
+struct MgHeader {
+    unsigned flags[kMaxRanks][32];            // flags[r][0]: last epoch rank r has arrived at (one 128-B line per writer)
+    double slots[2][kMaxRanks][32];           // dot-product partials [parity][rank][kind*16 + depth]
+    int error;                                // set by a kernel whose peer wait timed out
+};
+struct MgDev {                                // passed by value to kernels
+    int rank, world;
+    MgHeader* hdr;                            // own header
+    MgHeader* peerHdr[kMaxRanks];
+};
+struct MgState {
+    int rank = 0, world = 1;
+    char* arena = nullptr;
+    size_t arenaBytes = 0, used = 0;
+    char* peer[kMaxRanks] = {nullptr};        // peer[rank] == arena
+    bool peerOpen[kMaxRanks] = {false};
+    unsigned epoch = 0;                       // last epoch used (host-tracked, identical on all ranks)
+    int minShardRows = 65536;                 // depths with fewer rows stay replicated
+    bool active() const { return world > 1; }
+    void reset_allocs() { used = kMgHeaderBytes; }
+    template <class T>
+    T* alloc(size_t count, size_t* offset) {  // 256-byte aligned bump allocation; nullptr when the arena is full
+        size_t a = (used + 255) & ~(size_t)255, b = a + count * sizeof(T);
+        if (!arena || b > arenaBytes) return nullptr;
+        used = b;
+        if (offset) *offset = a;
+        return (T*)(arena + a);
+    }
+    MgDev dev() const {
+        MgDev d;
+        d.rank = rank; d.world = world; d.hdr = (MgHeader*)arena;
+        for (int r = 0; r < kMaxRanks; r++) d.peerHdr[r] = (MgHeader*)peer[r];
+        return d;
+    }
+};
+int mg_barrier(struct Context& c);            // device-side flag barrier on the context stream (all ranks must call it)
+
 // One pass (the main depth-D pass or a refinement pass) of mesh output.
 struct PassRecord { int kind, nv, nt; };   // kind: 0 main, 1 coarse (single root), 2 batched per depth
 
@@ -153,6 +201,14 @@ struct Context {
     DBuf<unsigned short> wsEmask;
     DBuf<int> wsVbase, wsTbase;
     prb_stats stats;
+    // ---- multi-GPU
+    MgState mg;
+    int shardFrom = 0;                         // first sharded depth (D+1: none); set by stage_octree
+    int sgLo[kMaxDepth + 2][kMaxRanks + 1];    // super-group range of every rank at every depth
+    int rowLo[kMaxDepth + 2][kMaxRanks + 1];   // node range of every rank at every depth (sharded depths), else [base, base+cnt) for rank 0..
+    float* mgP = nullptr;                      // CG direction vector inside the arena (padded like x)
+    float* mgX = nullptr;                      // solution inside the arena
+    size_t mgPOff = 0, mgXOff = 0;
 };
 
 // stages (implemented in the .cu files)
@@ -220,3 +276,7 @@ __host__ __device__ inline void other_axes(int o, int& a0, int& a1) {
 }
 
 }  // namespace prb
+
+struct prb_context {
+    prb::Context c;
+};

@@ -153,10 +153,10 @@ __global__ void __launch_bounds__(256) k_divergence(const float* __restrict__ V,
 // children (one aligned 96-byte record of V) and the index is 2*(direction+1) + child bit.
 // Same terms, same order, same arithmetic as k_divergence<1>.
 __global__ void __launch_bounds__(256) k_divergence_leaf(const float* __restrict__ V, const int* __restrict__ neighs, const float* __restrict__ dfRow,
-                                                         int baseD, int count, float* __restrict__ divg) {
+                                                         int baseD, int first, int count, float* __restrict__ divg) {
     const float r0 = dfRow[0], r1 = dfRow[1], r2 = dfRow[2];
     for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < count; l += gridDim.x * blockDim.x) {
-        const int* nb = neighs + 27 * (i64)(baseD + l);
+        const int* nb = neighs + 27 * (i64)(first + l);
         double val = 0.0;
 #pragma unroll
         for (int j = 0; j < 27; j++) {
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) k_divergence_leaf(const float* __restrict
             dp = __fmaf_rn(v[2], u2, dp);
             val += (double)dp;
         }
-        divg[baseD + l] = (float)val;
+        divg[first + l] = (float)val;
     }
 }
 __global__ void __launch_bounds__(256) k_divergence_dm1(const float* __restrict__ V, const int* __restrict__ neighs, const int* __restrict__ child0,
@@ -323,15 +323,17 @@ int stage_divergence(Context& c) {
     for (int d = (dc >= 0 ? dc + 1 : 0); d <= D; d++) {
         int k = 1 << (D - d);
         const float* row = c.dDfT.p + c.tab.dfOffset[d];
-        int n = c.cnt[d];
+        // multi-GPU: at the sharded depths a rank only needs the right-hand side of its own rows
+        const bool sh = c.mg.active() && d >= c.shardFrom;
+        const int first = sh ? c.rowLo[d][c.mg.rank] : c.base[d];
+        const int n = sh ? c.rowLo[d][c.mg.rank + 1] - first : c.cnt[d];
+        if (n <= 0) continue;
         if (d == D)
-            PRB_LAUNCH(c, k_divergence_leaf, grid_for(c, n, 256), 256, 0, c.V.p, c.neighs.p, row, c.base[D], n, c.divg.p);
+            PRB_LAUNCH(c, k_divergence_leaf, grid_for(c, n, 256), 256, 0, c.V.p, c.neighs.p, row, c.base[D], first, n, c.divg.p);
         else if (d == D - 1)
-            PRB_LAUNCH(c, k_divergence_dm1, grid_for(c, n, 256), 256, 0, c.V.p, c.neighs.p, c.child0.p, row, c.base[d], n, c.base[D], c.divg.p);
-        else if (d >= D - 1)
-            PRB_LAUNCH(c, k_divergence<1>, grid_for(c, n, 256), 256, 0, c.V.p, c.offs.p, c.neighs.p, c.didx.p, c.dnum.p, row, c.base[d], n, c.base[D], k, c.divg.p);
+            PRB_LAUNCH(c, k_divergence_dm1, grid_for(c, n, 256), 256, 0, c.V.p, c.neighs.p, c.child0.p, row, first, n, c.base[D], c.divg.p);
         else
-            PRB_LAUNCH(c, k_divergence<32>, grid_for(c, (i64)n * 32, 256), 256, 0, c.V.p, c.offs.p, c.neighs.p, c.didx.p, c.dnum.p, row, c.base[d], n, c.base[D], k, c.divg.p);
+            PRB_LAUNCH(c, k_divergence<32>, grid_for(c, (i64)n * 32, 256), 256, 0, c.V.p, c.offs.p, c.neighs.p, c.didx.p, c.dnum.p, row, first, n, c.base[D], k, c.divg.p);
     }
     PRB_CUDA(cudaGetLastError());
     return PRB_OK;

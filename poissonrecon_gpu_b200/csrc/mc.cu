@@ -124,17 +124,35 @@ __global__ void __launch_bounds__(128) k_point_values(const float* __restrict__ 
     if (threadIdx.x == 0) atomicAdd(sum, red[0] + red[1] + red[2] + red[3]);
 }
 
+// multi-GPU: every rank writes its partial sum into slot 31 of every rank's header
+__global__ void k_mg_publish_sum(MgDev mg, const double* __restrict__ v) {
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        for (int r = 0; r < mg.world; r++) mg.peerHdr[r]->slots[0][mg.rank][31] = *v;
+}
+
 int stage_iso(Context& c) {
     cudaStream_t st = c.stream;
     PRB_TRY(c.pointValue.alloc((size_t)c.N, st));
     DBuf<double> sum;
     PRB_TRY(sum.alloc(1, st));
     PRB_CUDA(cudaMemsetAsync(sum.p, 0, sizeof(double), st));
-    PRB_LAUNCH(c, k_point_values, grid_for(c, c.N, 128, 16), 128, 0, c.P.p, c.p2n.p, c.N, c.base[c.D], c.neighs.p, c.parent.p, c.offs.p, c.xv, c.dBaseFn.p,
-               c.pointValue.p, sum.p);
+    // multi-GPU: the samples are split evenly; the partial sums meet in the arena header
+    const i64 p0 = c.mg.active() ? (c.N * c.mg.rank) / c.mg.world : 0, p1 = c.mg.active() ? (c.N * (c.mg.rank + 1)) / c.mg.world : c.N;
+    if (p1 > p0)
+        PRB_LAUNCH(c, k_point_values, grid_for(c, p1 - p0, 128, 16), 128, 0, c.P.p + 3 * p0, c.p2n.p + p0, p1 - p0, c.base[c.D], c.neighs.p, c.parent.p, c.offs.p, c.xv,
+                   c.dBaseFn.p, c.pointValue.p + p0, sum.p);
     double h = 0;
-    PRB_CUDA(cudaMemcpyAsync(&h, sum.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-    PRB_CUDA(cudaStreamSynchronize(st));
+    if (c.mg.active()) {
+        PRB_LAUNCH(c, k_mg_publish_sum, 1, 32, 0, c.mg.dev(), sum.p);
+        PRB_TRY(mg_barrier(c));
+        double parts[kMaxRanks][32];
+        PRB_CUDA(cudaMemcpyAsync(parts, &((MgHeader*)c.mg.arena)->slots[0][0][0], sizeof(parts), cudaMemcpyDeviceToHost, st));
+        PRB_CUDA(cudaStreamSynchronize(st));
+        for (int r = 0; r < c.mg.world; r++) h += parts[r][31];
+    } else {
+        PRB_CUDA(cudaMemcpyAsync(&h, sum.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        PRB_CUDA(cudaStreamSynchronize(st));
+    }
     // thrust::reduce(float) + "isoValue /= count" (main.cu:3494-3496)
     float iso = (float)h;
     iso /= (float)c.N;

@@ -1,0 +1,88 @@
+// Multi-GPU plumbing: peer-mapped arena (CUDA IPC), epoch-flag barrier, shard plan.
+// See the MgState comment in common.cuh for the model.  The reference is single-GPU
+// (devID = 0 hard-coded, CG_CUDA.cuh:356); this layer is new.
+#include "common.cuh"
+#include "mg_device.cuh"
+#include <cstring>
+
+namespace prb {
+
+__global__ void k_mg_barrier(MgDev mg, unsigned epoch) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) mg_signal_wait(mg, epoch);
+}
+
+int mg_barrier(Context& c) {
+    if (!c.mg.active()) return PRB_OK;
+    c.mg.epoch++;
+    PRB_LAUNCH(c, k_mg_barrier, 1, 32, 0, c.mg.dev(), c.mg.epoch);
+    return PRB_OK;
+}
+
+}  // namespace prb
+
+using namespace prb;
+
+extern "C" {
+
+int prb_mg_init(prb_context* h, int rank, int world, int64_t arena_bytes, void* handle_out /* 64 bytes */) {
+    if (!h || !handle_out || world < 1 || world > kMaxRanks || rank < 0 || rank >= world || arena_bytes < (int64_t)kMgHeaderBytes) {
+        set_error("prb_mg_init: bad argument (world <= 8, arena >= 16 KiB)");
+        return PRB_ERR_ARG;
+    }
+    Context& c = h->c;
+    PRB_CUDA(cudaSetDevice(c.device));
+    if (c.mg.arena) { set_error("prb_mg_init: already initialised"); return PRB_ERR_STATE; }
+    PRB_CUDA(cudaMalloc((void**)&c.mg.arena, (size_t)arena_bytes));
+    PRB_CUDA(cudaMemset(c.mg.arena, 0, kMgHeaderBytes));
+    c.mg.arenaBytes = (size_t)arena_bytes;
+    c.mg.rank = rank;
+    c.mg.world = world;
+    c.mg.peer[rank] = c.mg.arena;
+    c.mg.peerOpen[rank] = false;
+    c.mg.reset_allocs();
+    cudaIpcMemHandle_t hd;
+    PRB_CUDA(cudaIpcGetMemHandle(&hd, c.mg.arena));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::memcpy(handle_out, &hd, 64);
+    return PRB_OK;
+}
+
+int prb_mg_set_peer(prb_context* h, int peer_rank, const void* handle /* 64 bytes */) {
+    if (!h || !handle) return PRB_ERR_ARG;
+    Context& c = h->c;
+    if (!c.mg.arena || peer_rank < 0 || peer_rank >= c.mg.world) { set_error("prb_mg_set_peer: bad rank or prb_mg_init not called"); return PRB_ERR_ARG; }
+    if (peer_rank == c.mg.rank) return PRB_OK;
+    PRB_CUDA(cudaSetDevice(c.device));
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handle, 64);
+    void* p = nullptr;
+    PRB_CUDA(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    c.mg.peer[peer_rank] = (char*)p;
+    c.mg.peerOpen[peer_rank] = true;
+    return PRB_OK;
+}
+
+int prb_mg_barrier(prb_context* h) {
+    if (!h) return PRB_ERR_ARG;
+    Context& c = h->c;
+    PRB_CUDA(cudaSetDevice(c.device));
+    for (int r = 0; r < c.mg.world; r++)
+        if (!c.mg.peer[r]) { set_error("prb_mg_barrier: peer arena not set"); return PRB_ERR_STATE; }
+    PRB_TRY(mg_barrier(c));
+    PRB_CUDA(cudaStreamSynchronize(c.stream));
+    int err = 0;
+    PRB_CUDA(cudaMemcpy(&err, &((MgHeader*)c.mg.arena)->error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) { set_error("multi-GPU barrier timed out waiting for a peer"); return PRB_ERR_CUDA; }
+    return PRB_OK;
+}
+
+// Host-only shard plan (no GPU needed): splits `count` units into `world` contiguous chunks of
+// (nearly) equal size; out[r] = first unit of rank r, out[world] = count.  Every rank computes the
+// same plan from the same replicated counts.
+int prb_mg_plan(int64_t count, int world, int64_t* out) {
+    if (!out || world < 1 || world > kMaxRanks || count < 0) { set_error("prb_mg_plan: bad argument"); return PRB_ERR_ARG; }
+    for (int r = 0; r <= world; r++) out[r] = (count * r) / world;
+    return PRB_OK;
+}
+
+}  // extern "C"

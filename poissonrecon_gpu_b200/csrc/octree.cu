@@ -235,6 +235,24 @@ __global__ void __launch_bounds__(256) k_sg_table(const int* __restrict__ parent
         sgTab[t] = out;
     }
 }
+// first node of every rank's share at the sharded depths: the first existing sibling group at or
+// after the rank's first super-group (interior table entries in child order)
+__global__ void k_shard_rows(const int* __restrict__ sgTab, const int* __restrict__ sgLo /* [(D+2)][kMaxRanks+1] */, const int* __restrict__ sgEnd,
+                             const int* __restrict__ baseNext, int D, int world, int* __restrict__ rowLo) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (D + 2) * (kMaxRanks + 1)) return;
+    int d = t / (kMaxRanks + 1), r = t % (kMaxRanks + 1);
+    if (d < 1 || d > D || r > world) { rowLo[t] = 0; return; }
+    int sg = sgLo[t], out = baseNext[d];
+    if (sg < sgEnd[d]) {
+        const int idx[8] = {21, 22, 25, 26, 37, 38, 41, 42};
+        for (int k = 0; k < 8; k++) {
+            int v = sgTab[64 * (i64)sg + idx[k]];
+            if (v >= 0) { out = v; break; }
+        }
+    }
+    rowLo[t] = out;
+}
 __global__ void __launch_bounds__(256) k_point_to_leaf(const int* __restrict__ flag, const int* __restrict__ excl, const int* __restrict__ slotD, i64 n, int* __restrict__ p2n) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
         p2n[i] = slotD[excl[i] + flag[i] - 1];
@@ -369,6 +387,43 @@ int stage_octree(Context& c) {
     c.nSg = 1 + (c.base[D] - 1) / 8;
     PRB_TRY(c.sgTab.alloc(64 * (size_t)c.nSg, st));
     PRB_LAUNCH(c, k_sg_table, grid_for(c, (i64)c.nSg * 64, 256), 256, 0, c.parent.p, c.child0.p, c.neighs.p, c.nSg, c.sgTab.p);
+    // ---- multi-GPU shard plan: depths with at least minShardRows nodes (and every deeper one) are
+    // split into contiguous super-group ranges, the shallower ones are replicated on every rank
+    {
+        const int W = c.mg.world;
+        c.shardFrom = D + 1;
+        if (c.mg.active())
+            for (int d = D; d >= 2 && c.cnt[d] >= c.mg.minShardRows; --d) c.shardFrom = d;
+        int sgStart[kMaxDepth + 2];
+        sgStart[0] = sgStart[1] = 0;
+        for (int d = 2; d <= D + 1; d++) sgStart[d] = 1 + (c.base[d - 1] - 1) / 8;
+        for (int d = 0; d <= D + 1; d++)
+            for (int r = 0; r <= kMaxRanks; r++) { c.sgLo[d][r] = 0; c.rowLo[d][r] = 0; }
+        for (int d = 1; d <= D; d++) {
+            const i64 n = sgStart[d + 1] - sgStart[d];
+            for (int r = 0; r <= W; r++) {
+                c.sgLo[d][r] = d >= c.shardFrom ? sgStart[d] + (int)((n * r) / W) : (r == 0 ? sgStart[d] : sgStart[d + 1]);
+                c.rowLo[d][r] = r == 0 ? c.base[d] : c.base[d + 1];
+            }
+        }
+        if (c.shardFrom <= D) {
+            DBuf<int> dSgLo, dSgEnd, dBaseNext, dRowLo;
+            const int nt = (D + 2) * (kMaxRanks + 1);
+            PRB_TRY(dSgLo.alloc(nt, st)); PRB_TRY(dRowLo.alloc(nt, st)); PRB_TRY(dSgEnd.alloc(kMaxDepth + 2, st)); PRB_TRY(dBaseNext.alloc(kMaxDepth + 2, st));
+            int hEnd[kMaxDepth + 2] = {0}, hNext[kMaxDepth + 2] = {0};
+            for (int d = 1; d <= D; d++) { hEnd[d] = sgStart[d + 1]; hNext[d] = c.base[d + 1]; }
+            PRB_CUDA(cudaMemcpyAsync(dSgLo.p, &c.sgLo[0][0], sizeof(int) * nt, cudaMemcpyHostToDevice, st));
+            PRB_CUDA(cudaMemcpyAsync(dSgEnd.p, hEnd, sizeof(hEnd), cudaMemcpyHostToDevice, st));
+            PRB_CUDA(cudaMemcpyAsync(dBaseNext.p, hNext, sizeof(hNext), cudaMemcpyHostToDevice, st));
+            PRB_LAUNCH(c, k_shard_rows, 1, 256, 0, c.sgTab.p, dSgLo.p, dSgEnd.p, dBaseNext.p, D, W, dRowLo.p);
+            int hRow[kMaxDepth + 2][kMaxRanks + 1];
+            PRB_CUDA(cudaMemcpyAsync(&hRow[0][0], dRowLo.p, sizeof(int) * nt, cudaMemcpyDeviceToHost, st));
+            PRB_CUDA(cudaStreamSynchronize(st));
+            for (int d = c.shardFrom; d <= D; d++)
+                for (int r = 0; r <= W; r++) c.rowLo[d][r] = hRow[d][r];
+            dSgLo.release(); dSgEnd.release(); dBaseNext.release(); dRowLo.release();
+        }
+    }
     flagN.release(); exclN.release();
     for (int d = 0; d <= D; d++) { lkey[d].release(); fp[d].release(); fc[d].release(); fdm1[d].release(); prank[d].release(); slot[d].release(); }
     PRB_CUDA(cudaGetLastError());

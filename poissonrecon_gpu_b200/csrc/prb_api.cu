@@ -41,9 +41,6 @@ int upload_tables(Context& c) {
 
 using namespace prb;
 
-struct prb_context {
-    Context c;
-};
 
 extern "C" {
 
@@ -91,6 +88,9 @@ void prb_destroy(prb_context* h) {
     c.wsVal7.release(); c.wsLow.release(); c.wsCat.release(); c.wsNtri.release(); c.wsEmask.release(); c.wsVbase.release(); c.wsTbase.release();
     c.dMaxDepthFn.release(); c.dBaseFn.release(); c.dDfT.release(); c.dDfOffset.release(); c.dStencil.release();
     cudaStreamSynchronize(c.stream);
+    for (int r = 0; r < kMaxRanks; r++)
+        if (c.mg.peerOpen[r] && c.mg.peer[r]) cudaIpcCloseMemHandle(c.mg.peer[r]);
+    if (c.mg.arena) cudaFree(c.mg.arena);
     c.hMeshV.release(); c.hMeshT.release();
     for (auto& e : c.ev) cudaEventDestroy(e);
     cudaStreamDestroy(c.stream);
@@ -113,6 +113,8 @@ int prb_set_points(prb_context* h, const float* xyz, const float* normals, int64
     Context& c = h->c;
     PRB_CUDA(cudaSetDevice(c.device));
     release_all(c);
+    c.mg.reset_allocs();
+    c.mgP = c.mgX = nullptr;
     c.N = n;
     c.launches = 0;
     PRB_CUDA(cudaEventRecord(c.ev[0], c.stream));

@@ -26,6 +26,7 @@
 // Algorithmic bytes per row per iteration: 57.5 B
 //   (p=r+beta*p: 12, SpMV: 13.5 + 4 + 4, x/r update: 24).
 #include "common.cuh"
+#include "mg_device.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -55,7 +56,43 @@ struct CgParams {
     float* resOut;                 // [D+1] final r.r
     float tol2;
     int maxIter;
+    // ---- multi-GPU (world == 1: everything below is unused).  Depths >= shardFrom are split by
+    // super-group range; a rank updates only its rows and reads the p blocks of other ranks
+    // straight from their (peer-mapped) arenas; dot products and phase boundaries go through
+    // the arena header (mg_device.cuh).  Shallower depths are solved redundantly on every rank
+    // with rank 0's dot products so that all ranks take identical steps.
+    int world, rank, shardFrom;
+    int sg0[kMaxDepth + 2], sg1[kMaxDepth + 2];       // this rank's super-group range per depth
+    int row0[kMaxDepth + 2], row1[kMaxDepth + 2];     // this rank's node range per depth
+    int rowLo[kMaxDepth + 2][kMaxRanks + 1];          // node ranges of all ranks (sharded depths)
+    const float* peerP[kMaxRanks];
+    MgDev mg;
+    unsigned epoch0;
 };
+
+// grid-wide (world == 1) or box-wide barrier.  kind: -1 none, 0/1 = publish this rank's per-depth
+// partial sums `local[1..D]` to every rank's slot table before signalling.
+__device__ __forceinline__ void cg_sync(cg::grid_group& grid, const CgParams& P, unsigned& epoch, int parity, int kind, const double* local) {
+    grid.sync();
+    if (P.world == 1) return;
+    epoch++;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (kind >= 0)
+            for (int r = 0; r < P.world; r++)
+                for (int d = 1; d <= P.D; d++) P.mg.peerHdr[r]->slots[parity][P.rank][kind * 16 + d] = local[d];
+        mg_signal_wait(P.mg, epoch);
+    }
+    grid.sync();
+}
+// total of a per-depth dot product after cg_sync
+__device__ __forceinline__ double cg_total(const CgParams& P, int parity, int kind, int d, const double* local) {
+    if (P.world == 1) return local[d];
+    const volatile double* s = &P.mg.hdr->slots[parity][0][kind * 16 + d];
+    if (d < P.shardFrom) return s[0];
+    double t = 0.0;
+    for (int r = 0; r < P.world; r++) t += s[r * 32];
+    return t;
+}
 
 __device__ __forceinline__ void cp_async16(unsigned smemAddr, const void* gptr, int srcBytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smemAddr), "l"(gptr), "r"(srcBytes) : "memory");
@@ -115,7 +152,7 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
     {
         // b (the divergence) is an unpadded array, so its quads are not 16-byte aligned: scalar loads
         for (int d = 1; d <= D; d++) {
-            const int i0 = 1 + 8 * P.gbase[d], i1 = 1 + 8 * P.gbase[d + 1];
+            const int i0 = P.row0[d], i1 = P.row1[d];
             double part = 0.0;
             for (int i = i0 + gthread; i < i1; i += nthreads) {
                 float bv = P.b[i];
@@ -127,9 +164,10 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
         __syncthreads();
         if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&P.dots[64 + tid], sAcc[tid]);   // dedicated init buffer
     }
-    grid.sync();
+    unsigned epoch = P.epoch0;
+    cg_sync(grid, P, epoch, 0, 0, P.dots + 64);
     if (tid >= 1 && tid <= D) {
-        float r1 = (float)P.dots[64 + tid];
+        float r1 = (float)cg_total(P, 0, 0, tid, P.dots + 64);
         sR1[tid] = r1; sIter[tid] = 1; sBeta[tid] = 0.f; sAlpha[tid] = 0.f;
         sActive[tid] = (r1 > P.tol2 && 1 <= P.maxIter) ? 1 : 0;
     }
@@ -178,9 +216,8 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
         for (int d = 1; d <= D; d++) {
             if (!sActive[d]) continue;
             const float be = sBeta[d];
-            const int q1 = 2 * P.gbase[d + 1];
-            for (int q = 2 * P.gbase[d] + gthread; q < q1; q += nthreads) {
-                const int i = 1 + 4 * q;
+            const int i1 = P.row1[d];
+            for (int i = P.row0[d] + 4 * gthread; i < i1; i += 4 * nthreads) {
                 float4 rv = *reinterpret_cast<const float4*>(P.r + i);
                 float4 pv = *reinterpret_cast<const float4*>(P.p + i);
                 pv.x = __fadd_rn(rv.x, __fmul_rn(be, pv.x));
@@ -190,13 +227,22 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
                 *reinterpret_cast<float4*>(P.p + i) = pv;
             }
         }
-        grid.sync();
+        cg_sync(grid, P, epoch, cur, -1, nullptr);
         // ---------------- phase A: Ap = A p ; p.Ap
         for (int d = 1; d <= D; d++) {
             if (!sActive[d]) continue;
             const float s0 = sSt[d][0], s1 = sSt[d][1], s2 = sSt[d][2], s3 = sSt[d][3];
-            const int t1 = P.sgStart[d + 1];
-            int t = P.sgStart[d] + gwarp;
+            const int t1 = P.sg1[d];
+            int t = P.sg0[d] + gwarp;
+            const bool remote = P.world > 1 && d >= P.shardFrom;
+            const int myLo = P.row0[d], myHi = P.row1[d];
+            // source of a block: this rank's p, or the owner's through its peer-mapped arena
+            auto src = [&](int base) -> const float* {
+                if (!remote || (base >= myLo && base < myHi)) return P.p + base;
+                int r = 0;
+                while (r + 1 < P.world && base >= P.rowLo[d][r + 1]) r++;
+                return P.peerP[r] + base;
+            };
             double part = 0.0;
             // table registers of the current tile (A), the next (B) and the one after (C)
             int a0 = -1, a1 = -1, b0 = -1, b1 = -1;
@@ -207,7 +253,7 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     int base = __shfl_sync(0xffffffffu, k < 2 ? a0 : a1, ((lane >> 1) + 16 * k) & 31);
-                    cp_async16(cubeS + 4u * (unsigned)stOff[k], base >= 0 ? (const void*)(P.p + base + 4 * (lane & 1)) : (const void*)(P.p + 1), base >= 0 ? 16 : 0);
+                    cp_async16(cubeS + 4u * (unsigned)stOff[k], base >= 0 ? (const void*)(src(base) + 4 * (lane & 1)) : (const void*)(P.p + 1), base >= 0 ? 16 : 0);
                 }
             }
             cp_async_commit();
@@ -218,7 +264,7 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         int base = __shfl_sync(0xffffffffu, k < 2 ? b0 : b1, ((lane >> 1) + 16 * k) & 31);
-                        cp_async16(cubeS + 4u * (unsigned)((buf ^ 1) * kCube + stOff[k]), base >= 0 ? (const void*)(P.p + base + 4 * (lane & 1)) : (const void*)(P.p + 1),
+                        cp_async16(cubeS + 4u * (unsigned)((buf ^ 1) * kCube + stOff[k]), base >= 0 ? (const void*)(src(base) + 4 * (lane & 1)) : (const void*)(P.p + 1),
                                    base >= 0 ? 16 : 0);
                     }
                     if (t + 2 * nwarps < t1) { c0 = P.sgTab[64 * (i64)(t + 2 * nwarps) + lane]; c1 = P.sgTab[64 * (i64)(t + 2 * nwarps) + 32 + lane]; }
@@ -257,21 +303,20 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
         }
         __syncthreads();
         if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&dPAp[tid], sAcc[tid]);
-        grid.sync();
+        cg_sync(grid, P, epoch, cur, 0, dPAp);
         // both accumulators of the NEXT iteration are zeroed here: every block has passed this
         // iteration's syncs, hence finished reading them after the previous iteration's syncs
         if (blockIdx.x == 0 && tid < 32) P.dots[nxt * 32 + tid] = 0.0;
         if (tid <= D) sAcc[tid] = 0.0;
-        if (tid >= 1 && tid <= D && sActive[tid]) sAlpha[tid] = (float)((double)sR1[tid] / dPAp[tid]);
+        if (tid >= 1 && tid <= D && sActive[tid]) sAlpha[tid] = (float)((double)sR1[tid] / cg_total(P, cur, 0, tid, dPAp));
         __syncthreads();
         // ---------------- phase B: x += alpha p ; r -= alpha Ap ; r.r
         for (int d = 1; d <= D; d++) {
             if (!sActive[d]) continue;
             const float al = sAlpha[d];
-            const int q1 = 2 * P.gbase[d + 1];
+            const int i1 = P.row1[d];
             double part = 0.0;
-            for (int q = 2 * P.gbase[d] + gthread; q < q1; q += nthreads) {
-                const int i = 1 + 4 * q;
+            for (int i = P.row0[d] + 4 * gthread; i < i1; i += 4 * nthreads) {
                 float4 pv = *reinterpret_cast<const float4*>(P.p + i);
                 float4 av = *reinterpret_cast<const float4*>(P.Ap + i);
                 float4 xv = *reinterpret_cast<const float4*>(P.x + i);
@@ -289,9 +334,9 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
         }
         __syncthreads();
         if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&dRRn[tid], sAcc[tid]);
-        grid.sync();
+        cg_sync(grid, P, epoch, cur, 1, dRRn);
         if (tid >= 1 && tid <= D && sActive[tid]) {
-            float r0 = sR1[tid], r1 = (float)dRRn[tid];
+            float r0 = sR1[tid], r1 = (float)cg_total(P, cur, 1, tid, dRRn);
             sR1[tid] = r1;
             int k = sIter[tid] + 1;
             sIter[tid] = k;
@@ -301,6 +346,7 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
         __syncthreads();
     }
     if (blockIdx.x == 0 && tid >= 1 && tid <= D) { P.itersOut[tid] = sIter[tid] - 1; P.resOut[tid] = sR1[tid]; }
+    if (blockIdx.x == 0 && tid == 0) P.itersOut[15] = (int)epoch;
 }
 
 int stage_solve(Context& c) {
@@ -308,13 +354,30 @@ int stage_solve(Context& c) {
     cudaStream_t st = c.stream;
     // vectors are padded by 7 floats so that node 1 (the first sibling block) is 32-byte aligned
     const size_t padN = (size_t)M + 8;
-    PRB_TRY(c.x.alloc(padN, st));
-    c.xv = c.x.p + 7;
+    const bool mg = c.mg.active();
+    float* pBuf = nullptr;
     DBuf<float> r, p, Ap, resOut;
+    if (mg) {
+        // x and p live in the peer-mapped arena: p is read by the other ranks during the solve,
+        // x is collected from them afterwards
+        for (int q = 0; q < c.mg.world; q++)
+            if (!c.mg.peer[q]) { set_error("multi-GPU: peer arenas not exchanged (prb_mg_set_peer)"); return PRB_ERR_STATE; }
+        if (!c.mgX) {
+            c.mgX = c.mg.alloc<float>(padN, &c.mgXOff);
+            c.mgP = c.mg.alloc<float>(padN, &c.mgPOff);
+            if (!c.mgX || !c.mgP) { set_error("multi-GPU arena too small for the CG vectors (prb_mg_init arena_bytes)"); return PRB_ERR_NOMEM; }
+        }
+        c.xv = c.mgX + 7;
+        pBuf = c.mgP;
+    } else {
+        PRB_TRY(c.x.alloc(padN, st));
+        c.xv = c.x.p + 7;
+        PRB_TRY(p.alloc(padN, st));
+        pBuf = p.p;
+    }
     DBuf<double> dots;
     DBuf<int> itersOut;
     PRB_TRY(r.alloc(padN, st));
-    PRB_TRY(p.alloc(padN, st));
     PRB_TRY(Ap.alloc(padN, st));
     PRB_TRY(dots.alloc(96, st));
     PRB_TRY(itersOut.alloc(16, st));
@@ -330,7 +393,21 @@ int stage_solve(Context& c) {
     P.sgStart[1] = 0;
     for (int d = 2; d <= D + 1; d++) P.sgStart[d] = 1 + P.gbase[d - 1];
     P.sgTab = c.sgTab.p; P.stencil = c.dStencil.p; P.b = c.divg.p;
-    P.x = c.xv; P.r = r.p + 7; P.p = p.p + 7; P.Ap = Ap.p + 7;
+    P.x = c.xv; P.r = r.p + 7; P.p = pBuf + 7; P.Ap = Ap.p + 7;
+    P.world = c.mg.world; P.rank = c.mg.rank; P.shardFrom = mg ? c.shardFrom : D + 1;
+    for (int d = 0; d <= D + 1; d++) {
+        const bool sh = mg && d >= c.shardFrom && d <= D;
+        P.sg0[d] = sh ? c.sgLo[d][c.mg.rank] : P.sgStart[d];
+        P.sg1[d] = sh ? c.sgLo[d][c.mg.rank + 1] : (d <= D ? P.sgStart[d + 1] : P.sgStart[d]);
+        P.row0[d] = sh ? c.rowLo[d][c.mg.rank] : (d <= D ? c.base[d] : 0);
+        P.row1[d] = sh ? c.rowLo[d][c.mg.rank + 1] : (d <= D ? c.base[d + 1] : 0);
+        for (int q = 0; q <= kMaxRanks; q++) P.rowLo[d][q] = c.rowLo[d][q];
+    }
+    for (int q = 0; q < kMaxRanks; q++) P.peerP[q] = (mg && q < c.mg.world) ? (const float*)(c.mg.peer[q] + c.mgPOff) + 7 : nullptr;
+    P.mg = c.mg.dev();
+    P.epoch0 = c.mg.epoch;
+    if (mg) PRB_TRY(mg_barrier(c));        // every rank's previous use of the arena buffers is over before anyone writes p / x again
+    P.epoch0 = c.mg.epoch;
     P.dots = dots.p; P.itersOut = itersOut.p; P.resOut = resOut.p;
     float tol = (float)c.cgTol;
     P.tol2 = tol * tol;
@@ -354,7 +431,25 @@ int stage_solve(Context& c) {
     PRB_CUDA(cudaMemcpyAsync(hIters, itersOut.p, sizeof(hIters), cudaMemcpyDeviceToHost, st));
     PRB_CUDA(cudaStreamSynchronize(st));
     c.cgRowIters = 0;
-    for (int d = 0; d <= D; d++) { c.cgIters[d] = hIters[d]; c.cgRowIters += (i64)c.cnt[d] * hIters[d]; }
+    for (int d = 0; d <= D; d++) { c.cgIters[d] = hIters[d]; c.cgRowIters += (i64)(P.row1[d] - P.row0[d]) * hIters[d]; }
+    if (mg) {
+        c.mg.epoch = (unsigned)hIters[15];
+        // collect the other ranks' parts of the solution (pull over NVLink), then let nobody run ahead
+        PRB_TRY(mg_barrier(c));
+        for (int q = 0; q < c.mg.world; q++) {
+            if (q == c.mg.rank) continue;
+            const float* px = (const float*)(c.mg.peer[q] + c.mgXOff) + 7;
+            for (int d = c.shardFrom; d <= D; d++) {
+                size_t n = (size_t)(c.rowLo[d][q + 1] - c.rowLo[d][q]);
+                if (n) PRB_CUDA(cudaMemcpyAsync(c.xv + c.rowLo[d][q], px + c.rowLo[d][q], n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            }
+        }
+        PRB_TRY(mg_barrier(c));
+        int err = 0;
+        PRB_CUDA(cudaMemcpyAsync(&err, &((MgHeader*)c.mg.arena)->error, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PRB_CUDA(cudaStreamSynchronize(st));
+        if (err) { set_error("multi-GPU solve: timed out waiting for a peer"); return PRB_ERR_CUDA; }
+    }
     r.release(); p.release(); Ap.release(); dots.release(); itersOut.release(); resOut.release();
     return PRB_OK;
 }
