@@ -12,6 +12,8 @@
 // scans.  Vertex and triangle ORDER equal the reference's (edges by owner cell then edge kind;
 // triangles by cell then case-table order), so meshes compare index by index.
 #include "common.cuh"
+#include "mg_device.cuh"
+#include <algorithm>
 #include "mc_case_table.h"
 #include "scan.cuh"
 
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(128) k_vertex_values(Topo T, int M, int D, con
 // its owner cell).  Each lane still adds its terms in the reference's order: own level, parents
 // up to the root, then the finer nodes at that corner (main.cu:2277-2322).
 constexpr int kVvWarps = 8;
-__global__ void __launch_bounds__(kVvWarps * 32) k_vertex_values_grouped(Topo T, int nGroups, int D, const int* __restrict__ parent, const int* __restrict__ child0,
+__global__ void __launch_bounds__(kVvWarps * 32) k_vertex_values_grouped(Topo T, int gFirst, int nGroups, int D, const int* __restrict__ parent, const int* __restrict__ child0,
                                                                          const ushort4* __restrict__ offs, const float* __restrict__ x,
                                                                          const float* __restrict__ baseFn, float iso, float* __restrict__ vval) {
     __shared__ float sX[kVvWarps][27];
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(kVvWarps * 32) k_vertex_values_grouped(Topo T,
     __shared__ float sB0[kVvWarps][3][3][4];     // own level: [axis][point coordinate][cube coordinate]
     const int exceedTab[8] = {0, 1, 3, 2, 4, 5, 7, 6};     // childrenVertexKind, MarchingCubes.cuh:721-723 (applied as the reference does)
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    for (int g = blockIdx.x * kVvWarps + wp; g < nGroups; g += gridDim.x * kVvWarps) {
+    for (int g = gFirst + blockIdx.x * kVvWarps + wp; g < gFirst + nGroups; g += gridDim.x * kVvWarps) {
         const int gb = 1 + 8 * g;                // first sibling (root vertices are dropped, main.cu:1634-1638)
         const ushort4 o0 = offs[gb];
         const int d0 = o0.w;
@@ -679,14 +681,14 @@ __global__ void __launch_bounds__(256) k_rv_roots(int nr, int rd, int M, const i
 }
 
 
-__global__ void __launch_bounds__(512) k_rv_brick_values(RGeom G) {
+__global__ void __launch_bounds__(512) k_rv_brick_values(RGeom G, unsigned brick0) {
     __shared__ float sX[kMaxDepth + 1][27];
     __shared__ float sBv[3][kMaxDepth + 1][3][8];
     __shared__ int sIds[27];
     __shared__ int sAny[kMaxDepth + 1];
     __shared__ int sNeedFine;
     const int tid = threadIdx.x;
-    const i64 cell0 = (i64)blockIdx.x * 512;
+    const i64 cell0 = ((i64)blockIdx.x + brick0) * 512;
     const int r = (int)(cell0 / G.per);
     const unsigned l0 = (unsigned)(cell0 - (i64)r * G.per);
     const int L = G.D - 3;                                   // level of the brick
@@ -1068,12 +1070,20 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     DBuf<int> rootNb;
     DBuf<float> rootX;
     DBuf<int>&vbase = c.wsVbase, &tbase = c.wsTbase;
-    DBuf<float>&val7 = c.wsVal7, &low = c.wsLow;
+    DBuf<float>& low = c.wsLow;
+    const bool mg = c.mg.active();
     DBuf<unsigned char>&cat = c.wsCat, &ntri = c.wsNtri;
     DBuf<unsigned short>& emask = c.wsEmask;
     PRB_TRY(rootNb.alloc(27 * (size_t)nr, st));
     PRB_TRY(rootX.alloc((size_t)nr * (rd + 1) * 27, st));
-    PRB_TRY(val7.ensure((size_t)total, st));
+    float* val7p = nullptr;
+    if (mg) {
+        if (!c.mgVal7 || (size_t)total > c.mgVal7Cap) { set_error("multi-GPU arena too small for the refinement pass values"); return PRB_ERR_NOMEM; }
+        val7p = c.mgVal7;
+    } else {
+        PRB_TRY(c.wsVal7.ensure((size_t)total, st));
+        val7p = c.wsVal7.p;
+    }
     PRB_TRY(low.ensure((size_t)nr * 3 * n1 * n1, st));
     PRB_LAUNCH(c, k_set_rootmap, grid_for(c, nr, 256), 256, 0, dRoots, nr, 0, 0, rootMap.p);
     PRB_LAUNCH(c, k_rv_roots, div_up((i64)nr * 32, 256), 256, 0, nr, rd, c.M, dRoots, rootMap.p, c.neighs.p, c.parent.p, c.xv, rootNb.p, rootX.p);
@@ -1081,8 +1091,24 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     RGeom G;
     G.M = c.M; G.D = D; G.rd = rd; G.lv = lv; G.n = n; G.nr = nr; G.per = per;
     G.roots = dRoots; G.rootNb = rootNb.p; G.rootX = rootX.p; G.offs = c.offs.p; G.child0 = c.child0.p; G.x = c.xv; G.baseFn = c.dBaseFn.p;
-    G.iso = c.iso; G.val7 = val7.p; G.low = low.p;
-    PRB_LAUNCH(c, k_rv_brick_values, (unsigned)(total / 512), 512, 0, G);
+    G.iso = c.iso; G.val7 = val7p; G.low = low.p;
+    {
+        // multi-GPU: the bricks of the pass are split evenly, the other ranks' values are pulled over NVLink
+        const i64 nBricks = total / 512;
+        const int W = c.mg.world, me = c.mg.rank;
+        const i64 b0 = mg ? (nBricks * me) / W : 0, b1 = mg ? (nBricks * (me + 1)) / W : nBricks;
+        if (b1 > b0) PRB_LAUNCH(c, k_rv_brick_values, (unsigned)(b1 - b0), 512, 0, G, (unsigned)b0);
+        if (mg) {
+            PRB_TRY(mg_barrier(c));
+            for (int q = 0; q < W; q++) {
+                if (q == me) continue;
+                const i64 a = (nBricks * q) / W, b = (nBricks * (q + 1)) / W;
+                const float* src = (const float*)(c.mg.peer[q] + c.mgVal7Off);
+                if (b > a) PRB_CUDA(cudaMemcpyAsync(val7p + 512 * a, src + 512 * a, sizeof(float) * 512 * (size_t)(b - a), cudaMemcpyDeviceToDevice, st));
+            }
+            PRB_TRY(mg_barrier(c));     // nobody overwrites its values (next pass) while a peer still reads them
+        }
+    }
     PRB_LAUNCH(c, k_rv_low_values, grid_for(c, (i64)nr * 3 * n1 * n1, 128, 16), 128, 0, G);
     PRB_TRY(cat.ensure((size_t)total, st));
     PRB_TRY(ntri.ensure((size_t)total, st));
@@ -1167,12 +1193,33 @@ int stage_extract(Context& c) {
     c.hMeshValid = false;
     Topo R;
     R.nbr = c.neighs.p; R.rowBase = 0; R.minId = 0; R.cellBase = c.base[D]; R.nCells = c.cnt[D];
-    PRB_TRY(c.vval.alloc(8 * (size_t)M, st));
+    const bool mg = c.mg.active();
+    if (mg) {
+        if (!c.mgVval) c.mgVval = c.mg.alloc<float>(8 * (size_t)M, &c.mgVvalOff);
+        if (!c.mgVval) { set_error("multi-GPU arena too small for the corner values (32 bytes per node)"); return PRB_ERR_NOMEM; }
+        c.vvalPtr = c.mgVval;
+    } else {
+        PRB_TRY(c.vval.alloc(8 * (size_t)M, st));
+        c.vvalPtr = c.vval.p;
+    }
     {
-        const int nGroups = (M - 1) / 8;
-        if (nGroups > 0)
-            PRB_LAUNCH(c, k_vertex_values_grouped, grid_for(c, (i64)nGroups * 32, kVvWarps * 32, 8), kVvWarps * 32, 0, R, nGroups, D, c.parent.p, c.child0.p, c.offs.p, c.xv,
-                       c.dBaseFn.p, c.iso, c.vval.p);
+        // multi-GPU: the sibling groups are split evenly; every rank then pulls the other ranks' values over NVLink
+        const i64 nGroups = (M - 1) / 8;
+        const int W = c.mg.world, me = c.mg.rank;
+        const int g0 = mg ? (int)((nGroups * me) / W) : 0, g1 = mg ? (int)((nGroups * (me + 1)) / W) : (int)nGroups;
+        if (g1 > g0)
+            PRB_LAUNCH(c, k_vertex_values_grouped, grid_for(c, (i64)(g1 - g0) * 32, kVvWarps * 32, 8), kVvWarps * 32, 0, R, g0, g1 - g0, D, c.parent.p, c.child0.p, c.offs.p,
+                       c.xv, c.dBaseFn.p, c.iso, c.vvalPtr);
+        if (mg) {
+            PRB_TRY(mg_barrier(c));
+            for (int q = 0; q < W; q++) {
+                if (q == me) continue;
+                const i64 a = (nGroups * q) / W, b = (nGroups * (q + 1)) / W;
+                const float* src = (const float*)(c.mg.peer[q] + c.mgVvalOff);
+                if (b > a) PRB_CUDA(cudaMemcpyAsync(c.vvalPtr + 8 * (1 + 8 * a), src + 8 * (1 + 8 * a), sizeof(float) * 64 * (size_t)(b - a), cudaMemcpyDeviceToDevice, st));
+            }
+            PRB_TRY(mg_barrier(c));
+        }
     }
     DBuf<unsigned> fmark;
     PRB_TRY(fmark.alloc((size_t)M, st));
@@ -1180,14 +1227,14 @@ int stage_extract(Context& c) {
     std::vector<PassOut> outs;
     outs.reserve(64);
     outs.emplace_back();
-    PRB_TRY(run_mc_on_cells(c, R, c.vval.p, 0, c.offs.p + c.base[D], true, fmark.p, outs.back()));
+    PRB_TRY(run_mc_on_cells(c, R, c.vvalPtr, 0, c.offs.p + c.base[D], true, fmark.p, outs.back()));
     c.passes.push_back({0, outs.back().nv, outs.back().nt});
     // ---- leaves to refine
     const int nUpper = c.base[D];
     DBuf<int> flag, excl, subIds;
     PRB_TRY(flag.alloc((size_t)nUpper, st));
     PRB_TRY(excl.alloc((size_t)nUpper, st));
-    PRB_LAUNCH(c, k_find_subdivide, grid_for(c, nUpper, 128, 16), 128, 0, R, nUpper, c.child0.p, c.vval.p, fmark.p, flag.p);
+    PRB_LAUNCH(c, k_find_subdivide, grid_for(c, nUpper, 128, 16), 128, 0, R, nUpper, c.child0.p, c.vvalPtr, fmark.p, flag.p);
     i64 nSub = 0;
     PRB_TRY(exclusive_scan(c, flag.p, excl.p, nUpper, &nSub));
     PRB_TRY(subIds.alloc((size_t)nSub, st));
@@ -1213,6 +1260,20 @@ int stage_extract(Context& c) {
             firstOfDepth[D + 1] = (int)nSub;
         }
         const int finerDepth = 3;    // main.cu:3886
+        if (mg && !c.mgVal7) {
+            // one arena buffer for the values of the largest implicit pass (same size on every rank)
+            i64 maxTotal = 0;
+            for (int d = 1; d < D; d++) {
+                if (D - d < 3 || D - d > 10) continue;
+                i64 nr = (d < finerDepth) ? (firstOfDepth[d + 1] > firstOfDepth[d] ? 1 : 0) : (firstOfDepth[d + 1] - firstOfDepth[d]);
+                maxTotal = std::max(maxTotal, nr << (3 * (D - d)));
+            }
+            if (maxTotal > 0) {
+                c.mgVal7 = c.mg.alloc<float>((size_t)maxTotal, &c.mgVal7Off);
+                if (!c.mgVal7) { set_error("multi-GPU arena too small for the refinement pass values (4 bytes per virtual cell of the largest pass)"); return PRB_ERR_NOMEM; }
+                c.mgVal7Cap = (size_t)maxTotal;
+            }
+        }
         for (int d = 1; d < finerDepth && d < D; d++)                      // coarse roots: one pass each (main.cu:3887-4202)
             for (int q = firstOfDepth[d]; q < firstOfDepth[d + 1]; q++) PRB_TRY(refine_pass(c, subIds.p + q, 1, d, true, rootMap, outs));
         for (int d = finerDepth; d < D; d++)                               // batched per depth (main.cu:4211-4561)

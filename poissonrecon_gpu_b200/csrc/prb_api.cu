@@ -114,7 +114,9 @@ int prb_set_points(prb_context* h, const float* xyz, const float* normals, int64
     PRB_CUDA(cudaSetDevice(c.device));
     release_all(c);
     c.mg.reset_allocs();
-    c.mgP = c.mgX = nullptr;
+    c.mgP = c.mgX = c.mgVval = c.mgVal7 = nullptr;
+    c.mgVal7Cap = 0;
+    c.vvalPtr = nullptr;
     c.N = n;
     c.launches = 0;
     PRB_CUDA(cudaEventRecord(c.ev[0], c.stream));
@@ -295,7 +297,7 @@ int64_t prb_get_array(prb_context* h, const char* name, void* dst, int64_t cap) 
     else if (s == "divergence") D_(c.divg.p, c.divg.bytes());
     else if (s == "x") D_(c.xv, c.xv ? 4 * (size_t)M : 0);
     else if (s == "pointvalue") D_(c.pointValue.p, c.pointValue.bytes());
-    else if (s == "vvalue_slots") D_(c.vval.p, c.vval.bytes());
+    else if (s == "vvalue_slots") D_(c.vvalPtr, c.vvalPtr ? 32 * (size_t)M : 0);
     else if (s == "mesh_v") D_(c.meshV.p, 12 * (size_t)c.nMeshV);
     else if (s == "mesh_t") D_(c.meshT.p, 12 * (size_t)c.nMeshT);
     else if (s == "iso") H_(&c.iso, 4);

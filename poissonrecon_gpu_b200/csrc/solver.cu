@@ -72,9 +72,10 @@ struct CgParams {
 
 // grid-wide (world == 1) or box-wide barrier.  kind: -1 none, 0/1 = publish this rank's per-depth
 // partial sums `local[1..D]` to every rank's slot table before signalling.
+template <bool MG>
 __device__ __forceinline__ void cg_sync(cg::grid_group& grid, const CgParams& P, unsigned& epoch, int parity, int kind, const double* local) {
     grid.sync();
-    if (P.world == 1) return;
+    if (!MG) return;
     epoch++;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (kind >= 0)
@@ -85,8 +86,9 @@ __device__ __forceinline__ void cg_sync(cg::grid_group& grid, const CgParams& P,
     grid.sync();
 }
 // total of a per-depth dot product after cg_sync
+template <bool MG>
 __device__ __forceinline__ double cg_total(const CgParams& P, int parity, int kind, int d, const double* local) {
-    if (P.world == 1) return local[d];
+    if (!MG) return local[d];
     const volatile double* s = &P.mg.hdr->slots[parity][0][kind * 16 + d];
     if (d < P.shardFrom) return s[0];
     double t = 0.0;
@@ -110,7 +112,8 @@ __device__ __forceinline__ void warp_add(double part, double* sAcc, int d, int l
 
 extern __shared__ __align__(16) float sDyn[];   // [kCgWarps][2][kCube]
 
-__global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
+template <bool MG>
+__global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(const __grid_constant__ CgParams P) {
     cg::grid_group grid = cg::this_grid();
     __shared__ float sSt[kMaxDepth + 1][4];
     __shared__ double sAcc[kMaxDepth + 1];
@@ -165,9 +168,9 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
         if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&P.dots[64 + tid], sAcc[tid]);   // dedicated init buffer
     }
     unsigned epoch = P.epoch0;
-    cg_sync(grid, P, epoch, 0, 0, P.dots + 64);
+    cg_sync<MG>(grid, P, epoch, 0, 0, P.dots + 64);
     if (tid >= 1 && tid <= D) {
-        float r1 = (float)cg_total(P, 0, 0, tid, P.dots + 64);
+        float r1 = (float)cg_total<MG>(P, 0, 0, tid, P.dots + 64);
         sR1[tid] = r1; sIter[tid] = 1; sBeta[tid] = 0.f; sAlpha[tid] = 0.f;
         sActive[tid] = (r1 > P.tol2 && 1 <= P.maxIter) ? 1 : 0;
     }
@@ -227,14 +230,14 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
                 *reinterpret_cast<float4*>(P.p + i) = pv;
             }
         }
-        cg_sync(grid, P, epoch, cur, -1, nullptr);
+        cg_sync<MG>(grid, P, epoch, cur, -1, nullptr);
         // ---------------- phase A: Ap = A p ; p.Ap
         for (int d = 1; d <= D; d++) {
             if (!sActive[d]) continue;
             const float s0 = sSt[d][0], s1 = sSt[d][1], s2 = sSt[d][2], s3 = sSt[d][3];
             const int t1 = P.sg1[d];
             int t = P.sg0[d] + gwarp;
-            const bool remote = P.world > 1 && d >= P.shardFrom;
+            const bool remote = MG && d >= P.shardFrom;
             const int myLo = P.row0[d], myHi = P.row1[d];
             // source of a block: this rank's p, or the owner's through its peer-mapped arena
             auto src = [&](int base) -> const float* {
@@ -303,12 +306,12 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
         }
         __syncthreads();
         if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&dPAp[tid], sAcc[tid]);
-        cg_sync(grid, P, epoch, cur, 0, dPAp);
+        cg_sync<MG>(grid, P, epoch, cur, 0, dPAp);
         // both accumulators of the NEXT iteration are zeroed here: every block has passed this
         // iteration's syncs, hence finished reading them after the previous iteration's syncs
         if (blockIdx.x == 0 && tid < 32) P.dots[nxt * 32 + tid] = 0.0;
         if (tid <= D) sAcc[tid] = 0.0;
-        if (tid >= 1 && tid <= D && sActive[tid]) sAlpha[tid] = (float)((double)sR1[tid] / cg_total(P, cur, 0, tid, dPAp));
+        if (tid >= 1 && tid <= D && sActive[tid]) sAlpha[tid] = (float)((double)sR1[tid] / cg_total<MG>(P, cur, 0, tid, dPAp));
         __syncthreads();
         // ---------------- phase B: x += alpha p ; r -= alpha Ap ; r.r
         for (int d = 1; d <= D; d++) {
@@ -334,9 +337,9 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(CgParams P) {
         }
         __syncthreads();
         if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&dRRn[tid], sAcc[tid]);
-        cg_sync(grid, P, epoch, cur, 1, dRRn);
+        cg_sync<MG>(grid, P, epoch, cur, 1, dRRn);
         if (tid >= 1 && tid <= D && sActive[tid]) {
-            float r0 = sR1[tid], r1 = (float)cg_total(P, cur, 1, tid, dRRn);
+            float r0 = sR1[tid], r1 = (float)cg_total<MG>(P, cur, 1, tid, dRRn);
             sR1[tid] = r1;
             int k = sIter[tid] + 1;
             sIter[tid] = k;
@@ -413,10 +416,11 @@ int stage_solve(Context& c) {
     P.tol2 = tol * tol;
     P.maxIter = c.cgMaxIter;
     const size_t dynSmem = (size_t)kCgWarps * 2 * kCube * sizeof(float);
-    PRB_CUDA(cudaFuncSetAttribute(k_cg_all_depths, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynSmem));
-    PRB_CUDA(cudaFuncSetAttribute(k_cg_all_depths, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    const void* kern = mg ? (const void*)k_cg_all_depths<true> : (const void*)k_cg_all_depths<false>;
+    PRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynSmem));
+    PRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int perSM = 0;
-    PRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_cg_all_depths, kCgBlock, dynSmem));
+    PRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kCgBlock, dynSmem));
     if (perSM < 1) { set_error("CG kernel does not fit on an SM"); return PRB_ERR_CUDA; }
     int gridSize = c.smCount * perSM;
     i64 maxTiles = P.sgStart[D + 1];
@@ -425,7 +429,7 @@ int stage_solve(Context& c) {
     if (gridSize > c.smCount * perSM) gridSize = c.smCount * perSM;
     if (gridSize < 1) gridSize = 1;
     void* args[] = {(void*)&P};
-    PRB_CUDA(cudaLaunchCooperativeKernel((void*)k_cg_all_depths, dim3(gridSize), dim3(kCgBlock), args, dynSmem, st));
+    PRB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(gridSize), dim3(kCgBlock), args, dynSmem, st));
     c.launches++;
     int hIters[16];
     PRB_CUDA(cudaMemcpyAsync(hIters, itersOut.p, sizeof(hIters), cudaMemcpyDeviceToHost, st));

@@ -32,7 +32,7 @@ def main():
     t1 = ref.stats()
     ref.close()
     pr = PoissonRecon(D, device=local)
-    pr.mg_setup(arena_bytes=8 * (rst["n_nodes"] + 4096) + (1 << 20))
+    pr.mg_setup(arena_bytes=int(os.environ.get("PRB_ARENA_BYTES", 6 << 30)))
     ok = True
     for k in range(reps):
         dist.barrier()
