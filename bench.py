@@ -9,9 +9,10 @@ BASELINE.json configs[2], the non-uniform scan, 5 M points, maxDepth 10 (the con
 metric is quoted on; it fits one B200).  `value` is measured with the samples already resident
 in HBM (device pointers into prb_set_points), `e2e` with pinned HOST buffers in and the mesh
 copied back to the host, both through the C ABI (include/prb.h) and both timed with CUDA events
-on the library's own stream.  N > 1: one process per GPU, every rank reconstructs its own
-cloud (same generator, different seed) -- weak scaling, no data-path collective
-(DESIGN.md "multi-GPU").  The CG kernel's roofline line uses the algorithmic 57.5 B per row
+on the library's own stream.  N > 1: one process per GPU reconstructing the SAME cloud together
+(strong scaling): the octree is replicated, divergence / CG / iso value / corner values /
+refinement values are sharded by Morton range and exchanged over NVLink through peer-mapped
+arenas (DESIGN.md "multi-GPU"); `--replicas` instead runs one independent cloud per GPU.  The CG kernel's roofline line uses the algorithmic 57.5 B per row
 per iteration of SURVEY.md 8(d) and the CUDA-event duration of the solve stage.
 
 `--impl reference`: the reference has no CPU path and its CUDA build stops at depth 9
@@ -202,6 +203,8 @@ def main():
     ap.add_argument("--workload", default="scan5m_d10")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-cuda", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: one independent reconstruction per GPU (weak scaling) instead of the sharded one")
+    ap.add_argument("--arena-gb", type=float, default=float(os.environ.get("PRB_ARENA_GB", "8")))
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -229,11 +232,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    p, n, D = make_cloud(a.workload, rank)
+    sharded = world > 1 and not a.replicas
+    p, n, D = make_cloud(a.workload, 0 if sharded else rank)
     N = p.shape[0]
     hp, hn = torch.from_numpy(p).pin_memory(), torch.from_numpy(n).pin_memory()
     dp, dn = hp.cuda(), hn.cuda()
     pr = PoissonRecon(D, device=local)
+    if sharded:
+        pr.mg_setup(int(a.arena_gb * (1 << 30)))
     stream = torch.cuda.ExternalStream(pr.stream(), device=local)
 
     def step_resident():
@@ -288,12 +294,12 @@ def main():
     nv, nt = pr.mesh_device_size()
     clk = clocks.stop() if rank == 0 else None
 
-    units = N * world
+    units = N if sharded else N * world
     value = units * a.steps / (ms_total * 1e-3) / 1e6
     e2e = units * a.steps / (ms_e2e * 1e-3) / 1e6
     peak, peak_src = measured_peaks()
     cg_t = statistics.mean(cg_ms)
-    achieved = B_ITER * statistics.mean(cg_row_iters) / (cg_t * 1e-3) / 1e9
+    achieved = B_ITER * statistics.mean(cg_row_iters) / (cg_t * 1e-3) / 1e9       # this rank's rows (per-GPU figure)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "cg_traffic.json")
     if os.path.exists(tp):
@@ -308,11 +314,12 @@ def main():
     line = {
         "metric": "M points/s end-to-end (octree+solve+MC) at depth 10; CG SpMV HBM GB/s vs peak",
         "value": value, "unit": "Mpoints/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": a.workload, "points_per_gpu": N, "depth": D, "nodes": st["n_nodes"], "mesh_vertices": nv, "mesh_triangles": nt,
-                   "cg_iters": st["cg_iters"][: D + 1], "parallelism": f"replicas x{world} (one cloud per GPU, no collective)" if world > 1 else "1 GPU",
+        "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": a.workload, "points": N if (sharded or world == 1) else N * world, "depth": D, "nodes": st["n_nodes"], "mesh_vertices": nv, "mesh_triangles": nt,
+                   "cg_iters": st["cg_iters"][: D + 1], "parallelism": ("1 GPU" if world == 1 else (f"morton-range shards x{world}: replicated octree, sharded divergence/CG/iso/corner+refinement values, NVLink peer-arena exchange"
+                                                                if sharded else f"replicas x{world} (one cloud per GPU, no collective)")),
                    "l2": "no flush: every step streams > 3 GB of samples, node slabs and vectors, far beyond the 126 MB L2"},
-        "e2e": {"value": e2e, "unit": "Mpoints/s", "h2d_bytes_per_step": 24 * N, "d2h_bytes_per_step": 12 * (nv + nt), "ms_per_step": ms_e2e / a.steps,
+        "e2e": {"value": e2e, "unit": "Mpoints/s", "h2d_bytes_per_step": 24 * N * world, "d2h_bytes_per_step": 12 * (nv + nt) * world, "ms_per_step": ms_e2e / a.steps,
                 "api": "prb_set_points(pinned host) + prb_run + prb_get_mesh (C ABI, include/prb.h)"},
         "gpu_launches": launches,
         "roofline": {"kernel": "k_cg_all_depths (matrix-free 27-point stencil CG, all depths in one persistent launch)", "bound": "hbm",
