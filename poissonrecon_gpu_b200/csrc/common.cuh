@@ -33,7 +33,16 @@ void set_error(const std::string& msg);
 constexpr int kMaxDepth = 12;
 constexpr int kSMs = 148;   // B200: 2 dies x 74 SMs; persistent grids are sized in multiples of this
 
-// Stream-ordered device buffer (cudaMallocAsync pool: allocation cost disappears after warm-up).
+// Device buffers come from a per-context arena (arena.cpp): a host-side free-list allocator over a
+// few large cudaMalloc slabs, keyed by the context's stream.  All work of a context is ordered on
+// that one stream, so freed blocks are reusable at once; after the first run of a given size no
+// driver allocation happens any more (deterministic step times).
+void arena_register(cudaStream_t st);
+void arena_unregister(cudaStream_t st);
+int arena_alloc(void** out, size_t bytes, cudaStream_t st);
+void arena_free(void* p, cudaStream_t st);
+void arena_stats(cudaStream_t st, size_t* reserved, size_t* peak, long* driverCalls);
+
 template <class T>
 struct DBuf {
     T* p = nullptr;
@@ -44,28 +53,24 @@ struct DBuf {
         s = st;
         n = count;
         if (count == 0) { p = nullptr; return PRB_OK; }
-        PRB_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), st));
-        return PRB_OK;
+        return arena_alloc((void**)&p, count * sizeof(T), st);
     }
     void release() {
-        if (p) cudaFreeAsync(p, s);
+        if (p) arena_free(p, s);
         p = nullptr;
         n = 0;
         cap = 0;
     }
-    // grow-only reuse (workspace buffers kept by the context between passes and runs: repeated
-    // multi-hundred-MB alloc/free cycles of varying sizes fragment the stream-ordered pool and
-    // occasionally stall a run on fresh device allocations)
+    // grow-only reuse (workspace buffers kept by the context between passes and runs)
     size_t cap = 0;
     int ensure(size_t count, cudaStream_t st) {
         if (p && count <= cap) { n = count; return PRB_OK; }
-        if (p) cudaFreeAsync(p, s);
+        if (p) arena_free(p, s);
         p = nullptr;
         s = st;
         cap = count + count / 8 + 256;
         n = count;
-        PRB_CUDA(cudaMallocAsync((void**)&p, cap * sizeof(T), st));
-        return PRB_OK;
+        return arena_alloc((void**)&p, cap * sizeof(T), st);
     }
     size_t bytes() const { return n * sizeof(T); }
 };

@@ -69,13 +69,10 @@ int prb_create(int device, int depth, prb_context** out) {
     c.deviceMemBytes = prop.totalGlobalMem;
     PRB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     for (auto& e : c.ev) PRB_CUDA(cudaEventCreate(&e));
-    cudaMemPool_t pool;
-    PRB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    unsigned long long thr = ~0ull;
-    PRB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    arena_register(c.stream);
     std::memset(&c.stats, 0, sizeof(c.stats));
     int r = upload_tables(c);
-    if (r != PRB_OK) { delete h; return r; }
+    if (r != PRB_OK) { arena_unregister(c.stream); cudaStreamDestroy(c.stream); delete h; return r; }
     *out = h;
     return PRB_OK;
 }
@@ -88,6 +85,7 @@ void prb_destroy(prb_context* h) {
     c.wsVal7.release(); c.wsLow.release(); c.wsCat.release(); c.wsNtri.release(); c.wsEmask.release(); c.wsVbase.release(); c.wsTbase.release();
     c.dMaxDepthFn.release(); c.dBaseFn.release(); c.dDfT.release(); c.dDfOffset.release(); c.dStencil.release();
     cudaStreamSynchronize(c.stream);
+    arena_unregister(c.stream);
     for (int r = 0; r < kMaxRanks; r++)
         if (c.mg.peerOpen[r] && c.mg.peer[r]) cudaIpcCloseMemHandle(c.mg.peer[r]);
     if (c.mg.arena) cudaFree(c.mg.arena);
