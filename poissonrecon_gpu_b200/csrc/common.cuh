@@ -156,6 +156,7 @@ struct Context {
     int launches = 0;
     double cgTol = 1e-5;
     int cgMaxIter = 10000;
+    int cgZigzag = 1;
     int doRefine = 1;
     int refineImplicit = 1;        // 0: materialised virtual subtrees for every pass (debug / cross-check)
     int smCount = kSMs;
@@ -176,7 +177,8 @@ struct Context {
     DBuf<int> parent, child0, pidx, pnum, didx, dnum;
     DBuf<int> neighs;              // [M][27]
     DBuf<ushort4> offs;            // per node (ox, oy, oz, depth)
-    DBuf<int> sgTab;               // [nSg][64] super-group table of the stencil SpMV (octree.cu k_sg_table)
+    DBuf<int> sgTab;               // [nSg][64] super-group table: first row of every block of the 4x4x4 cube (octree.cu k_sg_table)
+    DBuf<int> sgTab4;              // [nSg][8][12] the same in the staging order of the CG kernel (solver.cu k_sg_table4)
     int nSg = 0;
     // ---- tables
     BSplineTables tab;
@@ -228,6 +230,7 @@ int stage_solve(Context& c);
 int stage_iso(Context& c);
 int stage_extract(Context& c);
 int upload_tables(Context& c);
+int build_cg_table(Context& c);       // solver.cu: sgTab -> sgTab4
 
 // exclusive scan of n ints on the context stream; returns the grand total through *total_host
 // (synchronises the stream) when total_host != nullptr.

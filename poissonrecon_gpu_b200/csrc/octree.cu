@@ -387,6 +387,7 @@ int stage_octree(Context& c) {
     c.nSg = 1 + (c.base[D] - 1) / 8;
     PRB_TRY(c.sgTab.alloc(64 * (size_t)c.nSg, st));
     PRB_LAUNCH(c, k_sg_table, grid_for(c, (i64)c.nSg * 64, 256), 256, 0, c.parent.p, c.child0.p, c.neighs.p, c.nSg, c.sgTab.p);
+    PRB_TRY(build_cg_table(c));
     // ---- multi-GPU shard plan: depths with at least minShardRows nodes (and every deeper one) are
     // split into contiguous super-group ranges, the shallower ones are replicated on every rank
     {

@@ -12,7 +12,7 @@ void set_error(const std::string& msg) { g_lastError = msg; }
 static void release_all(Context& c) {
     c.rawP.release(); c.rawN.release(); c.P.release(); c.Nr.release(); c.sortedKey.release(); c.sortedIdx.release(); c.p2n.release();
     c.dBase.release(); c.key.release(); c.parent.release(); c.child0.release(); c.pidx.release(); c.pnum.release(); c.didx.release(); c.dnum.release();
-    c.neighs.release(); c.offs.release(); c.sgTab.release();
+    c.neighs.release(); c.offs.release(); c.sgTab.release(); c.sgTab4.release();
     c.V.release(); c.divg.release(); c.x.release(); c.pointValue.release();
     c.meshV.release(); c.meshT.release(); c.vval.release();
     c.nMeshV = c.nMeshT = 0;
@@ -100,6 +100,7 @@ int prb_set_option(prb_context* h, const char* key, double value) {
     std::string k(key);
     if (k == "cg_tol") h->c.cgTol = value;
     else if (k == "cg_max_iter") h->c.cgMaxIter = (int)value;
+    else if (k == "cg_zigzag") h->c.cgZigzag = (int)value;
     else if (k == "refine") h->c.doRefine = (int)value;
     else if (k == "refine_implicit") h->c.refineImplicit = (int)value;
     else { set_error("unknown option " + k); return PRB_ERR_ARG; }

@@ -6,20 +6,24 @@
 // memory, 7 grid syncs per iteration and host loops over managed arrays around the launch.
 // Here:
 //   * the matrix is never formed: rows are the translation-invariant 27-point stencil
-//     (4 distinct values per depth) applied through the super-group table sgTab[sg][64]
-//     (octree.cu k_sg_table): the up to 64 rows under one node Q (8 sibling groups) and all
-//     their neighbours live in the 4x4x4 cube of 8-row blocks around Q's children
-//     (256 B of topology per <= 64 rows instead of 216 B per ROW of CSR);
+//     (4 distinct values per depth) applied through a per-super-group table: the up to 64 rows
+//     under one node Q (8 sibling groups) and all their neighbours live in the 4x4x4 cube of
+//     8-row blocks around Q's children;
 //   * the depths are independent, so they all iterate in lock-step inside one
 //     launch: one iteration of the kernel = one CG iteration of every still-active depth, with
 //     per-depth alpha / beta / residual and per-depth stopping.  Grid syncs per solve drop from
 //     7 * sum_d iters_d to 3 * max_d iters_d;
-//   * SpMV: a warp owns a super-group per step.  The 64 blocks (an 8x8x8 cube of p values, 2 KB)
-//     are copied global -> shared with 16-byte cp.async into a double buffer, one tile ahead of
-//     the compute, and the table two tiles ahead, so the gather latency is off the critical path;
-//     every lane then produces two rows (a z pair) from a 3x3x4 register window read with
-//     conflict-free LDS (padded block-major layout; the two half-warps walk z in opposite
-//     directions so that they always hit different banks);
+//   * SpMV: the super-groups of all active depths form one flat tile list; a warp takes 4
+//     consecutive super-groups (one per quarter-warp) per step.  The p values a super-group
+//     touches are a 6x8x8 box = 96 half-blocks of 16 bytes; they are copied global -> shared with
+//     cp.async into a double buffer one step ahead of the compute (their addresses come from the
+//     table, which is loaded two steps ahead), so the gather latency is off the critical path.
+//     Every lane then produces EIGHT rows (an x pair times the four z of its column) from a
+//     4x3x8 window read with 64-bit LDS: 6 shared-memory floats per row instead of 18 with one
+//     z pair per lane -- the SpMV is bound by shared-memory wavefronts, not by issue slots or
+//     HBM.  The half-block layout P = xx + 10 bz + 36 by (16-byte units, odd cube stride) makes
+//     both the LDS.64 window reads (per half-warp) and the cp.async stores (per quarter-warp)
+//     bank-conflict free;
 //   * the row sum runs over the neighbour slots in order j = 0..26 with FMAs, exactly the
 //     reference's CSR order (absent neighbours contribute an exact +0), so A*p is bit-identical;
 //     dots are float products accumulated in double (CG_CUDA.cuh:217-220); alpha, beta are float.
@@ -32,18 +36,79 @@ namespace cg = cooperative_groups;
 
 namespace prb {
 
-constexpr int kCgBlock = 256;
-constexpr int kCgWarps = kCgBlock / 32;
-// shared cube of one super-group: block (bx,by,bz) at bx*kSX + by*kSY + bz*8 floats, 8 floats per
-// block in child-code order; the paddings make both the 16-byte staging stores and the
-// per-lane window loads bank-conflict free (see k_cg_all_depths)
-constexpr int kSX = 200, kSY = 48, kCube = 4 * kSX;
+constexpr int kCgWarps = 12;
+constexpr int kCgBlock = kCgWarps * 32;
+// shared box of one super-group: half-block (xx, by, bz) -- the four p values (y&1, z&1) at
+// x = xx of block (xx>>1, by, bz) -- sits at 16-byte unit P = xx + 10 bz + 36 by (xx = 1..6).
+// P mod 8 = xx + 2 bz + 4 by: the 16 lanes of a half-warp (two cubes, shifted by one unit) read 16
+// different 8-byte bank pairs, and the staging rounds below write 8 different 16-byte bank groups.
+constexpr int kUnitBz = 10, kUnitBy = 36, kCubeUnits = 145, kCubeFloats = 4 * kCubeUnits;
+constexpr int kWarpBufFloats = 4 * kCubeFloats;          // 4 cubes per warp-step
+constexpr int kRounds = 12;                               // 96 half-blocks / 8 lanes
+constexpr int kPrefetchSteps = 2;                         // L2 prefetch distance of the SpMV table, in steps beyond the register pipeline
+constexpr int kStreamUnroll = 4, kStreamUnrollB = 3;     // independent 16-byte loads per array per thread in the streaming phases
+
+// Staging plan of a quarter-warp: in round r (12 rounds x 8 lanes = the 96 half-blocks) lane li
+// copies one 16-byte half-block.  The cost of the gather is the number of distinct 128-byte
+// lines an LDGSTS instruction touches (LSU tag stage), so every round takes its 8 half-blocks from
+// as few of Q's 27 neighbours as possible (the children of one neighbour are contiguous in memory):
+//   rounds 0..7  full blocks (bx = 1, 2): the lane PAIR (li, li^1) copies the two x halves of one
+//                block (one full 32-byte sector): r0 / r1 the pair's own rows' blocks bz = 1 / 2 (centre
+//                neighbour), r2 / r3 the y faces, r4 / r5 the z faces, r6 / r7 the x-parallel edges;
+//   rounds 8..11 edge blocks (bx = 0: upper half, bx = 3: lower half), one lane each: x faces,
+//                z-parallel edges, y-parallel edges, corners.
+// The table holds the 64 block bases in that order: [pair][8] then [lane][4].
+__host__ __device__ constexpr int plan_block(int li, int r) {      // bx * 16 + by * 4 + bz
+    const int m = li >> 1, a = li >> 2, b = (li >> 1) & 1, c = li & 1;
+    int bx = 0, by = 0, bz = 0;
+    switch (r) {
+        case 0: bx = 1 + a; by = 1 + b; bz = 1; break;
+        case 1: bx = 1 + a; by = 1 + b; bz = 2; break;
+        case 2: bx = 1 + (m >> 1); by = 0; bz = 1 + (m & 1); break;
+        case 3: bx = 1 + (m >> 1); by = 3; bz = 1 + (m & 1); break;
+        case 4: bx = 1 + (m >> 1); by = 1 + (m & 1); bz = 0; break;
+        case 5: bx = 1 + (m >> 1); by = 1 + (m & 1); bz = 3; break;
+        case 6: bx = 1 + (m & 1); by = 0; bz = 3 * (m >> 1); break;
+        case 7: bx = 1 + (m & 1); by = 3; bz = 3 * (m >> 1); break;
+        case 8: bx = 3 * a; by = 1 + b; bz = 1 + c; break;
+        case 9: bx = 3 * a; by = 3 * b; bz = 1 + c; break;
+        case 10: bx = 3 * a; by = 1 + c; bz = 3 * b; break;
+        default: bx = 3 * a; by = 3 * b; bz = 3 * c; break;
+    }
+    return bx * 16 + by * 4 + bz;
+}
+__host__ __device__ constexpr int plan_half(int li, int r) { return r < 8 ? (li & 1) : ((li >> 2) ? 0 : 1); }
+constexpr bool plan_ok() {
+    bool seen[8][4][4] = {};
+    for (int r = 0; r < kRounds; r++)
+        for (int li = 0; li < 8; li++) {
+            int u = plan_block(li, r), xx = 2 * (u >> 4) + plan_half(li, r), by = (u >> 2) & 3, bz = u & 3;
+            if (xx < 1 || xx > 6 || seen[xx][by][bz]) return false;
+            seen[xx][by][bz] = true;
+        }
+    return true;
+}
+static_assert(plan_ok(), "staging plan must cover the 96 half-blocks exactly once");
+
+constexpr int kAbsent = -7;    // table entry of a missing block (the address p - 7 stays valid and 32-byte aligned; it is never read)
+
+// sgTab4[sg][64]: block bases in staging order, kAbsent when the block does not exist.
+__global__ void __launch_bounds__(256) k_sg_table4(const int* __restrict__ sgTab, i64 nSg, int* __restrict__ tab4) {
+    const i64 total = nSg * 64;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        const int k = (int)(t & 63);
+        const int u = k < 32 ? plan_block(2 * (k >> 3), k & 7) : plan_block((k - 32) >> 2, 8 + ((k - 32) & 3));
+        const int b = sgTab[(t & ~(i64)63) + u];
+        tab4[t] = b >= 0 ? b : kAbsent;
+    }
+}
 
 struct CgParams {
     int D;
-    int gbase[kMaxDepth + 2];     // first sibling group of depth d (groups cover nodes 1..M-1), gbase[D+1] = total
     int sgStart[kMaxDepth + 2];   // first super-group of depth d (d = 1..D), sgStart[D+1] = total
-    const int* sgTab;
+    const int* tab4;
+    int nSg;
+    int zigzag;                    // sweep memory in alternating directions phase by phase (L2 reuse across phase boundaries)
     const float* stencil;          // [D+1][27]
     const float* b;                // divergence
     // vectors indexed by node id; node 1 sits on a 32-byte boundary (pointer = allocation + 7)
@@ -110,15 +175,16 @@ __device__ __forceinline__ void warp_add(double part, double* sAcc, int d, int l
     if (lane == 0 && part != 0.0) atomicAdd(&sAcc[d], part);
 }
 
-extern __shared__ __align__(16) float sDyn[];   // [kCgWarps][2][kCube]
+extern __shared__ __align__(16) float sDyn[];   // [kCgWarps][2][kWarpBufFloats]
 
 template <bool MG>
-__global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(const __grid_constant__ CgParams P) {
+__global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_constant__ CgParams P) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ float sSt[kMaxDepth + 1][4];
+    __shared__ __align__(16) float sSt[kMaxDepth + 1][4];
     __shared__ double sAcc[kMaxDepth + 1];
     __shared__ float sR1[kMaxDepth + 1], sAlpha[kMaxDepth + 1], sBeta[kMaxDepth + 1];
     __shared__ int sActive[kMaxDepth + 1], sIter[kMaxDepth + 1];
+    __shared__ int sStep[kMaxDepth + 3];      // sStep[d] = first flat SpMV step of depth d (active depths only), sStep[D+1] = total
     const int D = P.D, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gwarp = blockIdx.x * kCgWarps + warp, nwarps = gridDim.x * kCgWarps;
     const int gthread = blockIdx.x * kCgBlock + tid, nthreads = gridDim.x * kCgBlock;
@@ -177,132 +243,233 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(const __grid_constan
     __syncthreads();
 
     // ---- per-lane constants of the SpMV
-    float* const cube0 = sDyn + (size_t)warp * 2 * kCube;
-    const unsigned cubeS = (unsigned)__cvta_generic_to_shared(cube0);
-    // staging: copy task t = lane + 32k (k = 0..3) moves half-block (blk = t>>1, half = t&1)
-    int stOff[4];
+    // quarter-warp q works on cube q; within it lane li = (Xp, Y) produces the rows
+    // x = 2 + 2 Xp + {0, 1}, y = 2 + Y, z = 2..5 of the 8x8x8 node cube
+    const int q = lane >> 3, li = lane & 7, Xp = li >> 2, Y = li & 3;
+    float* const wbuf = sDyn + (size_t)warp * 2 * kWarpBufFloats;
+    const unsigned cubeS = (unsigned)__cvta_generic_to_shared(wbuf) + 4u * (unsigned)(q * kCubeFloats);   // byte address of this lane's cube, buffer 0
+    const float* const cube0 = wbuf + q * kCubeFloats;
+    const int Ylo = Y & 1;
+    int dstOff[kRounds];       // float offset of the lane's half-block of round r inside the cube
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int t = lane + 32 * k, blk = t >> 1, half = t & 1;
-        stOff[k] = (blk >> 4) * kSX + ((blk >> 2) & 3) * kSY + (blk & 3) * 8 + half * 4;
+    for (int r = 0; r < kRounds; r++) {
+        const int u = plan_block(li, r);
+        dstOff[r] = 4 * ((2 * (u >> 4) + plan_half(li, r)) + kUnitBz * (u & 3) + kUnitBy * ((u >> 2) & 3));
     }
-    // compute: lane -> (kz, X, Y); it produces the rows at cube node (2+X, 2+Y, 2+2kz + {0,1})
-    const int kz = lane >> 4, X = (lane >> 2) & 3, Y = lane & 3;
-    const int pb = (1 + (X >> 1)) * 16 + (1 + (Y >> 1)) * 4 + (1 + kz);      // cube block of the rows' parent
-    const int rowIn = ((X & 1) << 2) | ((Y & 1) << 1);                         // child code of the z pair's first row
-    int ax[3], ay[3], zo[4];
+    const int hFull = 4 * (li & 1), hEdge = (li >> 2) ? 0 : 4;    // source offset of the x half copied in rounds 0..7 / 8..11
+    // window column (dxp, dy): xx = 1 + 2 Xp + dxp, yy = 1 + Y + dy, z pairs bz = 0..3 at stride 4 kUnitBz floats
+    int colOff[3];
 #pragma unroll
-    for (int t = 0; t < 3; t++) {
-        int xx = 1 + X + t, yy = 1 + Y + t;
-        ax[t] = (xx >> 1) * kSX + ((xx & 1) << 2);
-        ay[t] = (yy >> 1) * kSY + ((yy & 1) << 1);
+    for (int dy = 0; dy < 3; dy++) {
+        int yy = 1 + Y + dy;
+        colOff[dy] = 4 * ((1 + 2 * Xp) + kUnitBy * (yy >> 1)) + 2 * (yy & 1);
     }
+    const bool upper = lane >= 16;
+    int colA[3], colB[3];      // z = 1 (pair bz = 0, odd word) and z = 6 (pair bz = 3, even word), swapped in the upper half-warp
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        // half-warp 0 reads z = z0-1 .. z0+2 upwards, half-warp 1 downwards: at every step the two
-        // halves touch z of opposite parity, i.e. different banks
-        int z = kz ? (2 + 2 * kz + 2 - i) : (1 + i);
-        zo[i] = (z >> 1) * 8 + (z & 1);
+    for (int dy = 0; dy < 3; dy++) {
+        colA[dy] = colOff[dy] + (upper ? 12 * kUnitBz : 1);
+        colB[dy] = colOff[dy] + (upper ? 1 : 12 * kUnitBz);
     }
+    const int outOff = 2 * Ylo;          // the lane's rows (y = Y & 1) start 2 (Y & 1) floats after the block base
 
+    int phase = 0;
     for (int it = 1;; it++) {
         int anyActive = 0;
         for (int d = 1; d <= D; d++) anyActive |= sActive[d];
         if (!anyActive) break;
         if (tid <= D) sAcc[tid] = 0.0;
+        if (tid == 0) {
+            int acc = 0;
+            sStep[0] = 0; sStep[1] = 0;
+            for (int d = 1; d <= D; d++) {
+                if (sActive[d]) acc += (P.sg1[d] - P.sg0[d] + 3) >> 2;
+                sStep[d + 1] = acc;
+            }
+        }
         __syncthreads();
         const int cur = it & 1, nxt = cur ^ 1;
         double* dPAp = P.dots + cur * 32;         // kind 0
         double* dRRn = P.dots + cur * 32 + 16;    // kind 1 (this iteration's new r.r)
 
         // ---------------- phase C: p = r + beta p   (beta = 0 and p = 0 in the first iteration)
-        for (int d = 1; d <= D; d++) {
+        const bool revC = P.zigzag && (phase++ & 1) != 0;
+        for (int dd = 1; dd <= D; dd++) {
+            const int d = revC ? D + 1 - dd : dd;
             if (!sActive[d]) continue;
             const float be = sBeta[d];
-            const int i1 = P.row1[d];
-            for (int i = P.row0[d] + 4 * gthread; i < i1; i += 4 * nthreads) {
-                float4 rv = *reinterpret_cast<const float4*>(P.r + i);
-                float4 pv = *reinterpret_cast<const float4*>(P.p + i);
-                pv.x = __fadd_rn(rv.x, __fmul_rn(be, pv.x));
-                pv.y = __fadd_rn(rv.y, __fmul_rn(be, pv.y));
-                pv.z = __fadd_rn(rv.z, __fmul_rn(be, pv.z));
-                pv.w = __fadd_rn(rv.w, __fmul_rn(be, pv.w));
-                *reinterpret_cast<float4*>(P.p + i) = pv;
+            const int i0 = P.row0[d], n4 = (P.row1[d] - i0) >> 2;
+            for (int c = gthread; c < n4; c += kStreamUnroll * nthreads) {
+                float4 rv[kStreamUnroll], pv[kStreamUnroll];
+#pragma unroll
+                for (int k = 0; k < kStreamUnroll; k++) {
+                    const int ck = c + k * nthreads, ik = i0 + 4 * (revC ? n4 - 1 - ck : ck);
+                    if (ck < n4) { rv[k] = *reinterpret_cast<const float4*>(P.r + ik); pv[k] = *reinterpret_cast<const float4*>(P.p + ik); }
+                }
+#pragma unroll
+                for (int k = 0; k < kStreamUnroll; k++) {
+                    const int ck = c + k * nthreads, ik = i0 + 4 * (revC ? n4 - 1 - ck : ck);
+                    if (ck < n4) {
+                        float4 o;
+                        o.x = __fadd_rn(rv[k].x, __fmul_rn(be, pv[k].x));
+                        o.y = __fadd_rn(rv[k].y, __fmul_rn(be, pv[k].y));
+                        o.z = __fadd_rn(rv[k].z, __fmul_rn(be, pv[k].z));
+                        o.w = __fadd_rn(rv[k].w, __fmul_rn(be, pv[k].w));
+                        *reinterpret_cast<float4*>(P.p + ik) = o;
+                    }
+                }
             }
         }
         cg_sync<MG>(grid, P, epoch, cur, -1, nullptr);
-        // ---------------- phase A: Ap = A p ; p.Ap
-        for (int d = 1; d <= D; d++) {
-            if (!sActive[d]) continue;
-            const float s0 = sSt[d][0], s1 = sSt[d][1], s2 = sSt[d][2], s3 = sSt[d][3];
-            const int t1 = P.sg1[d];
-            int t = P.sg0[d] + gwarp;
-            const bool remote = MG && d >= P.shardFrom;
-            const int myLo = P.row0[d], myHi = P.row1[d];
-            // source of a block: this rank's p, or the owner's through its peer-mapped arena
-            auto src = [&](int base) -> const float* {
-                if (!remote || (base >= myLo && base < myHi)) return P.p + base;
-                int r = 0;
-                while (r + 1 < P.world && base >= P.rowLo[d][r + 1]) r++;
-                return P.peerP[r] + base;
+        // ---------------- phase A: Ap = A p ; p.Ap over the flat step list of all active depths
+        {
+            const int total = sStep[D + 1];
+            const bool rev = P.zigzag && (phase++ & 1) != 0;       // zig-zag: every phase sweeps memory in the direction opposite to the previous one
+            // locate flat step u: depth and this quarter-warp's super-group (-1: past the end of the depth's
+            // range).  (d, lo, hi) is carried along: consecutive steps of a warp move monotonically
+            int ld = 1, llo = sStep[1], lhi = sStep[2];
+            auto locate = [&](int t, int& sg) {
+                const int u = rev ? total - 1 - t : t;
+                while (u >= lhi) { ld++; llo = lhi; lhi = sStep[ld + 1]; }
+                while (u < llo) { ld--; lhi = llo; llo = sStep[ld]; }
+                sg = P.sg0[ld] + 4 * (u - llo) + q;
+                if (sg >= P.sg1[ld]) sg = -1;
+            };
+            auto load_tab = [&](int sg, int (&e)[kRounds]) {
+                if (sg >= 0) {
+                    const int* row = P.tab4 + (i64)sg * 64;
+                    const int4* tf = reinterpret_cast<const int4*>(row + (li >> 1) * 8);
+                    const int4 a = __ldcs(tf), b = __ldcs(tf + 1), c = __ldcs(reinterpret_cast<const int4*>(row + 32 + li * 4));   // streamed once per sweep
+                    e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w; e[8] = c.x; e[9] = c.y; e[10] = c.z; e[11] = c.w;
+                    if (kPrefetchSteps > 0 && (li & 3) == 0) {      // the table of a later step is on its way to L2 meanwhile
+                        i64 sgp = (i64)sg + (rev ? -4 : 4) * (i64)kPrefetchSteps * nwarps;
+                        sgp = sgp < 0 ? 0 : (sgp >= P.nSg ? P.nSg - 1 : sgp);
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.tab4 + sgp * 64 + li * 8));
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kRounds; k++) e[k] = kAbsent;
+                }
+            };
+            // source of a half-block: this rank's p, or the owner's through its peer-mapped arena
+            auto stage = [&](const int (&e)[kRounds], int d, int buf) {
+                const bool remote = MG && d >= P.shardFrom;
+                const unsigned dst = cubeS + 4u * (unsigned)(buf * kWarpBufFloats);
+#pragma unroll
+                for (int r = 0; r < kRounds; r++) {
+                    const int b = e[r];
+                    const float* src = P.p + (b + (r >= 8 ? hEdge : hFull));
+                    if (MG && remote && b >= 0 && (b < P.row0[d] || b >= P.row1[d])) {
+                        int rk = 0;
+                        while (rk + 1 < P.world && b >= P.rowLo[d][rk + 1]) rk++;
+                        src = P.peerP[rk] + (b + (r >= 8 ? hEdge : hFull));
+                    }
+                    cp_async16(dst + 4u * (unsigned)dstOff[r], src, b >= 0 ? 16 : 0);     // missing block: zero fill, no memory access
+                }
             };
             double part = 0.0;
-            // table registers of the current tile (A), the next (B) and the one after (C)
-            int a0 = -1, a1 = -1, b0 = -1, b1 = -1;
-            if (t < t1) { a0 = P.sgTab[64 * (i64)t + lane]; a1 = P.sgTab[64 * (i64)t + 32 + lane]; }
-            if (t + nwarps < t1) { b0 = P.sgTab[64 * (i64)(t + nwarps) + lane]; b1 = P.sgTab[64 * (i64)(t + nwarps) + 32 + lane]; }
-            int buf = 0;
-            if (t < t1) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    int base = __shfl_sync(0xffffffffu, k < 2 ? a0 : a1, ((lane >> 1) + 16 * k) & 31);
-                    cp_async16(cubeS + 4u * (unsigned)stOff[k], base >= 0 ? (const void*)(src(base) + 4 * (lane & 1)) : (const void*)(P.p + 1), base >= 0 ? 16 : 0);
-                }
+            int partDepth = 0;
+            int t = gwarp;
+            int eB[kRounds], eC[kRounds];
+            int dA = 1, dB = 1, sgq;
+            int rb0 = kAbsent, rb1 = kAbsent;          // bases of the blocks bz = 1 / bz = 2 of the lane's rows (current tile)
+            if (t < total) {
+                locate(t, sgq);
+                dA = ld;
+                load_tab(sgq, eB);
+                stage(eB, dA, 0);
+                rb0 = eB[0]; rb1 = eB[1];
             }
             cp_async_commit();
-            for (; t < t1; t += nwarps, buf ^= 1) {
+            bool haveB = t + nwarps < total;
+            if (haveB) { locate(t + nwarps, sgq); dB = ld; load_tab(sgq, eB); }
+            int buf = 0;
+            for (; t < total; t += nwarps, buf ^= 1) {
                 // next tile's copies into the other buffer, the table of the tile after that into registers
-                int c0 = -1, c1 = -1;
-                if (t + nwarps < t1) {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        int base = __shfl_sync(0xffffffffu, k < 2 ? b0 : b1, ((lane >> 1) + 16 * k) & 31);
-                        cp_async16(cubeS + 4u * (unsigned)((buf ^ 1) * kCube + stOff[k]), base >= 0 ? (const void*)(src(base) + 4 * (lane & 1)) : (const void*)(P.p + 1),
-                                   base >= 0 ? 16 : 0);
-                    }
-                    if (t + 2 * nwarps < t1) { c0 = P.sgTab[64 * (i64)(t + 2 * nwarps) + lane]; c1 = P.sgTab[64 * (i64)(t + 2 * nwarps) + 32 + lane]; }
+                bool haveC = false;
+                int dC = dB;
+                if (haveB) {
+                    stage(eB, dB, buf ^ 1);
+                    haveC = t + 2 * nwarps < total;
+                    if (haveC) { locate(t + 2 * nwarps, sgq); dC = ld; load_tab(sgq, eC); }
                 }
                 cp_async_commit();
+                if (dA != partDepth) {               // flush the dot-product partial when the depth changes
+                    if (partDepth) warp_add(part, sAcc, partDepth, lane);
+                    part = 0.0;
+                    partDepth = dA;
+                }
+                const float4 sv = *reinterpret_cast<const float4*>(&sSt[dA][0]);
                 cp_async_wait<1>();
                 __syncwarp();
-                const int r0 = __shfl_sync(0xffffffffu, a0, pb & 31), r1 = __shfl_sync(0xffffffffu, a1, pb & 31);
-                const int rowBase = pb < 32 ? r0 : r1;
-                if (rowBase >= 0) {
-                    const float* cb = cube0 + buf * kCube;
-                    float acc0 = 0.f, acc1 = 0.f, pc0 = 0.f, pc1 = 0.f;
+                {
+                    const float* cb = cube0 + buf * kWarpBufFloats;
+                    float acc[2][4], pc[2][4];
 #pragma unroll
-                    for (int dx = 0; dx < 3; dx++)
+                    for (int a = 0; a < 2; a++)
+#pragma unroll
+                        for (int z = 0; z < 4; z++) { acc[a][z] = 0.f; pc[a][z] = 0.f; }
+#pragma unroll
+                    for (int dxp = 0; dxp < 4; dxp++)
 #pragma unroll
                         for (int dy = 0; dy < 3; dy++) {
-                            const float* q = cb + ax[dx] + ay[dy];
-                            float t0 = q[zo[0]], t1v = q[zo[1]], t2 = q[zo[2]], t3 = q[zo[3]];
-                            const float w0 = kz ? t3 : t0, w1 = kz ? t2 : t1v, w2 = kz ? t1v : t2, w3 = kz ? t0 : t3;
-                            const int ty = (dx != 1) + (dy != 1);
-                            const float se = ty == 0 ? s1 : (ty == 1 ? s2 : s3);     // dz != 0
-                            const float sc = ty == 0 ? s0 : (ty == 1 ? s1 : s2);     // dz == 0
-                            acc0 = __fmaf_rn(se, w0, acc0); acc0 = __fmaf_rn(sc, w1, acc0); acc0 = __fmaf_rn(se, w2, acc0);
-                            acc1 = __fmaf_rn(se, w1, acc1); acc1 = __fmaf_rn(sc, w2, acc1); acc1 = __fmaf_rn(se, w3, acc1);
-                            if (dx == 1 && dy == 1) { pc0 = w1; pc1 = w2; }
+                            // z = 2..5 as two 64-bit loads (conflict free per half-warp); z = 1 and z = 6 as
+                            // 32-bit loads: the lower half-warp reads z = 1 while the upper one reads z = 6 and
+                            // vice versa, so the 32 lanes always hit banks of both parities (1 wavefront each)
+                            const float* col = cb + colOff[dy] + 4 * dxp;
+                            float w[8];
+                            const float ea = cb[colA[dy] + 4 * dxp], eb = cb[colB[dy] + 4 * dxp];
+                            const float2 v12 = *reinterpret_cast<const float2*>(col + 4 * kUnitBz);
+                            const float2 v34 = *reinterpret_cast<const float2*>(col + 8 * kUnitBz);
+                            w[0] = 0.f; w[7] = 0.f;
+                            w[1] = upper ? eb : ea; w[6] = upper ? ea : eb;
+                            w[2] = v12.x; w[3] = v12.y; w[4] = v34.x; w[5] = v34.y;
+#pragma unroll
+                            for (int xr = 0; xr < 2; xr++) {
+                                const int dx = dxp - 1 - xr;
+                                if (dx < -1 || dx > 1) continue;
+                                const int ty = (dx != 0) + (dy != 1);
+                                const float se = ty == 0 ? sv.y : (ty == 1 ? sv.z : sv.w);     // dz != 0
+                                const float sc = ty == 0 ? sv.x : (ty == 1 ? sv.y : sv.z);     // dz == 0
+#pragma unroll
+                                for (int zr = 0; zr < 4; zr++) {
+                                    float a = acc[xr][zr];
+                                    a = __fmaf_rn(se, w[1 + zr], a);
+                                    a = __fmaf_rn(sc, w[2 + zr], a);
+                                    a = __fmaf_rn(se, w[3 + zr], a);
+                                    acc[xr][zr] = a;
+                                    if (dx == 0 && dy == 1) pc[xr][zr] = w[2 + zr];
+                                }
+                            }
                         }
-                    *reinterpret_cast<float2*>(P.Ap + rowBase + rowIn) = make_float2(acc0, acc1);
-                    part += (double)(pc0 * acc0);
-                    part += (double)(pc1 * acc1);
+                    if (rb0 >= 0) {
+                        float* o = P.Ap + rb0 + outOff;
+                        *reinterpret_cast<float2*>(o) = make_float2(acc[0][0], acc[0][1]);
+                        *reinterpret_cast<float2*>(o + 4) = make_float2(acc[1][0], acc[1][1]);
+                        part += (double)(pc[0][0] * acc[0][0]);
+                        part += (double)(pc[0][1] * acc[0][1]);
+                        part += (double)(pc[1][0] * acc[1][0]);
+                        part += (double)(pc[1][1] * acc[1][1]);
+                    }
+                    if (rb1 >= 0) {
+                        float* o = P.Ap + rb1 + outOff;
+                        *reinterpret_cast<float2*>(o) = make_float2(acc[0][2], acc[0][3]);
+                        *reinterpret_cast<float2*>(o + 4) = make_float2(acc[1][2], acc[1][3]);
+                        part += (double)(pc[0][2] * acc[0][2]);
+                        part += (double)(pc[0][3] * acc[0][3]);
+                        part += (double)(pc[1][2] * acc[1][2]);
+                        part += (double)(pc[1][3] * acc[1][3]);
+                    }
                 }
                 __syncwarp();      // all lanes are done with this buffer before the next copies land in it
-                a0 = b0; a1 = b1; b0 = c0; b1 = c1;
+                rb0 = eB[0]; rb1 = eB[1];
+                dA = dB; dB = dC;
+                haveB = haveC;
+#pragma unroll
+                for (int k = 0; k < kRounds; k++) eB[k] = eC[k];
             }
             cp_async_wait<0>();
-            warp_add(part, sAcc, d, lane);
+            if (partDepth) warp_add(part, sAcc, partDepth, lane);
         }
         __syncthreads();
         if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&dPAp[tid], sAcc[tid]);
@@ -314,24 +481,40 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(const __grid_constan
         if (tid >= 1 && tid <= D && sActive[tid]) sAlpha[tid] = (float)((double)sR1[tid] / cg_total<MG>(P, cur, 0, tid, dPAp));
         __syncthreads();
         // ---------------- phase B: x += alpha p ; r -= alpha Ap ; r.r
-        for (int d = 1; d <= D; d++) {
+        const bool revB = P.zigzag && (phase++ & 1) != 0;
+        for (int dd = 1; dd <= D; dd++) {
+            const int d = revB ? D + 1 - dd : dd;
             if (!sActive[d]) continue;
             const float al = sAlpha[d];
-            const int i1 = P.row1[d];
+            const int i0 = P.row0[d], n4 = (P.row1[d] - i0) >> 2;
             double part = 0.0;
-            for (int i = P.row0[d] + 4 * gthread; i < i1; i += 4 * nthreads) {
-                float4 pv = *reinterpret_cast<const float4*>(P.p + i);
-                float4 av = *reinterpret_cast<const float4*>(P.Ap + i);
-                float4 xv = *reinterpret_cast<const float4*>(P.x + i);
-                float4 rv = *reinterpret_cast<const float4*>(P.r + i);
-                xv.x = __fmaf_rn(al, pv.x, xv.x); xv.y = __fmaf_rn(al, pv.y, xv.y); xv.z = __fmaf_rn(al, pv.z, xv.z); xv.w = __fmaf_rn(al, pv.w, xv.w);
-                rv.x = __fmaf_rn(-al, av.x, rv.x); rv.y = __fmaf_rn(-al, av.y, rv.y); rv.z = __fmaf_rn(-al, av.z, rv.z); rv.w = __fmaf_rn(-al, av.w, rv.w);
-                *reinterpret_cast<float4*>(P.x + i) = xv;
-                *reinterpret_cast<float4*>(P.r + i) = rv;
-                part += (double)(rv.x * rv.x);
-                part += (double)(rv.y * rv.y);
-                part += (double)(rv.z * rv.z);
-                part += (double)(rv.w * rv.w);
+            for (int c = gthread; c < n4; c += kStreamUnrollB * nthreads) {
+                float4 pv[kStreamUnrollB], av[kStreamUnrollB], xv[kStreamUnrollB], rv[kStreamUnrollB];
+#pragma unroll
+                for (int k = 0; k < kStreamUnrollB; k++) {
+                    const int ck = c + k * nthreads, ik = i0 + 4 * (revB ? n4 - 1 - ck : ck);
+                    if (ck < n4) {
+                        pv[k] = *reinterpret_cast<const float4*>(P.p + ik);
+                        av[k] = *reinterpret_cast<const float4*>(P.Ap + ik);
+                        xv[k] = *reinterpret_cast<const float4*>(P.x + ik);
+                        rv[k] = *reinterpret_cast<const float4*>(P.r + ik);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < kStreamUnrollB; k++) {
+                    const int ck = c + k * nthreads, ik = i0 + 4 * (revB ? n4 - 1 - ck : ck);
+                    if (ck < n4) {
+                        float4 xo, ro;
+                        xo.x = __fmaf_rn(al, pv[k].x, xv[k].x); xo.y = __fmaf_rn(al, pv[k].y, xv[k].y); xo.z = __fmaf_rn(al, pv[k].z, xv[k].z); xo.w = __fmaf_rn(al, pv[k].w, xv[k].w);
+                        ro.x = __fmaf_rn(-al, av[k].x, rv[k].x); ro.y = __fmaf_rn(-al, av[k].y, rv[k].y); ro.z = __fmaf_rn(-al, av[k].z, rv[k].z); ro.w = __fmaf_rn(-al, av[k].w, rv[k].w);
+                        *reinterpret_cast<float4*>(P.x + ik) = xo;
+                        *reinterpret_cast<float4*>(P.r + ik) = ro;
+                        part += (double)(ro.x * ro.x);
+                        part += (double)(ro.y * ro.y);
+                        part += (double)(ro.z * ro.z);
+                        part += (double)(ro.w * ro.w);
+                    }
+                }
             }
             warp_add(part, sAcc, d, lane);
         }
@@ -350,6 +533,12 @@ __global__ void __launch_bounds__(kCgBlock) k_cg_all_depths(const __grid_constan
     }
     if (blockIdx.x == 0 && tid >= 1 && tid <= D) { P.itersOut[tid] = sIter[tid] - 1; P.resOut[tid] = sR1[tid]; }
     if (blockIdx.x == 0 && tid == 0) P.itersOut[15] = (int)epoch;
+}
+
+int build_cg_table(Context& c) {
+    PRB_TRY(c.sgTab4.alloc(64 * (size_t)c.nSg, c.stream));
+    PRB_LAUNCH(c, k_sg_table4, grid_for(c, (i64)c.nSg * 64, 256), 256, 0, c.sgTab.p, (i64)c.nSg, c.sgTab4.p);
+    return PRB_OK;
 }
 
 int stage_solve(Context& c) {
@@ -389,13 +578,11 @@ int stage_solve(Context& c) {
     PRB_CUDA(cudaMemsetAsync(itersOut.p, 0, 16 * sizeof(int), st));
     CgParams P;
     P.D = D;
-    for (int d = 1; d <= D + 1; d++) P.gbase[d] = (c.base[d] - 1) / 8;
-    P.gbase[0] = 0;
     // super-groups: sg 0 = depth 1; depth d >= 2 owns the super-groups 1 + (sibling groups of depth d-1)
     P.sgStart[0] = 0;
     P.sgStart[1] = 0;
-    for (int d = 2; d <= D + 1; d++) P.sgStart[d] = 1 + P.gbase[d - 1];
-    P.sgTab = c.sgTab.p; P.stencil = c.dStencil.p; P.b = c.divg.p;
+    for (int d = 2; d <= D + 1; d++) P.sgStart[d] = 1 + (c.base[d - 1] - 1) / 8;
+    P.tab4 = c.sgTab4.p; P.nSg = c.nSg; P.zigzag = c.cgZigzag; P.stencil = c.dStencil.p; P.b = c.divg.p;
     P.x = c.xv; P.r = r.p + 7; P.p = pBuf + 7; P.Ap = Ap.p + 7;
     P.world = c.mg.world; P.rank = c.mg.rank; P.shardFrom = mg ? c.shardFrom : D + 1;
     for (int d = 0; d <= D + 1; d++) {
@@ -415,7 +602,7 @@ int stage_solve(Context& c) {
     float tol = (float)c.cgTol;
     P.tol2 = tol * tol;
     P.maxIter = c.cgMaxIter;
-    const size_t dynSmem = (size_t)kCgWarps * 2 * kCube * sizeof(float);
+    const size_t dynSmem = (size_t)kCgWarps * 2 * kWarpBufFloats * sizeof(float);
     const void* kern = mg ? (const void*)k_cg_all_depths<true> : (const void*)k_cg_all_depths<false>;
     PRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynSmem));
     PRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -423,7 +610,7 @@ int stage_solve(Context& c) {
     PRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kCgBlock, dynSmem));
     if (perSM < 1) { set_error("CG kernel does not fit on an SM"); return PRB_ERR_CUDA; }
     int gridSize = c.smCount * perSM;
-    i64 maxTiles = P.sgStart[D + 1];
+    i64 maxTiles = (P.sgStart[D + 1] + 3) / 4 + D;      // warp-steps of one SpMV sweep (4 super-groups each)
     i64 needBlocks = (maxTiles + kCgWarps - 1) / kCgWarps;
     if (gridSize > needBlocks) gridSize = (int)(((needBlocks + c.smCount - 1) / c.smCount) * c.smCount);   // small problems: fewer CTAs, cheaper grid syncs
     if (gridSize > c.smCount * perSM) gridSize = c.smCount * perSM;
