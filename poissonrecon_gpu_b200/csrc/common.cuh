@@ -184,6 +184,8 @@ struct Context {
     BSplineTables tab;
     DBuf<float> dMaxDepthFn, dBaseFn, dDfT, dStencil;
     DBuf<int> dDfOffset;
+    DBuf<float> dBvAnc, dBvOwn;    // base-function values at cell corners per (depth, ancestor level) (mc.cu k_build_bv)
+    int bvAncOff[kMaxDepth + 1] = {0}, bvOwnOff[kMaxDepth + 1] = {0};
     // ---- fields
     DBuf<float> V;                 // [M_D][3]
     DBuf<float> divg, x;          // x is padded: node i lives at xv[i] = x.p[7 + i] (sibling blocks 32-byte aligned)

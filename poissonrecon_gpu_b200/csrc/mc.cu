@@ -354,6 +354,148 @@ __global__ void __launch_bounds__(kVvWarps * 32) k_vertex_values_grouped(Topo T,
     }
 }
 
+// Streaming version of the kernel above (the one stage_extract launches).  Sibling groups are
+// numbered in Morton order inside a depth, so consecutive groups share almost all ancestors: a
+// warp walks a CONTIGUOUS chunk of groups and keeps the 27 neighbour values of every ancestor
+// level in shared memory, re-gathering only the levels whose ancestor changed (1.3 levels per
+// group on a surface instead of all d0 of them, and no dependent parent -> neighbour -> x chain per
+// level).  The base-function values B_{l, a+k-1}((o + pc) w) depend only on (depth, level, o/2, pc, k)
+// per axis; they come from a table filled once per context by k_build_bv with the same
+// base_value() arithmetic (bit-identical to evaluating them in place).
+struct BvTables {
+    const float4* anc;            // [d0][l < d0][g < 2^(d0-1)][pc < 3] -> (k = 0, 1, 2, unused)
+    const float4* own;            // [d0][g][pc] -> cube coordinate 0..3
+    int ancOff[kMaxDepth + 1];    // first float4 of depth d0
+    int ownOff[kMaxDepth + 1];
+};
+__global__ void __launch_bounds__(256) k_build_bv(int D, const float* __restrict__ baseFn, BvTables B, float4* __restrict__ anc, float4* __restrict__ own) {
+    for (int d0 = 1; d0 <= D; d0++) {
+        const int ng = 1 << (d0 - 1);
+        const float w = 1.0f / (float)(1 << d0);
+        const int nAnc = d0 * ng * 3;
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nAnc + ng * 3; t += gridDim.x * blockDim.x) {
+            if (t < nAnc) {
+                const int l = t / (ng * 3), g = (t / 3) % ng, pc = t % 3;
+                const int nn = 1 << l, oa = (2 * g) >> (d0 - l);
+                const float pp = (float)(2 * g + pc) * w;
+                float v[3];
+                for (int k = 0; k < 3; k++) {
+                    const int ao = oa + k - 1;
+                    v[k] = (ao >= 0 && ao < nn) ? base_value(baseFn, nn - 1 + ao, pp) : 0.f;
+                }
+                anc[B.ancOff[d0] + t] = make_float4(v[0], v[1], v[2], 0.f);
+            } else {
+                const int u = t - nAnc, g = u / 3, pc = u % 3;
+                const int nn = 1 << d0;
+                const float pp = (float)(2 * g + pc) * w;
+                float v[4];
+                for (int cu = 0; cu < 4; cu++) {
+                    const int ao = 2 * g + cu - 1;
+                    v[cu] = (ao >= 0 && ao < nn) ? base_value(baseFn, nn - 1 + ao, pp) : 0.f;
+                }
+                own[B.ownOff[d0] + u] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+    }
+}
+
+constexpr int kVsWarps = 8, kVsChunk = 32;
+__global__ void __launch_bounds__(kVsWarps * 32) k_vertex_values_stream(Topo T, int gFirst, int nGroups, int D, const int* __restrict__ parent, const int* __restrict__ child0,
+                                                                        const ushort4* __restrict__ offs, const float* __restrict__ x,
+                                                                        const float* __restrict__ baseFn, const __grid_constant__ BvTables B, float iso, float* __restrict__ vval) {
+    __shared__ float sX[kVsWarps][kMaxDepth][28];     // neighbour values of the cached ancestor of level l
+    __shared__ int sAnc[kVsWarps][kMaxDepth];         // ... and which node that is
+    __shared__ float sXc[kVsWarps][64];               // solution on the 4x4x4 node cube around the group (own level)
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int px = lane / 9, py = (lane / 3) % 3, pz = lane % 3;      // lane -> point of the group's 3x3x3 corner grid
+    const int nChunks = (nGroups + kVsChunk - 1) / kVsChunk;
+    for (int ch = blockIdx.x * kVsWarps + wp; ch < nChunks; ch += gridDim.x * kVsWarps) {
+        int curDepth = -1;
+        const int gEnd = min(gFirst + nGroups, gFirst + (ch + 1) * kVsChunk);
+        for (int g = gFirst + ch * kVsChunk; g < gEnd; g++) {
+            const int gb = 1 + 8 * g;                // first sibling (root vertices are dropped, main.cu:1634-1638)
+            const ushort4 o0 = offs[gb];
+            const int d0 = o0.w;
+            const float w = 1.0f / (float)(1 << d0);
+            __syncwarp();
+            if (d0 != curDepth) {
+                if (lane < kMaxDepth) sAnc[wp][lane] = -1;
+                curDepth = d0;
+            }
+            bool mine = false;
+            int owner = -1, jo = 0;
+            if (lane < 27) {
+                const int sx = (px + 1) >> 1, sy = (py + 1) >> 1, sz = (pz + 1) >> 1;
+                const int id = gb + ((sx << 2) | (sy << 1) | sz);
+                const int j = (px - sx) | ((py - sy) << 1) | ((pz - sz) << 2);
+                int m;
+                owner = corner_owner(T, id, j, m);
+                mine = owner >= gb && owner < gb + 8;
+                jo = j ^ m;
+            }
+            // own level: every neighbour of every sibling lies in the 4x4x4 cube around the group
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int e = lane + 32 * h, ux = e >> 4, uy = (e >> 2) & 3, uz = e & 3;
+                const int sx = ux >> 1, sy = uy >> 1, sz = uz >> 1;
+                const int j = 9 * (ux - sx) + 3 * (uy - sy) + (uz - sz);          // 9(dx+1)+3(dy+1)+(dz+1) with d = u - 1 - s
+                const int q = T.nbr[27 * (i64)(gb + ((sx << 2) | (sy << 1) | sz)) + j];
+                sXc[wp][e] = q >= 0 ? x[q] : 0.f;
+            }
+            // ancestors: re-gather the levels whose node changed since the previous group (warp-uniform walk)
+            __syncwarp();
+            {
+                int a = parent[gb];
+                for (int l = d0 - 1; l >= 0 && sAnc[wp][l] != a; --l) {
+                    if (lane < 27) {
+                        const int q = T.nbr[27 * (i64)a + lane];
+                        sX[wp][l][lane] = q >= 0 ? x[q] : 0.f;
+                    }
+                    __syncwarp();
+                    if (lane == 0) sAnc[wp][l] = a;
+                    a = parent[a];
+                }
+            }
+            __syncwarp();
+            if (mine) {
+                float val = 0.f;
+                const int gx = o0.x >> 1, gy = o0.y >> 1, gz = o0.z >> 1;
+                {
+                    const int k = owner - gb, sox = (k >> 2) & 1, soy = (k >> 1) & 1, soz = k & 1;
+                    const float4 bx = B.own[B.ownOff[d0] + gx * 3 + px], by = B.own[B.ownOff[d0] + gy * 3 + py], bz = B.own[B.ownOff[d0] + gz * 3 + pz];
+                    const float vx[3] = {sox ? bx.y : bx.x, sox ? bx.z : bx.y, sox ? bx.w : bx.z};
+                    const float vy[3] = {soy ? by.y : by.x, soy ? by.z : by.y, soy ? by.w : by.z};
+                    const float vz[3] = {soz ? bz.y : bz.x, soz ? bz.z : bz.y, soz ? bz.w : bz.z};
+                    const float* xc = &sXc[wp][sox * 16 + soy * 4 + soz];
+#pragma unroll
+                    for (int j = 0; j < 27; j++)
+                        val = __fmaf_rn(__fmul_rn(__fmul_rn(xc[(j / 9) * 16 + ((j / 3) % 3) * 4 + (j % 3)], vx[j / 9]), vy[(j / 3) % 3]), vz[j % 3], val);
+                }
+                // shared ancestor levels d0-1 .. 0
+                const int ng = 1 << (d0 - 1);
+                const float4* ba = B.anc + B.ancOff[d0];
+                for (int l = d0 - 1; l >= 0; --l) {
+                    const float4 bx = ba[(l * ng + gx) * 3 + px], by = ba[(l * ng + gy) * 3 + py], bz = ba[(l * ng + gz) * 3 + pz];
+                    const float vx[3] = {bx.x, bx.y, bx.z}, vy[3] = {by.x, by.y, by.z}, vz[3] = {bz.x, bz.y, bz.z};
+                    RV_ACC27(val, sX[wp][l], vx, vy, vz);
+                }
+                // finer nodes at this corner (vertices owned above depth D)
+                const float pos[3] = {(float)((int)o0.x + px) * w, (float)((int)o0.y + py) * w, (float)((int)o0.z + pz) * w};
+                int now = owner, depth = d0;
+                const int ex = jo ^ ((jo >> 1) & 1);      // childrenVertexKind {0,1,3,2,4,5,7,6}, MarchingCubes.cuh:721-723 (applied as the reference does)
+                while (depth < D) {
+                    ++depth;
+                    int c0 = child0[now];
+                    if (c0 < 0) break;
+                    now = c0 + ex;
+                    accumulate_level(val, T.nbr + 27 * (i64)now, offs[now], x, baseFn, pos);
+                }
+                vval[8 * (i64)owner + jo] = __fsub_rn(val, iso);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ classification of depth-D cells
 // per cell: MC case, triangle count, mask of OWNED crossed edges (v1*v2 <= 0, main.cu:2475)
 __global__ void __launch_bounds__(128) k_classify(Topo T, const float* __restrict__ vals, int valBase, unsigned char* __restrict__ cat,
@@ -1184,6 +1326,27 @@ static int refine_pass(Context& c, const int* dRoots, int nr, int rd, bool singl
     return PRB_OK;
 }
 
+// base-value tables of k_vertex_values_stream (depend on the depth only: built once per context)
+static int ensure_bv_tables(Context& c) {
+    if (c.dBvAnc.p) return PRB_OK;
+    const int D = c.D;
+    size_t na = 0, no = 0;
+    for (int d = 0; d <= kMaxDepth; d++) { c.bvAncOff[d] = 0; c.bvOwnOff[d] = 0; }
+    for (int d0 = 1; d0 <= D; d0++) {
+        const size_t ng = (size_t)1 << (d0 - 1);
+        c.bvAncOff[d0] = (int)na; c.bvOwnOff[d0] = (int)no;
+        na += (size_t)d0 * ng * 3;
+        no += ng * 3;
+    }
+    PRB_TRY(c.dBvAnc.alloc(4 * na, c.stream));
+    PRB_TRY(c.dBvOwn.alloc(4 * no, c.stream));
+    BvTables B;
+    B.anc = (const float4*)c.dBvAnc.p; B.own = (const float4*)c.dBvOwn.p;
+    for (int d = 0; d <= kMaxDepth; d++) { B.ancOff[d] = c.bvAncOff[d]; B.ownOff[d] = c.bvOwnOff[d]; }
+    PRB_LAUNCH(c, k_build_bv, c.smCount * 4, 256, 0, D, c.dBaseFn.p, B, (float4*)c.dBvAnc.p, (float4*)c.dBvOwn.p);
+    return PRB_OK;
+}
+
 int stage_extract(Context& c) {
     cudaStream_t st = c.stream;
     const int D = c.D, M = c.M;
@@ -1207,9 +1370,15 @@ int stage_extract(Context& c) {
         const i64 nGroups = (M - 1) / 8;
         const int W = c.mg.world, me = c.mg.rank;
         const int g0 = mg ? (int)((nGroups * me) / W) : 0, g1 = mg ? (int)((nGroups * (me + 1)) / W) : (int)nGroups;
-        if (g1 > g0)
-            PRB_LAUNCH(c, k_vertex_values_grouped, grid_for(c, (i64)(g1 - g0) * 32, kVvWarps * 32, 8), kVvWarps * 32, 0, R, g0, g1 - g0, D, c.parent.p, c.child0.p, c.offs.p,
-                       c.xv, c.dBaseFn.p, c.iso, c.vvalPtr);
+        if (g1 > g0) {
+            PRB_TRY(ensure_bv_tables(c));
+            BvTables B;
+            B.anc = (const float4*)c.dBvAnc.p; B.own = (const float4*)c.dBvOwn.p;
+            for (int d = 0; d <= kMaxDepth; d++) { B.ancOff[d] = c.bvAncOff[d]; B.ownOff[d] = c.bvOwnOff[d]; }
+            const i64 nChunks = ((i64)(g1 - g0) + kVsChunk - 1) / kVsChunk;
+            PRB_LAUNCH(c, k_vertex_values_stream, grid_for(c, nChunks * 32, kVsWarps * 32, 8), kVsWarps * 32, 0, R, g0, g1 - g0, D, c.parent.p, c.child0.p, c.offs.p,
+                       c.xv, c.dBaseFn.p, B, c.iso, c.vvalPtr);
+        }
         if (mg) {
             PRB_TRY(mg_barrier(c));
             for (int q = 0; q < W; q++) {
