@@ -46,7 +46,7 @@ constexpr int kUnitBz = 10, kUnitBy = 36, kCubeUnits = 145, kCubeFloats = 4 * kC
 constexpr int kWarpBufFloats = 4 * kCubeFloats;          // 4 cubes per warp-step
 constexpr int kRounds = 12;                               // 96 half-blocks / 8 lanes
 constexpr int kPrefetchSteps = 2;                         // L2 prefetch distance of the SpMV table, in steps beyond the register pipeline
-constexpr int kStreamUnroll = 6, kStreamUnrollB = 3;     // independent 16-byte loads per array per thread in the streaming phases
+constexpr int kStreamUnroll = 4, kStreamUnrollB = 3;     // independent 16-byte loads per array per thread in the streaming phases
 
 // Staging plan of a quarter-warp: in round r (12 rounds x 8 lanes = the 96 half-blocks) lane li
 // copies one 16-byte half-block.  The cost of the gather is the number of distinct 128-byte
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
                     if (ck < n4) {
                         pv[k] = *reinterpret_cast<const float4*>(P.p + ik);
                         av[k] = *reinterpret_cast<const float4*>(P.Ap + ik);
-                        xv[k] = __ldcs(reinterpret_cast<const float4*>(P.x + ik));      // x is touched once per iteration: keep it out of the L2 working set
+                        xv[k] = *reinterpret_cast<const float4*>(P.x + ik);
                         rv[k] = *reinterpret_cast<const float4*>(P.r + ik);
                     }
                 }
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
                         float4 xo, ro;
                         xo.x = __fmaf_rn(al, pv[k].x, xv[k].x); xo.y = __fmaf_rn(al, pv[k].y, xv[k].y); xo.z = __fmaf_rn(al, pv[k].z, xv[k].z); xo.w = __fmaf_rn(al, pv[k].w, xv[k].w);
                         ro.x = __fmaf_rn(-al, av[k].x, rv[k].x); ro.y = __fmaf_rn(-al, av[k].y, rv[k].y); ro.z = __fmaf_rn(-al, av[k].z, rv[k].z); ro.w = __fmaf_rn(-al, av[k].w, rv[k].w);
-                        __stcs(reinterpret_cast<float4*>(P.x + ik), xo);
+                        *reinterpret_cast<float4*>(P.x + ik) = xo;
                         *reinterpret_cast<float4*>(P.r + ik) = ro;
                         part += (double)(ro.x * ro.x);
                         part += (double)(ro.y * ro.y);
