@@ -414,99 +414,128 @@ __global__ void __launch_bounds__(256) k_build_bv(int D, const float* __restrict
     }
 }
 
-constexpr int kVsWarps = 8, kVsChunk = 32;
+// A group owns only ~8 of the 27 points of its corner grid (every vertex belongs to exactly one
+// cell), so a warp takes FOUR consecutive groups per step: their owned points are compacted
+// (ballot) into a list and handed out one per lane, each lane reading the staged neighbour
+// values of its own group's slot.  The 27-term sums -- the bulk of the work -- then run with all
+// lanes busy instead of one in four.
+constexpr int kVsWarps = 4, kVsChunk = 32, kVsSlots = 4;
+constexpr int kVsSlotStride = kMaxDepth * 28 + 8;     // floats; 8 mod 32 apart: the four slots sit in different banks
 __global__ void __launch_bounds__(kVsWarps * 32) k_vertex_values_stream(Topo T, int gFirst, int nGroups, int D, const int* __restrict__ parent, const int* __restrict__ child0,
                                                                         const ushort4* __restrict__ offs, const float* __restrict__ x,
                                                                         const float* __restrict__ baseFn, const __grid_constant__ BvTables B, float iso, float* __restrict__ vval) {
-    __shared__ float sX[kVsWarps][kMaxDepth][28];     // neighbour values of the cached ancestor of level l
-    __shared__ int sAnc[kVsWarps][kMaxDepth];         // ... and which node that is
-    __shared__ float sXc[kVsWarps][64];               // solution on the 4x4x4 node cube around the group (own level)
+    __shared__ __align__(16) float sX[kVsWarps][kVsSlots * kVsSlotStride];   // [slot][level][28]: neighbour values of the slot's cached ancestors
+    __shared__ int sAnc[kVsWarps][kVsSlots][kMaxDepth];                       // ... and which nodes those are
+    __shared__ float sXc[kVsWarps][kVsSlots][64];                             // solution on the 4x4x4 node cube around each group (own level)
+    __shared__ unsigned short sPt[kVsWarps][kVsSlots * 27];                  // owned points: slot | point << 2 | (owner - gb) << 7 | jo << 10
+    __shared__ ushort4 sO0[kVsWarps][kVsSlots];
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    const int px = lane / 9, py = (lane / 3) % 3, pz = lane % 3;      // lane -> point of the group's 3x3x3 corner grid
+    const int px = lane / 9, py = (lane / 3) % 3, pz = lane % 3;      // lane -> point of a group's 3x3x3 corner grid (staging)
     const int nChunks = (nGroups + kVsChunk - 1) / kVsChunk;
     for (int ch = blockIdx.x * kVsWarps + wp; ch < nChunks; ch += gridDim.x * kVsWarps) {
-        int curDepth = -1;
         const int gEnd = min(gFirst + nGroups, gFirst + (ch + 1) * kVsChunk);
-        for (int g = gFirst + ch * kVsChunk; g < gEnd; g++) {
-            const int gb = 1 + 8 * g;                // first sibling (root vertices are dropped, main.cu:1634-1638)
-            const ushort4 o0 = offs[gb];
-            const int d0 = o0.w;
+        int curDepth = -1;
+        for (int g0 = gFirst + ch * kVsChunk; g0 < gEnd;) {
+            const int d0 = offs[1 + 8 * g0].w;
             const float w = 1.0f / (float)(1 << d0);
             __syncwarp();
             if (d0 != curDepth) {
-                if (lane < kMaxDepth) sAnc[wp][lane] = -1;
+                for (int t = lane; t < kVsSlots * kMaxDepth; t += 32) sAnc[wp][t / kMaxDepth][t % kMaxDepth] = -1;
                 curDepth = d0;
+                __syncwarp();
             }
-            bool mine = false;
-            int owner = -1, jo = 0;
-            if (lane < 27) {
-                const int sx = (px + 1) >> 1, sy = (py + 1) >> 1, sz = (pz + 1) >> 1;
-                const int id = gb + ((sx << 2) | (sy << 1) | sz);
-                const int j = (px - sx) | ((py - sy) << 1) | ((pz - sz) << 2);
-                int m;
-                owner = corner_owner(T, id, j, m);
-                mine = owner >= gb && owner < gb + 8;
-                jo = j ^ m;
-            }
-            // own level: every neighbour of every sibling lies in the 4x4x4 cube around the group
+            // ---- stage up to four groups of this depth
+            int nq = 0, np = 0;
+            for (; nq < kVsSlots && g0 + nq < gEnd; nq++) {
+                const int gb = 1 + 8 * (g0 + nq);            // first sibling (root vertices are dropped, main.cu:1634-1638)
+                const ushort4 o0 = offs[gb];
+                if (o0.w != d0) break;                        // the next depth starts here: it gets its own step
+                bool mine = false;
+                int owner = -1, jo = 0;
+                if (lane < 27) {
+                    const int sx = (px + 1) >> 1, sy = (py + 1) >> 1, sz = (pz + 1) >> 1;
+                    const int id = gb + ((sx << 2) | (sy << 1) | sz);
+                    const int j = (px - sx) | ((py - sy) << 1) | ((pz - sz) << 2);
+                    int m;
+                    owner = corner_owner(T, id, j, m);
+                    mine = owner >= gb && owner < gb + 8;
+                    jo = j ^ m;
+                }
+                const unsigned mm = __ballot_sync(0xffffffffu, mine);
+                if (mine) sPt[wp][np + __popc(mm & ((1u << lane) - 1u))] = (unsigned short)(nq | (lane << 2) | ((owner - gb) << 7) | (jo << 10));
+                np += __popc(mm);
+                if (lane == 0) sO0[wp][nq] = o0;
+                // own level: every neighbour of every sibling lies in the 4x4x4 cube around the group
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int e = lane + 32 * h, ux = e >> 4, uy = (e >> 2) & 3, uz = e & 3;
-                const int sx = ux >> 1, sy = uy >> 1, sz = uz >> 1;
-                const int j = 9 * (ux - sx) + 3 * (uy - sy) + (uz - sz);          // 9(dx+1)+3(dy+1)+(dz+1) with d = u - 1 - s
-                const int q = T.nbr[27 * (i64)(gb + ((sx << 2) | (sy << 1) | sz)) + j];
-                sXc[wp][e] = q >= 0 ? x[q] : 0.f;
-            }
-            // ancestors: re-gather the levels whose node changed since the previous group (warp-uniform walk)
-            __syncwarp();
-            {
+                for (int h = 0; h < 2; h++) {
+                    const int e = lane + 32 * h, ux = e >> 4, uy = (e >> 2) & 3, uz = e & 3;
+                    const int sx = ux >> 1, sy = uy >> 1, sz = uz >> 1;
+                    const int j = 9 * (ux - sx) + 3 * (uy - sy) + (uz - sz);          // 9(dx+1)+3(dy+1)+(dz+1) with d = u - 1 - s
+                    const int q = T.nbr[27 * (i64)(gb + ((sx << 2) | (sy << 1) | sz)) + j];
+                    sXc[wp][nq][e] = q >= 0 ? x[q] : 0.f;
+                }
+                // ancestors: re-gather the levels whose node changed since this slot's previous group (warp-uniform walk)
                 int a = parent[gb];
-                for (int l = d0 - 1; l >= 0 && sAnc[wp][l] != a; --l) {
+                float* sx_ = &sX[wp][nq * kVsSlotStride];
+                for (int l = d0 - 1; l >= 0 && sAnc[wp][nq][l] != a; --l) {
                     if (lane < 27) {
                         const int q = T.nbr[27 * (i64)a + lane];
-                        sX[wp][l][lane] = q >= 0 ? x[q] : 0.f;
+                        sx_[l * 28 + lane] = q >= 0 ? x[q] : 0.f;
                     }
                     __syncwarp();
-                    if (lane == 0) sAnc[wp][l] = a;
+                    if (lane == 0) sAnc[wp][nq][l] = a;
                     a = parent[a];
                 }
             }
             __syncwarp();
-            if (mine) {
-                float val = 0.f;
-                const int gx = o0.x >> 1, gy = o0.y >> 1, gz = o0.z >> 1;
-                {
-                    const int k = owner - gb, sox = (k >> 2) & 1, soy = (k >> 1) & 1, soz = k & 1;
-                    const float4 bx = B.own[B.ownOff[d0] + gx * 3 + px], by = B.own[B.ownOff[d0] + gy * 3 + py], bz = B.own[B.ownOff[d0] + gz * 3 + pz];
-                    const float vx[3] = {sox ? bx.y : bx.x, sox ? bx.z : bx.y, sox ? bx.w : bx.z};
-                    const float vy[3] = {soy ? by.y : by.x, soy ? by.z : by.y, soy ? by.w : by.z};
-                    const float vz[3] = {soz ? bz.y : bz.x, soz ? bz.z : bz.y, soz ? bz.w : bz.z};
-                    const float* xc = &sXc[wp][sox * 16 + soy * 4 + soz];
+            // ---- one owned point per lane
+            const int ng = 1 << (d0 - 1);
+            const float4* ba = B.anc + B.ancOff[d0];
+            for (int p0 = 0; p0 < np; p0 += 32) {
+                if (p0 + lane < np) {
+                    const int e = sPt[wp][p0 + lane];
+                    const int q = e & 3, pt = (e >> 2) & 31, k = (e >> 7) & 7, jo = (e >> 10) & 7;
+                    const int qx = pt / 9, qy = (pt / 3) % 3, qz = pt % 3;
+                    const ushort4 o0 = sO0[wp][q];
+                    const int gb = 1 + 8 * (g0 + q);
+                    const int gx = o0.x >> 1, gy = o0.y >> 1, gz = o0.z >> 1;
+                    float val = 0.f;
+                    {
+                        const int sox = (k >> 2) & 1, soy = (k >> 1) & 1, soz = k & 1;
+                        const float4 bx = B.own[B.ownOff[d0] + gx * 3 + qx], by = B.own[B.ownOff[d0] + gy * 3 + qy], bz = B.own[B.ownOff[d0] + gz * 3 + qz];
+                        const float vx[3] = {sox ? bx.y : bx.x, sox ? bx.z : bx.y, sox ? bx.w : bx.z};
+                        const float vy[3] = {soy ? by.y : by.x, soy ? by.z : by.y, soy ? by.w : by.z};
+                        const float vz[3] = {soz ? bz.y : bz.x, soz ? bz.z : bz.y, soz ? bz.w : bz.z};
+                        const float* xc = &sXc[wp][q][sox * 16 + soy * 4 + soz];
 #pragma unroll
-                    for (int j = 0; j < 27; j++)
-                        val = __fmaf_rn(__fmul_rn(__fmul_rn(xc[(j / 9) * 16 + ((j / 3) % 3) * 4 + (j % 3)], vx[j / 9]), vy[(j / 3) % 3]), vz[j % 3], val);
+                        for (int j = 0; j < 27; j++)
+                            val = __fmaf_rn(__fmul_rn(__fmul_rn(xc[(j / 9) * 16 + ((j / 3) % 3) * 4 + (j % 3)], vx[j / 9]), vy[(j / 3) % 3]), vz[j % 3], val);
+                    }
+                    // shared ancestor levels d0-1 .. 0
+                    const float* sx_ = &sX[wp][q * kVsSlotStride];
+                    for (int l = d0 - 1; l >= 0; --l) {
+                        const float4 bx = ba[(l * ng + gx) * 3 + qx], by = ba[(l * ng + gy) * 3 + qy], bz = ba[(l * ng + gz) * 3 + qz];
+                        const float vx[3] = {bx.x, bx.y, bx.z}, vy[3] = {by.x, by.y, by.z}, vz[3] = {bz.x, bz.y, bz.z};
+                        RV_ACC27(val, sx_ + l * 28, vx, vy, vz);
+                    }
+                    // finer nodes at this corner (vertices owned above depth D)
+                    const int owner = gb + k;
+                    if (d0 < D) {
+                        const float pos[3] = {(float)((int)o0.x + qx) * w, (float)((int)o0.y + qy) * w, (float)((int)o0.z + qz) * w};
+                        int now = owner, depth = d0;
+                        const int ex = jo ^ ((jo >> 1) & 1);      // childrenVertexKind {0,1,3,2,4,5,7,6}, MarchingCubes.cuh:721-723 (applied as the reference does)
+                        while (depth < D) {
+                            ++depth;
+                            int c0 = child0[now];
+                            if (c0 < 0) break;
+                            now = c0 + ex;
+                            accumulate_level(val, T.nbr + 27 * (i64)now, offs[now], x, baseFn, pos);
+                        }
+                    }
+                    vval[8 * (i64)owner + jo] = __fsub_rn(val, iso);
                 }
-                // shared ancestor levels d0-1 .. 0
-                const int ng = 1 << (d0 - 1);
-                const float4* ba = B.anc + B.ancOff[d0];
-                for (int l = d0 - 1; l >= 0; --l) {
-                    const float4 bx = ba[(l * ng + gx) * 3 + px], by = ba[(l * ng + gy) * 3 + py], bz = ba[(l * ng + gz) * 3 + pz];
-                    const float vx[3] = {bx.x, bx.y, bx.z}, vy[3] = {by.x, by.y, by.z}, vz[3] = {bz.x, bz.y, bz.z};
-                    RV_ACC27(val, sX[wp][l], vx, vy, vz);
-                }
-                // finer nodes at this corner (vertices owned above depth D)
-                const float pos[3] = {(float)((int)o0.x + px) * w, (float)((int)o0.y + py) * w, (float)((int)o0.z + pz) * w};
-                int now = owner, depth = d0;
-                const int ex = jo ^ ((jo >> 1) & 1);      // childrenVertexKind {0,1,3,2,4,5,7,6}, MarchingCubes.cuh:721-723 (applied as the reference does)
-                while (depth < D) {
-                    ++depth;
-                    int c0 = child0[now];
-                    if (c0 < 0) break;
-                    now = c0 + ex;
-                    accumulate_level(val, T.nbr + 27 * (i64)now, offs[now], x, baseFn, pos);
-                }
-                vval[8 * (i64)owner + jo] = __fsub_rn(val, iso);
             }
+            g0 += nq;
         }
     }
 }
@@ -1131,16 +1160,30 @@ __global__ void __launch_bounds__(512) k_rv_classify_brick(RGeom G, unsigned cha
     const unsigned l0 = (unsigned)(cell0 - (i64)r * G.per);
     const int bx = (int)compact3(l0 >> 2), by = (int)compact3(l0 >> 1), bz = (int)compact3(l0);   // root-local origin of the brick
     const int cx = (int)compact3((unsigned)tid >> 2), cy = (int)compact3((unsigned)tid >> 1), cz = (int)compact3((unsigned)tid);
-    sV[(cx + 1) * 81 + (cy + 1) * 9 + (cz + 1)] = G.val7[cell0 + tid];
+    const float own = G.val7[cell0 + tid];
+    sV[(cx + 1) * 81 + (cy + 1) * 9 + (cz + 1)] = own;
+    bool pos = own > 0.f, neg = own < 0.f;
     if (tid < 217) {
         // points with a zero brick-local coordinate: 81 with x = 0, 72 with y = 0 (x >= 1), 64 with z = 0 (x, y >= 1)
         int gx, gy, gz;
         if (tid < 81) { gx = 0; gy = tid / 9; gz = tid % 9; }
         else if (tid < 153) { int t = tid - 81; gx = 1 + t / 9; gy = 0; gz = t % 9; }
         else { int t = tid - 153; gx = 1 + t / 8; gy = 1 + t % 8; gz = 0; }
-        sV[gx * 81 + gy * 9 + gz] = rv_point_value(G, r, bx + gx, by + gy, bz + gz);
+        const float f = rv_point_value(G, r, bx + gx, by + gy, bz + gz);
+        sV[gx * 81 + gy * 9 + gz] = f;
+        pos = pos && f > 0.f; neg = neg && f < 0.f;
     }
-    __syncthreads();
+    // a brick whose 729 grid values all have the same strict sign has no crossed edge and the
+    // same trivial case (0 or 255, both without triangles) in every cell: nothing else to do
+    const int allPos = __syncthreads_and(pos), allNeg = __syncthreads_and(neg);
+    if (allPos || allNeg) {
+        const i64 t = cell0 + tid;
+        const int c = allNeg ? 255 : 0;
+        cat[t] = (unsigned char)c;
+        ntri[t] = cMcCount[c];
+        emask[t] = 0;
+        return;
+    }
     float v[8];
 #pragma unroll
     for (int q = 0; q < 8; q++) {

@@ -34,7 +34,8 @@ for r in rows[2:]:
         v = int(r[i] or 0)
         if v: a[4][hdr[i]] += v
 print('total samples', tot)
-srcl = open('/root/repo/poissonrecon_gpu_b200/csrc/solver.cu').read().splitlines() if 'solver' in cubin else None
+import os
+srcl = open('/root/repo/poissonrecon_gpu_b200/csrc/' + os.path.basename(cubin).split('.')[0] + '.cu').read().splitlines()
 for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     st = ', '.join(f'{k[6:]}={v}' for k, v in a[4].most_common(3))
     text = srcl[ln - 1].strip()[:70] if (srcl and ln) else ''
