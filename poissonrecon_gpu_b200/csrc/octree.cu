@@ -141,37 +141,74 @@ __global__ void __launch_bounds__(128) k_fill_groups(NodeArrays A, int d, int D,
                                                      const int* __restrict__ fc, const u64* __restrict__ ckey, const int* __restrict__ cfp,
                                                      const int* __restrict__ cfdm1) {
     int shift = 3 * (D - d);
-    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < nGroups; g += gridDim.x * blockDim.x) {
-        int r0 = fc[g], r1 = fc[g + 1];
+    // the 8 records of a group are computed by one thread and then transposed through shared
+    // memory, so that every store instruction of a warp writes 32 consecutive nodes
+    __shared__ int sT[4][32 * 9];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    int* tile = sT[wp];
+    for (int gw = (blockIdx.x * blockDim.x + threadIdx.x) - lane; gw < nGroups; gw += gridDim.x * blockDim.x) {
+        const int g = gw + lane;
+        const bool act = g < nGroups;
         int pn[8], pi[8], dn[8], di[8], ch[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) { pn[k] = 0; pi[k] = 0; dn[k] = (d == D) ? 1 : 0; di[k] = 0; ch[k] = -1; }
         int firstP = 0, firstD = 0;
-        for (int r = r0; r < r1; r++) {
-            int cc = (int)((ckey[r] >> shift) & 7);
-            int p0 = cfp[r], p1 = cfp[r + 1];
-            int dd0 = 0, dd1 = 0;
-            if (d < D) { dd0 = 8 * cfdm1[r]; dd1 = 8 * cfdm1[r + 1]; }
-            if (r == r0) { firstP = p0; firstD = dd0; }
+        u64 kbase = 0;
+        int par = 0;
+        if (act) {
+            int r0 = fc[g], r1 = fc[g + 1];
+            for (int r = r0; r < r1; r++) {
+                int cc = (int)((ckey[r] >> shift) & 7);
+                int p0 = cfp[r], p1 = cfp[r + 1];
+                int dd0 = 0, dd1 = 0;
+                if (d < D) { dd0 = 8 * cfdm1[r]; dd1 = 8 * cfdm1[r + 1]; }
+                if (r == r0) { firstP = p0; firstD = dd0; }
 #pragma unroll
-            for (int k = 0; k < 8; k++)
-                if (k == cc) { pn[k] = p1 - p0; pi[k] = p0; dn[k] = (d == D) ? 1 : dd1 - dd0; di[k] = dd0; ch[k] = (d < D) ? baseChild + 8 * r : -1; }
+                for (int k = 0; k < 8; k++)
+                    if (k == cc) { pn[k] = p1 - p0; pi[k] = p0; dn[k] = (d == D) ? 1 : dd1 - dd0; di[k] = dd0; ch[k] = (d < D) ? baseChild + 8 * r : -1; }
+            }
+            kbase = pkey[g];
+            par = baseParent + pslot[g];
         }
         int nowP = firstP, nowD = firstD;
-        u64 kbase = pkey[g];
-        int par = baseParent + pslot[g];
-        int i0 = baseD + 8 * g;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            A.key[i0 + k] = kbase | ((u64)k << shift);
-            A.parent[i0 + k] = par;
-            A.child0[i0 + k] = ch[k];
-            A.pnum[i0 + k] = pn[k];
-            A.pidx[i0 + k] = nowP;
-            nowP += pn[k];
-            A.dnum[i0 + k] = dn[k];
-            if (d == D) A.didx[i0 + k] = 8 * g + k;
-            else { A.didx[i0 + k] = nowD; nowD += dn[k]; }
+            pi[k] = nowP; nowP += pn[k];
+            if (d == D) di[k] = 8 * g + k; else { di[k] = nowD; nowD += dn[k]; }
+        }
+        const int i0w = baseD + 8 * gw;                     // first node of the warp's 32 groups
+        const int nw = 8 * min(32, nGroups - gw);            // nodes of this warp step
+        auto flush = [&](const int (&v)[8], int* __restrict__ dst) {
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; k++) tile[lane * 9 + k] = v[k];
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int idx = r * 32 + lane;
+                if (idx < nw) dst[i0w + idx] = tile[(idx >> 3) * 9 + (idx & 7)];
+            }
+        };
+        flush(ch, A.child0);
+        flush(pn, A.pnum);
+        flush(pi, A.pidx);
+        flush(dn, A.dnum);
+        flush(di, A.didx);
+        // parent and key: the group's value is shared by its 8 nodes (key: plus the child code)
+        __syncwarp();
+        tile[lane * 9] = par;
+        tile[lane * 9 + 1] = (int)(unsigned)(kbase & 0xffffffffu);
+        tile[lane * 9 + 2] = (int)(unsigned)(kbase >> 32);
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int idx = r * 32 + lane;
+            if (idx < nw) {
+                const int gl = idx >> 3, k = idx & 7;
+                A.parent[i0w + idx] = tile[gl * 9];
+                const u64 kb = (u64)(unsigned)tile[gl * 9 + 1] | ((u64)(unsigned)tile[gl * 9 + 2] << 32);
+                A.key[i0w + idx] = kb | ((u64)k << shift);
+            }
         }
     }
 }
@@ -191,17 +228,35 @@ __global__ void __launch_bounds__(256) k_node_offsets(const u64* __restrict__ ke
         offs[base + l] = make_ushort4((unsigned short)ox, (unsigned short)oy, (unsigned short)oz, (unsigned short)d);
     }
 }
-// neighbours of depth d from the parents' (main.cu:492-509), one thread per (node, slot)
+// neighbours of depth d from the parents' (main.cu:492-509).  One WARP per sibling group: the 8
+// siblings share the parent, so its 27 neighbours and their first-child indices are fetched
+// once (one lane each) and the group's 216 table entries -- one contiguous 864-byte record --
+// are produced from them with shuffles through the closed-form LUT.
 __global__ void __launch_bounds__(256) k_neighbours(const int* __restrict__ parent, const int* __restrict__ child0, int* __restrict__ neighs, int base, int count) {
-    i64 total = (i64)count * 27;
-    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
-        int l = (int)(t / 27), j = (int)(t - (i64)l * 27);
-        int i = base + l, c = l & 7, pj, cc;
-        lut_parent_child(c, j, pj, cc);
-        int np = neighs[27 * (i64)parent[i] + pj];
-        int out = -1;
-        if (np >= 0) { int c0 = child0[np]; if (c0 >= 0) out = c0 + cc; }
-        neighs[27 * (i64)i + j] = out;
+    __shared__ unsigned char sLut[216];          // (c, j) -> pj | cc << 5
+    for (int t = threadIdx.x; t < 216; t += blockDim.x) {
+        int pj, cc;
+        lut_parent_child(t / 27, t % 27, pj, cc);
+        sLut[t] = (unsigned char)(pj | (cc << 5));
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, nGroups = count >> 3;
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < nGroups; g += (gridDim.x * blockDim.x) >> 5) {
+        const int i0 = base + 8 * g;
+        const int P = parent[i0];
+        int c0 = -1;
+        if (lane < 27) {
+            const int np = neighs[27 * (i64)P + lane];
+            if (np >= 0) c0 = child0[np];
+        }
+        int* out = neighs + 27 * (i64)i0;
+#pragma unroll
+        for (int r = 0; r < 7; r++) {
+            const int t = r * 32 + lane;
+            const int e = sLut[t < 216 ? t : 0];
+            const int v = __shfl_sync(0xffffffffu, c0, e & 31);
+            if (t < 216) out[t] = v >= 0 ? v + (e >> 5) : -1;
+        }
     }
 }
 __global__ void k_root_neighbours(int* __restrict__ neighs) {
@@ -382,7 +437,7 @@ int stage_octree(Context& c) {
     // ---- A6 neighbours, level by level
     PRB_LAUNCH(c, k_root_neighbours, 1, 32, 0, c.neighs.p);
     for (int d = 1; d <= D; d++)
-        PRB_LAUNCH(c, k_neighbours, grid_for(c, (i64)c.cnt[d] * 27, 256), 256, 0, c.parent.p, c.child0.p, c.neighs.p, c.base[d], c.cnt[d]);
+        PRB_LAUNCH(c, k_neighbours, grid_for(c, (i64)c.cnt[d] * 4, 256), 256, 0, c.parent.p, c.child0.p, c.neighs.p, c.base[d], c.cnt[d]);
     // super-groups: depth 1, then one per sibling group of depths 1..D-1
     c.nSg = 1 + (c.base[D] - 1) / 8;
     PRB_TRY(c.sgTab.alloc(64 * (size_t)c.nSg, st));
