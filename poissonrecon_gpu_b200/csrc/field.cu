@@ -67,32 +67,55 @@ __global__ void __launch_bounds__(128) k_splat_weights(const float* __restrict__
         }
     }
 }
+// One lane per depth-D slot, four sibling groups per warp.  The 27 neighbours of the 8 siblings of a
+// group all lie in the 4x4x4 node cube around it, so the sample ranges (pidx, pnum) of those 64
+// nodes are fetched once per group into shared memory (192 gathers instead of 8 x 27 x 3); every
+// slot then adds its terms in the reference's order: neighbour j = 0..26, samples ascending.
 __global__ void __launch_bounds__(128) k_splat(const float* __restrict__ W, const float* __restrict__ Nr,
                                                const int* __restrict__ neighs, const int* __restrict__ pidx, const int* __restrict__ pnum,
                                                int baseD, int countD, float* __restrict__ V) {
-    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < countD; l += gridDim.x * blockDim.x) {
-        int i = baseD + l;
-        float val[3] = {0.f, 0.f, 0.f};
-        const int* nb = neighs + 27 * (i64)i;
+    __shared__ int2 sInfo[4][4][64];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int nGroups = countD >> 3, nSteps = (nGroups + 3) >> 2;
+    for (int st = blockIdx.x * 4 + wp; st < nSteps; st += gridDim.x * 4) {
+        const int g0 = 4 * st;
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 27; j++) {
-            int n = nb[j];
-            if (n < 0) continue;
-            int p0 = pidx[n], pn = pnum[n];
-            // the slot lies at direction -d_j of the sample's leaf: weight index t = 2 - (digit of j)
-            const int tx = 2 - j / 9, ty = 2 - (j / 3) % 3, tz = 2 - j % 3;
-            for (int k = 0; k < pn; k++) {
-                i64 q = p0 + k;
-                const float* wq = W + 9 * q;
-                float w = __fmul_rn(__fmul_rn(wq[tx], wq[3 + ty]), wq[6 + tz]);
-                val[0] = __fmaf_rn(w, Nr[3 * q], val[0]);
-                val[1] = __fmaf_rn(w, Nr[3 * q + 1], val[1]);
-                val[2] = __fmaf_rn(w, Nr[3 * q + 2], val[2]);
+        for (int rr = 0; rr < 8; rr++) {
+            const int q = rr >> 1, e = lane + 32 * (rr & 1), ux = e >> 4, uy = (e >> 2) & 3, uz = e & 3;
+            const int sx = ux >> 1, sy = uy >> 1, sz = uz >> 1;
+            const int j = 9 * (ux - sx) + 3 * (uy - sy) + (uz - sz);          // 9(dx+1)+3(dy+1)+(dz+1) with d = u - 1 - s
+            int2 info = make_int2(0, 0);
+            if (g0 + q < nGroups) {
+                const int n = neighs[27 * (i64)(baseD + 8 * (g0 + q) + ((sx << 2) | (sy << 1) | sz)) + j];
+                if (n >= 0) info = make_int2(pidx[n], pnum[n]);
             }
+            sInfo[wp][q][e] = info;
         }
-        V[3 * (i64)l] = val[0];
-        V[3 * (i64)l + 1] = val[1];
-        V[3 * (i64)l + 2] = val[2];
+        __syncwarp();
+        const int q = lane >> 3, k = lane & 7;
+        if (g0 + q < nGroups) {
+            const int l = 8 * (g0 + q) + k;
+            const int sx = (k >> 2) & 1, sy = (k >> 1) & 1, sz = k & 1;
+            float val[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 27; j++) {
+                const int2 info = sInfo[wp][q][(sx + j / 9) * 16 + (sy + (j / 3) % 3) * 4 + (sz + j % 3)];
+                // the slot lies at direction -d_j of the sample's leaf: weight index t = 2 - (digit of j)
+                const int tx = 2 - j / 9, ty = 2 - (j / 3) % 3, tz = 2 - j % 3;
+                for (int t = 0; t < info.y; t++) {
+                    const i64 sq = info.x + t;
+                    const float* wq = W + 9 * sq;
+                    const float w = __fmul_rn(__fmul_rn(wq[tx], wq[3 + ty]), wq[6 + tz]);
+                    val[0] = __fmaf_rn(w, Nr[3 * sq], val[0]);
+                    val[1] = __fmaf_rn(w, Nr[3 * sq + 1], val[1]);
+                    val[2] = __fmaf_rn(w, Nr[3 * sq + 2], val[2]);
+                }
+            }
+            V[3 * (i64)l] = val[0];
+            V[3 * (i64)l + 1] = val[1];
+            V[3 * (i64)l + 2] = val[2];
+        }
     }
 }
 
@@ -145,6 +168,52 @@ __global__ void __launch_bounds__(256) k_divergence(const float* __restrict__ V,
             }
         }
         if (lane == 0 && l < count) divg[base + l] = (float)val;
+    }
+}
+
+// Depths D-2 / D-3: one warp per node over the CONCATENATED slot ranges of its 27 neighbours.
+// A neighbour of a surface octree often owns only 8 or 16 depth-D slots, so a lane-strided loop
+// per neighbour (k_divergence<32>) leaves most lanes idle; here element e of the concatenation
+// goes to lane e mod 32 and every lane advances its own segment cursor (the cursor only moves
+// forward: amortised O(1) shared-memory look-ups per element).  Terms as in k_divergence<1>;
+// the double-precision summation order differs (tolerance stated in tests/test_parity_gpu.py).
+__global__ void __launch_bounds__(256) k_divergence_flat(const float* __restrict__ V, const ushort4* __restrict__ offs, const int* __restrict__ neighs,
+                                                         const int* __restrict__ didx, const int* __restrict__ dnum, const float* __restrict__ dfRow,
+                                                         int base, int count, int baseD, int k /* 2^(D-d) */, float* __restrict__ divg) {
+    __shared__ int sEnd[8][28], sOff[8][28];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    for (int l = blockIdx.x * 8 + wp; l < count; l += gridDim.x * 8) {
+        const int i = base + l;
+        const ushort4 o = offs[i];
+        const int bx = k * ((int)o.x - 1), by = k * ((int)o.y - 1), bz = k * ((int)o.z - 1);
+        int s0 = 0, cnt = 0;
+        if (lane < 27) {
+            const int n = neighs[27 * (i64)i + lane];
+            if (n >= 0) { s0 = didx[n]; cnt = dnum[n]; }
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        const int total = __shfl_sync(0xffffffffu, incl, 26);
+        __syncwarp();
+        if (lane < 27) { sEnd[wp][lane] = incl; sOff[wp][lane] = s0 - (incl - cnt); }
+        if (lane == 27) { sEnd[wp][27] = 0x7fffffff; sOff[wp][27] = 0; }
+        __syncwarp();
+        double val = 0.0;
+        int seg = 0, segEnd = sEnd[wp][0];
+        for (int e = lane; e < total; e += 32) {
+            while (e >= segEnd) segEnd = sEnd[wp][++seg];
+            const int s = sOff[wp][seg] + e;
+            const ushort4 so = offs[baseD + s];
+            const float u0 = dfRow[(int)so.x - bx], u1 = dfRow[(int)so.y - by], u2 = dfRow[(int)so.z - bz];
+            float dp = __fmul_rn(V[3 * (i64)s], u0);                  // DotProduct (main.cu:966-972)
+            dp = __fmaf_rn(V[3 * (i64)s + 1], u1, dp);
+            dp = __fmaf_rn(V[3 * (i64)s + 2], u2, dp);
+            val += (double)dp;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) val += __shfl_down_sync(0xffffffffu, val, d);
+        if (lane == 0) divg[i] = (float)val;
     }
 }
 
@@ -287,7 +356,7 @@ int stage_splat(Context& c) {
         DBuf<float> W;
         PRB_TRY(W.alloc(9 * (size_t)c.N, st));
         PRB_LAUNCH(c, k_splat_weights, grid_for(c, c.N, 128, 16), 128, 0, c.dMaxDepthFn.p, c.P.p, c.p2n.p, c.offs.p + c.base[D], c.N, width, W.p);
-        PRB_LAUNCH(c, k_splat, grid_for(c, c.cnt[D], 128, 16), 128, 0, W.p, c.Nr.p, c.neighs.p, c.pidx.p, c.pnum.p, c.base[D], c.cnt[D], c.V.p);
+        PRB_LAUNCH(c, k_splat, grid_for(c, (i64)c.cnt[D], 128, 16), 128, 0, W.p, c.Nr.p, c.neighs.p, c.pidx.p, c.pnum.p, c.base[D], c.cnt[D], c.V.p);
         W.release();
     }
     PRB_CUDA(cudaEventRecord(c.ev[3], st));
@@ -333,7 +402,7 @@ int stage_divergence(Context& c) {
         else if (d == D - 1)
             PRB_LAUNCH(c, k_divergence_dm1, grid_for(c, n, 256), 256, 0, c.V.p, c.neighs.p, c.child0.p, row, first, n, c.base[D], c.divg.p);
         else
-            PRB_LAUNCH(c, k_divergence<32>, grid_for(c, (i64)n * 32, 256), 256, 0, c.V.p, c.offs.p, c.neighs.p, c.didx.p, c.dnum.p, row, first, n, c.base[D], k, c.divg.p);
+            PRB_LAUNCH(c, k_divergence_flat, grid_for(c, (i64)n * 32, 256), 256, 0, c.V.p, c.offs.p, c.neighs.p, c.didx.p, c.dnum.p, row, first, n, c.base[D], k, c.divg.p);
     }
     PRB_CUDA(cudaGetLastError());
     return PRB_OK;
