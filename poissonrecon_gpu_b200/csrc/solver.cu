@@ -46,7 +46,7 @@ constexpr int kUnitBz = 10, kUnitBy = 36, kCubeUnits = 145, kCubeFloats = 4 * kC
 constexpr int kWarpBufFloats = 4 * kCubeFloats;          // 4 cubes per warp-step
 constexpr int kRounds = 12;                               // 96 half-blocks / 8 lanes
 constexpr int kPrefetchSteps = 2;                         // L2 prefetch distance of the SpMV table, in steps beyond the register pipeline
-constexpr int kStreamUnroll = 4, kStreamUnrollB = 3;     // independent 16-byte loads per array per thread in the streaming phases
+constexpr int kStreamUnroll = 4, kStreamUnrollB = 4;     // independent 16-byte loads per array per thread in the streaming phases
 
 // Staging plan of a quarter-warp: in round r (12 rounds x 8 lanes = the 96 half-blocks) lane li
 // copies one 16-byte half-block.  The cost of the gather is the number of distinct 128-byte
@@ -114,7 +114,8 @@ struct CgParams {
     // vectors indexed by node id; node 1 sits on a 32-byte boundary (pointer = allocation + 7)
     float* x;
     float* r;
-    float* p;
+    float* p;                      // direction vector, double buffered: iteration k lives in p + (k & 1) * pStride
+    i64 pStride;
     float* Ap;
     double* dots;                  // [2 buffers][2 kinds][16] + [16] for the initial r.r
     int* itersOut;                 // [D+1]
@@ -185,6 +186,8 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
     __shared__ float sR1[kMaxDepth + 1], sAlpha[kMaxDepth + 1], sBeta[kMaxDepth + 1];
     __shared__ int sActive[kMaxDepth + 1], sIter[kMaxDepth + 1];
     __shared__ int sStep[kMaxDepth + 3];      // sStep[d] = first flat SpMV step of depth d (active depths only), sStep[D+1] = total
+    __shared__ int sPend[kMaxDepth + 1];      // x of depth d still lacks alpha_{k-1} p_{k-1} (applied under the next SpMV)
+    __shared__ int sXup[kMaxDepth + 3];       // sXup[d] = first flat 32-lane batch of the pending x updates of depth d
     const int D = P.D, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gwarp = blockIdx.x * kCgWarps + warp, nwarps = gridDim.x * kCgWarps;
     const int gthread = blockIdx.x * kCgBlock + tid, nthreads = gridDim.x * kCgBlock;
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
             double part = 0.0;
             for (int i = i0 + gthread; i < i1; i += nthreads) {
                 float bv = P.b[i];
-                P.x[i] = 0.f; P.r[i] = bv; P.p[i] = 0.f;
+                P.x[i] = 0.f; P.r[i] = bv; P.p[i] = 0.f;                // p_0 = 0 (buffer 0); iteration 1 writes buffer 1
                 part += (double)(bv * bv);
             }
             warp_add(part, sAcc, d, lane);
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
     cg_sync<MG>(grid, P, epoch, 0, 0, P.dots + 64);
     if (tid >= 1 && tid <= D) {
         float r1 = (float)cg_total<MG>(P, 0, 0, tid, P.dots + 64);
-        sR1[tid] = r1; sIter[tid] = 1; sBeta[tid] = 0.f; sAlpha[tid] = 0.f;
+        sR1[tid] = r1; sIter[tid] = 1; sBeta[tid] = 0.f; sAlpha[tid] = 0.f; sPend[tid] = 0;
         sActive[tid] = (r1 > P.tol2 && 1 <= P.maxIter) ? 1 : 0;
     }
     __syncthreads();
@@ -274,7 +277,8 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
     const int outOff = 2 * Ylo;          // the lane's rows (y = Y & 1) start 2 (Y & 1) floats after the block base
 
     int phase = 0;
-    for (int it = 1;; it++) {
+    int it = 1;
+    for (;; it++) {
         int anyActive = 0;
         for (int d = 1; d <= D; d++) anyActive |= sActive[d];
         if (!anyActive) break;
@@ -286,9 +290,17 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
                 if (sActive[d]) acc += (P.sg1[d] - P.sg0[d] + 3) >> 2;
                 sStep[d + 1] = acc;
             }
+            acc = 0;
+            sXup[0] = 0; sXup[1] = 0;
+            for (int d = 1; d <= D; d++) {
+                if (sPend[d]) acc += (((P.row1[d] - P.row0[d]) >> 2) + 31) >> 5;
+                sXup[d + 1] = acc;
+            }
         }
         __syncthreads();
         const int cur = it & 1, nxt = cur ^ 1;
+        float* const pNew = P.p + (i64)cur * P.pStride;            // p_k
+        const float* const pOld = P.p + (i64)nxt * P.pStride;      // p_{k-1}
         double* dPAp = P.dots + cur * 32;         // kind 0
         double* dRRn = P.dots + cur * 32 + 16;    // kind 1 (this iteration's new r.r)
 
@@ -304,7 +316,7 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
 #pragma unroll
                 for (int k = 0; k < kStreamUnroll; k++) {
                     const int ck = c + k * nthreads, ik = i0 + 4 * (revC ? n4 - 1 - ck : ck);
-                    if (ck < n4) { rv[k] = *reinterpret_cast<const float4*>(P.r + ik); pv[k] = *reinterpret_cast<const float4*>(P.p + ik); }
+                    if (ck < n4) { rv[k] = *reinterpret_cast<const float4*>(P.r + ik); pv[k] = *reinterpret_cast<const float4*>(pOld + ik); }
                 }
 #pragma unroll
                 for (int k = 0; k < kStreamUnroll; k++) {
@@ -315,7 +327,7 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
                         o.y = __fadd_rn(rv[k].y, __fmul_rn(be, pv[k].y));
                         o.z = __fadd_rn(rv[k].z, __fmul_rn(be, pv[k].z));
                         o.w = __fadd_rn(rv[k].w, __fmul_rn(be, pv[k].w));
-                        *reinterpret_cast<float4*>(P.p + ik) = o;
+                        *reinterpret_cast<float4*>(pNew + ik) = o;
                     }
                 }
             }
@@ -358,14 +370,28 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
 #pragma unroll
                 for (int r = 0; r < kRounds; r++) {
                     const int b = e[r];
-                    const float* src = P.p + (b + (r >= 8 ? hEdge : hFull));
+                    const float* src = pNew + (b + (r >= 8 ? hEdge : hFull));
                     if (MG && remote && b >= 0 && (b < P.row0[d] || b >= P.row1[d])) {
                         int rk = 0;
                         while (rk + 1 < P.world && b >= P.rowLo[d][rk + 1]) rk++;
-                        src = P.peerP[rk] + (b + (r >= 8 ? hEdge : hFull));
+                        src = P.peerP[rk] + (i64)cur * P.pStride + (b + (r >= 8 ? hEdge : hFull));
                     }
                     cp_async16(dst + 4u * (unsigned)dstOff[r], src, b >= 0 ? 16 : 0);     // missing block: zero fill, no memory access
                 }
+            };
+            // pending x updates (x += alpha_{k-1} p_{k-1}) ride along: one 32-lane batch of float4 per SpMV step,
+            // loaded before the step's compute and finished after it, so their memory latency is hidden by
+            // the FMAs; what is left (more batches than steps) is swept after the loop
+            const int xTotal = sXup[D + 1];
+            int xd = 1, xlo = sXup[1], xhi = sXup[2];
+            int xb = gwarp;                       // this warp's next batch (flat index over the pending depths)
+            auto x_locate = [&](int b, int& d, int& i) {        // -> depth and float index of this lane's float4 (i < 0: past the end)
+                const int u = rev ? xTotal - 1 - b : b;
+                while (u >= xhi) { xd++; xlo = xhi; xhi = sXup[xd + 1]; }
+                while (u < xlo) { xd--; xhi = xlo; xlo = sXup[xd]; }
+                d = xd;
+                const int c4 = (u - xlo) * 32 + lane;
+                i = c4 < ((P.row1[xd] - P.row0[xd]) >> 2) ? P.row0[xd] + 4 * c4 : -1;
             };
             double part = 0.0;
             int partDepth = 0;
@@ -394,6 +420,12 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
                     if (haveC) { locate(t + 2 * nwarps, sgq); dC = ld; load_tab(sgq, eC); }
                 }
                 cp_async_commit();
+                int xi = -1, xdep = 1;
+                float4 xpv = make_float4(0.f, 0.f, 0.f, 0.f), xxv = xpv;
+                if (xb < xTotal) {
+                    x_locate(xb, xdep, xi);
+                    if (xi >= 0) { xpv = *reinterpret_cast<const float4*>(pOld + xi); xxv = *reinterpret_cast<const float4*>(P.x + xi); }
+                }
                 if (dA != partDepth) {               // flush the dot-product partial when the depth changes
                     if (partDepth) warp_add(part, sAcc, partDepth, lane);
                     part = 0.0;
@@ -461,6 +493,12 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
                         part += (double)(pc[1][3] * acc[1][3]);
                     }
                 }
+                if (xi >= 0) {
+                    const float al = sAlpha[xdep];
+                    xxv.x = __fmaf_rn(al, xpv.x, xxv.x); xxv.y = __fmaf_rn(al, xpv.y, xxv.y); xxv.z = __fmaf_rn(al, xpv.z, xxv.z); xxv.w = __fmaf_rn(al, xpv.w, xxv.w);
+                    *reinterpret_cast<float4*>(P.x + xi) = xxv;
+                }
+                xb += nwarps;
                 __syncwarp();      // all lanes are done with this buffer before the next copies land in it
                 rb0 = eB[0]; rb1 = eB[1];
                 dA = dB; dB = dC;
@@ -470,6 +508,17 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
             }
             cp_async_wait<0>();
             if (partDepth) warp_add(part, sAcc, partDepth, lane);
+            for (; xb < xTotal; xb += nwarps) {      // x batches beyond this warp's SpMV steps
+                int xi, xdep;
+                x_locate(xb, xdep, xi);
+                if (xi >= 0) {
+                    const float al = sAlpha[xdep];
+                    const float4 pv = *reinterpret_cast<const float4*>(pOld + xi);
+                    float4 xv = *reinterpret_cast<const float4*>(P.x + xi);
+                    xv.x = __fmaf_rn(al, pv.x, xv.x); xv.y = __fmaf_rn(al, pv.y, xv.y); xv.z = __fmaf_rn(al, pv.z, xv.z); xv.w = __fmaf_rn(al, pv.w, xv.w);
+                    *reinterpret_cast<float4*>(P.x + xi) = xv;
+                }
+            }
         }
         __syncthreads();
         if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&dPAp[tid], sAcc[tid]);
@@ -480,7 +529,7 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
         if (tid <= D) sAcc[tid] = 0.0;
         if (tid >= 1 && tid <= D && sActive[tid]) sAlpha[tid] = (float)((double)sR1[tid] / cg_total<MG>(P, cur, 0, tid, dPAp));
         __syncthreads();
-        // ---------------- phase B: x += alpha p ; r -= alpha Ap ; r.r
+        // ---------------- phase B: r -= alpha Ap ; r.r   (x += alpha p is applied under the next SpMV, or by the sweep after the loop)
         const bool revB = P.zigzag && (phase++ & 1) != 0;
         for (int dd = 1; dd <= D; dd++) {
             const int d = revB ? D + 1 - dd : dd;
@@ -489,14 +538,12 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
             const int i0 = P.row0[d], n4 = (P.row1[d] - i0) >> 2;
             double part = 0.0;
             for (int c = gthread; c < n4; c += kStreamUnrollB * nthreads) {
-                float4 pv[kStreamUnrollB], av[kStreamUnrollB], xv[kStreamUnrollB], rv[kStreamUnrollB];
+                float4 av[kStreamUnrollB], rv[kStreamUnrollB];
 #pragma unroll
                 for (int k = 0; k < kStreamUnrollB; k++) {
                     const int ck = c + k * nthreads, ik = i0 + 4 * (revB ? n4 - 1 - ck : ck);
                     if (ck < n4) {
-                        pv[k] = *reinterpret_cast<const float4*>(P.p + ik);
                         av[k] = *reinterpret_cast<const float4*>(P.Ap + ik);
-                        xv[k] = *reinterpret_cast<const float4*>(P.x + ik);
                         rv[k] = *reinterpret_cast<const float4*>(P.r + ik);
                     }
                 }
@@ -504,10 +551,8 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
                 for (int k = 0; k < kStreamUnrollB; k++) {
                     const int ck = c + k * nthreads, ik = i0 + 4 * (revB ? n4 - 1 - ck : ck);
                     if (ck < n4) {
-                        float4 xo, ro;
-                        xo.x = __fmaf_rn(al, pv[k].x, xv[k].x); xo.y = __fmaf_rn(al, pv[k].y, xv[k].y); xo.z = __fmaf_rn(al, pv[k].z, xv[k].z); xo.w = __fmaf_rn(al, pv[k].w, xv[k].w);
+                        float4 ro;
                         ro.x = __fmaf_rn(-al, av[k].x, rv[k].x); ro.y = __fmaf_rn(-al, av[k].y, rv[k].y); ro.z = __fmaf_rn(-al, av[k].z, rv[k].z); ro.w = __fmaf_rn(-al, av[k].w, rv[k].w);
-                        *reinterpret_cast<float4*>(P.x + ik) = xo;
                         *reinterpret_cast<float4*>(P.r + ik) = ro;
                         part += (double)(ro.x * ro.x);
                         part += (double)(ro.y * ro.y);
@@ -528,8 +573,28 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
             sIter[tid] = k;
             sBeta[tid] = r1 / r0;
             sActive[tid] = (r1 > P.tol2 && k <= P.maxIter) ? 1 : 0;
+            sPend[tid] = 1;                 // this iteration's alpha p is still to be added to x
+        } else if (tid >= 1 && tid <= D) {
+            sPend[tid] = 0;                 // a depth that had stopped before: its last update went in under this iteration's SpMV
         }
         __syncthreads();
+    }
+    // ---- the last alpha p of every depth that was still iterating (p_k sits in the buffer of the last iteration)
+    {
+        const int itLast = it - 1;
+        const float* pLast = P.p + (i64)(itLast & 1) * P.pStride;
+        for (int d = 1; d <= D; d++) {
+            if (!sPend[d]) continue;
+            const float al = sAlpha[d];
+            const int i0 = P.row0[d], n4 = (P.row1[d] - i0) >> 2;
+            for (int c = gthread; c < n4; c += nthreads) {
+                const int ik = i0 + 4 * c;
+                const float4 pv = *reinterpret_cast<const float4*>(pLast + ik);
+                float4 xv = *reinterpret_cast<const float4*>(P.x + ik);
+                xv.x = __fmaf_rn(al, pv.x, xv.x); xv.y = __fmaf_rn(al, pv.y, xv.y); xv.z = __fmaf_rn(al, pv.z, xv.z); xv.w = __fmaf_rn(al, pv.w, xv.w);
+                *reinterpret_cast<float4*>(P.x + ik) = xv;
+            }
+        }
     }
     if (blockIdx.x == 0 && tid >= 1 && tid <= D) { P.itersOut[tid] = sIter[tid] - 1; P.resOut[tid] = sR1[tid]; }
     if (blockIdx.x == 0 && tid == 0) P.itersOut[15] = (int)epoch;
@@ -545,7 +610,7 @@ int stage_solve(Context& c) {
     const int D = c.D, M = c.M;
     cudaStream_t st = c.stream;
     // vectors are padded by 7 floats so that node 1 (the first sibling block) is 32-byte aligned
-    const size_t padN = (size_t)M + 8;
+    const size_t padN = ((size_t)M + 8 + 7) & ~(size_t)7;      // a multiple of 8: the second p buffer keeps the 32-byte alignment of the sibling blocks
     const bool mg = c.mg.active();
     float* pBuf = nullptr;
     DBuf<float> r, p, Ap, resOut;
@@ -556,7 +621,7 @@ int stage_solve(Context& c) {
             if (!c.mg.peer[q]) { set_error("multi-GPU: peer arenas not exchanged (prb_mg_set_peer)"); return PRB_ERR_STATE; }
         if (!c.mgX) {
             c.mgX = c.mg.alloc<float>(padN, &c.mgXOff);
-            c.mgP = c.mg.alloc<float>(padN, &c.mgPOff);
+            c.mgP = c.mg.alloc<float>(2 * padN, &c.mgPOff);
             if (!c.mgX || !c.mgP) { set_error("multi-GPU arena too small for the CG vectors (prb_mg_init arena_bytes)"); return PRB_ERR_NOMEM; }
         }
         c.xv = c.mgX + 7;
@@ -564,7 +629,7 @@ int stage_solve(Context& c) {
     } else {
         PRB_TRY(c.x.alloc(padN, st));
         c.xv = c.x.p + 7;
-        PRB_TRY(p.alloc(padN, st));
+        PRB_TRY(p.alloc(2 * padN, st));
         pBuf = p.p;
     }
     DBuf<double> dots;
@@ -583,7 +648,7 @@ int stage_solve(Context& c) {
     P.sgStart[1] = 0;
     for (int d = 2; d <= D + 1; d++) P.sgStart[d] = 1 + (c.base[d - 1] - 1) / 8;
     P.tab4 = c.sgTab4.p; P.nSg = c.nSg; P.zigzag = c.cgZigzag; P.stencil = c.dStencil.p; P.b = c.divg.p;
-    P.x = c.xv; P.r = r.p + 7; P.p = pBuf + 7; P.Ap = Ap.p + 7;
+    P.x = c.xv; P.r = r.p + 7; P.p = pBuf + 7; P.pStride = (i64)padN; P.Ap = Ap.p + 7;
     P.world = c.mg.world; P.rank = c.mg.rank; P.shardFrom = mg ? c.shardFrom : D + 1;
     for (int d = 0; d <= D + 1; d++) {
         const bool sh = mg && d >= c.shardFrom && d <= D;
