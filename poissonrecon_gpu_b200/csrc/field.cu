@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) k_divergence_dm1(const float* __restrict_
 // main.cu:3419-3458).  Work item = (node n, chunk of <= kChunk of the depth-D slots under n);
 // every slot contributes to the <= 27 neighbours o of n, so a block accumulates 27 partial sums
 // in double, reduces them and issues at most 27 atomicAdd(double).
-constexpr int kChunk = 2048;
+constexpr int kChunk = 8192;
 __global__ void __launch_bounds__(256) k_count_items(const int* __restrict__ dnum, int nNodes, int* __restrict__ items) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nNodes; i += gridDim.x * blockDim.x) items[i] = (dnum[i] + kChunk - 1) / kChunk;
 }
