@@ -207,7 +207,7 @@ struct Context {
     // grow-only workspace of the refinement passes (kept across runs)
     DBuf<float> wsVal7, wsLow;
     DBuf<unsigned char> wsCat, wsNtri;
-    DBuf<unsigned short> wsEmask;
+    DBuf<unsigned short> wsEmask, wsVpre;
     DBuf<int> wsVbase, wsTbase;
     prb_stats stats;
     // ---- multi-GPU

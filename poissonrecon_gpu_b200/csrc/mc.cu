@@ -1152,7 +1152,13 @@ __global__ void __launch_bounds__(256) k_rv_classify(RGeom G, unsigned char* __r
 // brick form of the classification: the 9x9x9 grid values of a brick are staged in shared memory
 // (own corner-7 values + the 217 points of its three lower faces), every cell then reads its 8
 // corners from there
-__global__ void __launch_bounds__(512) k_rv_classify_brick(RGeom G, unsigned char* __restrict__ cat, unsigned char* __restrict__ ntri, unsigned short* __restrict__ emask) {
+// Output per cell (only for bricks that produce anything): case, mask of owned crossed edges and the
+// exclusive prefix of the vertex count INSIDE the brick; per brick: vertex and triangle totals.  The
+// pass-wide offsets then come from a scan over bricks (hundreds of thousands) instead of cells
+// (hundreds of millions), and only the active bricks are visited again for the emission.
+__global__ void __launch_bounds__(512) k_rv_classify_brick(RGeom G, unsigned char* __restrict__ cat, unsigned short* __restrict__ emask, unsigned short* __restrict__ vpre,
+                                                           int* __restrict__ brickV, int* __restrict__ brickT) {
+    __shared__ int sScan[33];
     __shared__ float sV[9 * 9 * 9];
     const int tid = threadIdx.x;
     const i64 cell0 = (i64)blockIdx.x * 512;
@@ -1177,11 +1183,7 @@ __global__ void __launch_bounds__(512) k_rv_classify_brick(RGeom G, unsigned cha
     // same trivial case (0 or 255, both without triangles) in every cell: nothing else to do
     const int allPos = __syncthreads_and(pos), allNeg = __syncthreads_and(neg);
     if (allPos || allNeg) {
-        const i64 t = cell0 + tid;
-        const int c = allNeg ? 255 : 0;
-        cat[t] = (unsigned char)c;
-        ntri[t] = cMcCount[c];
-        emask[t] = 0;
+        if (tid == 0) { brickV[blockIdx.x] = 0; brickT[blockIdx.x] = 0; }
         return;
     }
     float v[8];
@@ -1202,9 +1204,62 @@ __global__ void __launch_bounds__(512) k_rv_classify_brick(RGeom G, unsigned cha
             if (rv_edge_owner(G, r, bx + cx, by + cy, bz + cz, e, e2) == t) m |= 1u << e;
         }
     }
-    cat[t] = (unsigned char)c;
-    ntri[t] = cMcCount[c];
-    emask[t] = (unsigned short)m;
+    int totV, totT;
+    const int pre = block_exclusive_scan(__popc(m), &totV, sScan);
+    block_exclusive_scan((int)cMcCount[c], &totT, sScan);
+    if (tid == 0) { brickV[blockIdx.x] = totV; brickT[blockIdx.x] = totT; }
+    if (totV | totT) {
+        cat[t] = (unsigned char)c;
+        emask[t] = (unsigned short)m;
+        vpre[t] = (unsigned short)pre;
+    }
+}
+__global__ void __launch_bounds__(256) k_brick_flags(const int* __restrict__ brickV, const int* __restrict__ brickT, int n, int* __restrict__ flag) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) flag[i] = (brickV[i] | brickT[i]) != 0;
+}
+// emission of one active brick per CTA: vertices of the owned crossed edges, then the triangles
+// (vertex ids through the owner cell's brick base + in-brick prefix + rank of the edge in its mask)
+__global__ void __launch_bounds__(512) k_rv_emit_brick(RGeom G, const int* __restrict__ active, const unsigned char* __restrict__ cat, const unsigned short* __restrict__ emask,
+                                                       const unsigned short* __restrict__ vpre, const int* __restrict__ brickVBase, const int* __restrict__ brickTBase,
+                                                       float* __restrict__ outV, int* __restrict__ outT) {
+    __shared__ int sScan[33];
+    const int b = active[blockIdx.x], tid = threadIdx.x;
+    const i64 t = (i64)b * 512 + tid;
+    const int r = (int)(t / G.per);
+    const unsigned l = (unsigned)(t - (i64)r * G.per);
+    const int cx = (int)compact3(l >> 2), cy = (int)compact3(l >> 1), cz = (int)compact3(l);
+    const unsigned m = emask[t];
+    const int c = cat[t], nt = cMcCount[c];
+    int totT;
+    const int tb = brickTBase[b] + block_exclusive_scan(nt, &totT, sScan);
+    if (m) {
+        const float w = 1.0f / (float)(1 << G.D);
+        float v[8];
+        rv_cell_values(G, r, cx, cy, cz, v);
+        const ushort4 ro = G.offs[G.roots[r]];
+        const int ox = ((int)ro.x << G.lv) + cx, oy = ((int)ro.y << G.lv) + cy, oz = ((int)ro.z << G.lv) + cz;
+        int k = brickVBase[b] + (int)vpre[t];
+        for (int e = 0; e < 12; e++) {
+            if (!(m & (1u << e))) continue;
+            int r1 = cEdgeVertex[e][0], r2 = cEdgeVertex[e][1], dim = e >> 2;
+            int b1 = ring_to_bits(r1), b2 = ring_to_bits(r2);
+            float p1[3] = {(float)(ox + (b1 & 1)) * w, (float)(oy + ((b1 >> 1) & 1)) * w, (float)(oz + ((b1 >> 2) & 1)) * w};
+            float p2d = (float)((dim == 0 ? ox + (b2 & 1) : (dim == 1 ? oy + ((b2 >> 1) & 1) : oz + ((b2 >> 2) & 1)))) * w;
+            float f1 = v[r1], f2 = v[r2];
+            float pivot = __fdiv_rn(f1, __fsub_rn(f1, f2));
+            float another = __fsub_rn(1.0f, pivot);
+            float out[3] = {p1[0], p1[1], p1[2]};
+            out[dim] = __fmaf_rn(p2d, pivot, __fmul_rn(p1[dim], another));
+            i64 a = 3 * (i64)k;
+            outV[a] = out[0]; outV[a + 1] = out[1]; outV[a + 2] = out[2];
+            k++;
+        }
+    }
+    for (int j = 0; j < 3 * nt; j++) {
+        int e = cMcTri[c][j], e2;
+        const i64 ow = rv_edge_owner(G, r, cx, cy, cz, e, e2);
+        outT[3 * (i64)tb + j] = brickVBase[(int)(ow >> 9)] + (int)vpre[ow] + __popc((unsigned)emask[ow] & ((1u << e2) - 1u));
+    }
 }
 __global__ void __launch_bounds__(256) k_rv_emit_vertices(RGeom G, const unsigned short* __restrict__ emask, const int* __restrict__ vbase, float* __restrict__ outV) {
     const float w = 1.0f / (float)(1 << G.D);
@@ -1301,10 +1356,9 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     if ((double)total * 20.0 > (double)c.deviceMemBytes * 0.8) { set_error("refinement pass too large for device memory"); return PRB_ERR_NOMEM; }
     DBuf<int> rootNb;
     DBuf<float> rootX;
-    DBuf<int>&vbase = c.wsVbase, &tbase = c.wsTbase;
     DBuf<float>& low = c.wsLow;
     const bool mg = c.mg.active();
-    DBuf<unsigned char>&cat = c.wsCat, &ntri = c.wsNtri;
+    DBuf<unsigned char>& cat = c.wsCat;
     DBuf<unsigned short>& emask = c.wsEmask;
     PRB_TRY(rootNb.alloc(27 * (size_t)nr, st));
     PRB_TRY(rootX.alloc((size_t)nr * (rd + 1) * 27, st));
@@ -1344,23 +1398,42 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
         }
     }
     PRB_LAUNCH(c, k_rv_low_values, grid_for(c, (i64)nr * 3 * n1 * n1, 128, 16), 128, 0, G);
+    const int nBricks = (int)(total / 512);
     PRB_TRY(cat.ensure((size_t)total, st));
-    PRB_TRY(ntri.ensure((size_t)total, st));
     PRB_TRY(emask.ensure((size_t)total, st));
-    PRB_TRY(vbase.ensure((size_t)total, st));
-    PRB_TRY(tbase.ensure((size_t)total, st));
-    PRB_LAUNCH(c, k_rv_classify_brick, (unsigned)(total / 512), 512, 0, G, cat.p, ntri.p, emask.p);
-    i64 totV = 0, totT = 0;
-    PRB_TRY(exclusive_scan_op(c, ScanLoadPopc16{emask.p}, vbase.p, total, &totV));
-    PRB_TRY(exclusive_scan_op(c, ScanLoadU8{ntri.p}, tbase.p, total, &totT));
+    PRB_TRY(c.wsVpre.ensure((size_t)total, st));
+    DBuf<int> brickV, brickT, brickVBase, brickTBase, bflag, bexcl, active;
+    PRB_TRY(brickV.alloc((size_t)nBricks, st)); PRB_TRY(brickT.alloc((size_t)nBricks, st));
+    PRB_TRY(brickVBase.alloc((size_t)nBricks, st)); PRB_TRY(brickTBase.alloc((size_t)nBricks, st));
+    PRB_TRY(bflag.alloc((size_t)nBricks, st)); PRB_TRY(bexcl.alloc((size_t)nBricks, st));
+    PRB_LAUNCH(c, k_rv_classify_brick, (unsigned)nBricks, 512, 0, G, cat.p, emask.p, c.wsVpre.p, brickV.p, brickT.p);
+    PRB_LAUNCH(c, k_brick_flags, grid_for(c, nBricks, 256), 256, 0, brickV.p, brickT.p, nBricks, bflag.p);
+    i64 totV = 0, totT = 0, nActive = 0;
+    PRB_TRY(exclusive_scan(c, brickV.p, brickVBase.p, nBricks, nullptr));
+    PRB_TRY(exclusive_scan(c, brickT.p, brickTBase.p, nBricks, nullptr));
+    PRB_TRY(exclusive_scan(c, bflag.p, bexcl.p, nBricks, &nActive));
+    {
+        int last[4] = {0, 0, 0, 0};     // totals = base + count of the last brick
+        PRB_CUDA(cudaMemcpyAsync(&last[0], brickVBase.p + nBricks - 1, 4, cudaMemcpyDeviceToHost, st));
+        PRB_CUDA(cudaMemcpyAsync(&last[1], brickV.p + nBricks - 1, 4, cudaMemcpyDeviceToHost, st));
+        PRB_CUDA(cudaMemcpyAsync(&last[2], brickTBase.p + nBricks - 1, 4, cudaMemcpyDeviceToHost, st));
+        PRB_CUDA(cudaMemcpyAsync(&last[3], brickT.p + nBricks - 1, 4, cudaMemcpyDeviceToHost, st));
+        PRB_CUDA(cudaStreamSynchronize(st));
+        totV = (i64)last[0] + last[1];
+        totT = (i64)last[2] + last[3];
+    }
     outs.emplace_back();
     PassOut& po = outs.back();
     po.nv = (int)totV;
     po.nt = (int)totT;
     PRB_TRY(po.v.alloc(3 * (size_t)totV, st));
     PRB_TRY(po.t.alloc(3 * (size_t)totT, st));
-    if (totV) PRB_LAUNCH(c, k_rv_emit_vertices, grid_for(c, total, 256, 8), 256, 0, G, emask.p, vbase.p, po.v.p);
-    if (totT) PRB_LAUNCH(c, k_rv_emit_triangles, grid_for(c, total, 256, 8), 256, 0, G, cat.p, ntri.p, tbase.p, emask.p, vbase.p, po.t.p);
+    if (nActive) {
+        PRB_TRY(active.alloc((size_t)nActive, st));
+        PRB_LAUNCH(c, k_compact_ids, grid_for(c, nBricks, 256), 256, 0, bflag.p, bexcl.p, nBricks, active.p);
+        PRB_LAUNCH(c, k_rv_emit_brick, (unsigned)nActive, 512, 0, G, active.p, cat.p, emask.p, c.wsVpre.p, brickVBase.p, brickTBase.p, po.v.p, po.t.p);
+    }
+    brickV.release(); brickT.release(); brickVBase.release(); brickTBase.release(); bflag.release(); bexcl.release(); active.release();
     if (single && po.nv == 0) {      // main.cu:4095-4103: nothing is inserted for a coarse root without crossings
         po.v.release(); po.t.release();
         outs.pop_back();
