@@ -1149,6 +1149,22 @@ __global__ void __launch_bounds__(256) k_rv_classify(RGeom G, unsigned char* __r
         emask[t] = (unsigned short)m;
     }
 }
+// sign summary of a brick's own 512 corner-7 values: 1 all > 0, 2 all < 0, 0 otherwise (one warp per brick)
+__global__ void __launch_bounds__(256) k_rv_brick_sign(const float* __restrict__ val7, int nBricks, unsigned char* __restrict__ sign) {
+    const int lane = threadIdx.x & 31;
+    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nBricks; b += (gridDim.x * blockDim.x) >> 5) {
+        const float4* v = reinterpret_cast<const float4*>(val7 + (i64)b * 512);
+        bool pos = true, neg = true;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float4 f = v[lane + 32 * k];
+            pos = pos && f.x > 0.f && f.y > 0.f && f.z > 0.f && f.w > 0.f;
+            neg = neg && f.x < 0.f && f.y < 0.f && f.z < 0.f && f.w < 0.f;
+        }
+        const bool ap = __all_sync(0xffffffffu, pos), an = __all_sync(0xffffffffu, neg);
+        if (lane == 0) sign[b] = ap ? 1 : (an ? 2 : 0);
+    }
+}
 // brick form of the classification: the 9x9x9 grid values of a brick are staged in shared memory
 // (own corner-7 values + the 217 points of its three lower faces), every cell then reads its 8
 // corners from there
@@ -1156,15 +1172,33 @@ __global__ void __launch_bounds__(256) k_rv_classify(RGeom G, unsigned char* __r
 // exclusive prefix of the vertex count INSIDE the brick; per brick: vertex and triangle totals.  The
 // pass-wide offsets then come from a scan over bricks (hundreds of thousands) instead of cells
 // (hundreds of millions), and only the active bricks are visited again for the emission.
-__global__ void __launch_bounds__(512) k_rv_classify_brick(RGeom G, unsigned char* __restrict__ cat, unsigned short* __restrict__ emask, unsigned short* __restrict__ vpre,
-                                                           int* __restrict__ brickV, int* __restrict__ brickT) {
+__global__ void __launch_bounds__(512) k_rv_classify_brick(RGeom G, const unsigned char* __restrict__ bsign, unsigned char* __restrict__ cat, unsigned short* __restrict__ emask,
+                                                           unsigned short* __restrict__ vpre, int* __restrict__ brickV, int* __restrict__ brickT, int nBricks) {
     __shared__ int sScan[33];
     __shared__ float sV[9 * 9 * 9];
     const int tid = threadIdx.x;
-    const i64 cell0 = (i64)blockIdx.x * 512;
+    // persistent CTAs: most bricks leave after eight byte loads, far cheaper than a 512-thread CTA launch each
+    for (int brick = blockIdx.x; brick < nBricks; brick += gridDim.x) {
+    __syncthreads();
+    const i64 cell0 = (i64)brick * 512;
     const int r = (int)(cell0 / G.per);
     const unsigned l0 = (unsigned)(cell0 - (i64)r * G.per);
     const int bx = (int)compact3(l0 >> 2), by = (int)compact3(l0 >> 1), bz = (int)compact3(l0);   // root-local origin of the brick
+    // the 9x9x9 grid of a brick inside its root takes its values from this brick and the 7 bricks below it
+    // (x-8, y-8, z-8 combinations): when all eight are uniformly of one strict sign, so is the grid
+    if (bx >= 8 && by >= 8 && bz >= 8) {
+        bool ok = true;                        // threads 0..7 look at one brick each (one memory latency, not eight)
+        if (tid < 8) {
+            const unsigned ln = rv_morton(bx - ((tid & 1) ? 8 : 0), by - ((tid & 2) ? 8 : 0), bz - ((tid & 4) ? 8 : 0));
+            const int sq = bsign[(int)(((i64)r * G.per + ln) >> 9)];
+            const int s0 = __shfl_sync(0xffu, sq, 0);
+            ok = sq != 0 && sq == s0;
+        }
+        if (__syncthreads_and(ok)) {
+            if (tid == 0) { brickV[brick] = 0; brickT[brick] = 0; }
+            continue;
+        }
+    }
     const int cx = (int)compact3((unsigned)tid >> 2), cy = (int)compact3((unsigned)tid >> 1), cz = (int)compact3((unsigned)tid);
     const float own = G.val7[cell0 + tid];
     sV[(cx + 1) * 81 + (cy + 1) * 9 + (cz + 1)] = own;
@@ -1183,8 +1217,8 @@ __global__ void __launch_bounds__(512) k_rv_classify_brick(RGeom G, unsigned cha
     // same trivial case (0 or 255, both without triangles) in every cell: nothing else to do
     const int allPos = __syncthreads_and(pos), allNeg = __syncthreads_and(neg);
     if (allPos || allNeg) {
-        if (tid == 0) { brickV[blockIdx.x] = 0; brickT[blockIdx.x] = 0; }
-        return;
+        if (tid == 0) { brickV[brick] = 0; brickT[brick] = 0; }
+        continue;
     }
     float v[8];
 #pragma unroll
@@ -1207,11 +1241,12 @@ __global__ void __launch_bounds__(512) k_rv_classify_brick(RGeom G, unsigned cha
     int totV, totT;
     const int pre = block_exclusive_scan(__popc(m), &totV, sScan);
     block_exclusive_scan((int)cMcCount[c], &totT, sScan);
-    if (tid == 0) { brickV[blockIdx.x] = totV; brickT[blockIdx.x] = totT; }
+    if (tid == 0) { brickV[brick] = totV; brickT[brick] = totT; }
     if (totV | totT) {
         cat[t] = (unsigned char)c;
         emask[t] = (unsigned short)m;
         vpre[t] = (unsigned short)pre;
+    }
     }
 }
 __global__ void __launch_bounds__(256) k_brick_flags(const int* __restrict__ brickV, const int* __restrict__ brickT, int n, int* __restrict__ flag) {
@@ -1406,7 +1441,11 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     PRB_TRY(brickV.alloc((size_t)nBricks, st)); PRB_TRY(brickT.alloc((size_t)nBricks, st));
     PRB_TRY(brickVBase.alloc((size_t)nBricks, st)); PRB_TRY(brickTBase.alloc((size_t)nBricks, st));
     PRB_TRY(bflag.alloc((size_t)nBricks, st)); PRB_TRY(bexcl.alloc((size_t)nBricks, st));
-    PRB_LAUNCH(c, k_rv_classify_brick, (unsigned)nBricks, 512, 0, G, cat.p, emask.p, c.wsVpre.p, brickV.p, brickT.p);
+    DBuf<unsigned char> bsign;
+    PRB_TRY(bsign.alloc((size_t)nBricks, st));
+    PRB_LAUNCH(c, k_rv_brick_sign, grid_for(c, (i64)nBricks * 32, 256), 256, 0, val7p, nBricks, bsign.p);
+    PRB_LAUNCH(c, k_rv_classify_brick, (unsigned)std::min(nBricks, c.smCount * 4), 512, 0, G, bsign.p, cat.p, emask.p, c.wsVpre.p, brickV.p, brickT.p, nBricks);
+    bsign.release();
     PRB_LAUNCH(c, k_brick_flags, grid_for(c, nBricks, 256), 256, 0, brickV.p, brickT.p, nBricks, bflag.p);
     i64 totV = 0, totT = 0, nActive = 0;
     PRB_TRY(exclusive_scan(c, brickV.p, brickVBase.p, nBricks, nullptr));
