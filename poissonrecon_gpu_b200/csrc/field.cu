@@ -119,63 +119,11 @@ __global__ void __launch_bounds__(128) k_splat(const float* __restrict__ W, cons
     }
 }
 
-// G cooperating threads per node: 1 (two finest depths), 32 (warp) or blockDim (coarse depths)
-template <int G>
-__global__ void __launch_bounds__(256) k_divergence(const float* __restrict__ V, const ushort4* __restrict__ offs, const int* __restrict__ neighs,
-                                                    const int* __restrict__ didx, const int* __restrict__ dnum, const float* __restrict__ dfRow,
-                                                    int base, int count, int baseD, int k /* 2^(D-d) */, float* __restrict__ divg) {
-    const int groupsPerBlock = (G == 1) ? blockDim.x : (G == 32 ? blockDim.x / 32 : 1);
-    const int gid = (G == 1) ? threadIdx.x : (G == 32 ? threadIdx.x >> 5 : 0);
-    const int lane = (G == 1) ? 0 : (G == 32 ? (threadIdx.x & 31) : threadIdx.x);
-    const int gsz = (G == 1) ? 1 : (G == 32 ? 32 : blockDim.x);
-    __shared__ double red[32];
-    for (int l0 = blockIdx.x * groupsPerBlock; l0 < count; l0 += gridDim.x * groupsPerBlock) {
-        int l = l0 + gid;
-        double val = 0.0;
-        if (l < count) {
-            int i = base + l;
-            ushort4 o = offs[i];
-            int bx = k * ((int)o.x - 1), by = k * ((int)o.y - 1), bz = k * ((int)o.z - 1);
-            const int* nb = neighs + 27 * (i64)i;
-            for (int j = 0; j < 27; j++) {
-                int n = nb[j];
-                if (n < 0) continue;
-                int s0 = didx[n], sn = dnum[n];
-                for (int q = lane; q < sn; q += gsz) {
-                    int s = s0 + q;
-                    ushort4 so = offs[baseD + s];
-                    float u0 = dfRow[(int)so.x - bx], u1 = dfRow[(int)so.y - by], u2 = dfRow[(int)so.z - bz];
-                    float dp = __fmul_rn(V[3 * (i64)s], u0);                  // DotProduct (main.cu:966-972)
-                    dp = __fmaf_rn(V[3 * (i64)s + 1], u1, dp);
-                    dp = __fmaf_rn(V[3 * (i64)s + 2], u2, dp);
-                    val += (double)dp;
-                }
-            }
-        }
-        if (G == 32) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
-        } else if (G > 32) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
-            __syncthreads();
-            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = val;
-            __syncthreads();
-            if (threadIdx.x < 32) {
-                val = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
-            }
-        }
-        if (lane == 0 && l < count) divg[base + l] = (float)val;
-    }
-}
-
 // Depths D-2 / D-3: one warp per node over the CONCATENATED slot ranges of its 27 neighbours.
 // A neighbour of a surface octree often owns only 8 or 16 depth-D slots, so a lane-strided loop
-// per neighbour (k_divergence<32>) leaves most lanes idle; here element e of the concatenation
+// per neighbour leaves most lanes idle; here element e of the concatenation
 // goes to lane e mod 32 and every lane advances its own segment cursor (the cursor only moves
-// forward: amortised O(1) shared-memory look-ups per element).  Terms as in k_divergence<1>;
+// forward: amortised O(1) shared-memory look-ups per element).  Terms as in k_divergence_leaf;
 // the double-precision summation order differs (tolerance stated in tests/test_parity_gpu.py).
 __global__ void __launch_bounds__(256) k_divergence_flat(const float* __restrict__ V, const ushort4* __restrict__ offs, const int* __restrict__ neighs,
                                                          const int* __restrict__ didx, const int* __restrict__ dnum, const float* __restrict__ dfRow,
@@ -220,7 +168,7 @@ __global__ void __launch_bounds__(256) k_divergence_flat(const float* __restrict
 // The two finest depths without the slot indirections: at depth D a neighbour IS its slot and the
 // table index is the neighbour direction; at depth D-1 the slots of a neighbour are its 8
 // children (one aligned 96-byte record of V) and the index is 2*(direction+1) + child bit.
-// Same terms, same order, same arithmetic as k_divergence<1>.
+// Same terms, same order, same arithmetic as the reference (computeEncodedFinerNodesDivergence, main.cu:1007-1056).
 __global__ void __launch_bounds__(256) k_divergence_leaf(const float* __restrict__ V, const int* __restrict__ neighs, const float* __restrict__ dfRow,
                                                          int baseD, int first, int count, float* __restrict__ divg) {
     const float r0 = dfRow[0], r1 = dfRow[1], r2 = dfRow[2];

@@ -219,142 +219,12 @@ __device__ __forceinline__ void cell_corner_values(const Topo& T, int id, const 
 }
 
 // ------------------------------------------------------------------ corner values, real tree (main.cu:2259-2326)
-__global__ void __launch_bounds__(128) k_vertex_values(Topo T, int M, int D, const int* __restrict__ parent, const int* __restrict__ child0,
-                                                       const ushort4* __restrict__ offs, const float* __restrict__ x, const float* __restrict__ baseFn,
-                                                       float iso, float* __restrict__ vval) {
-    const int exceedTab[8] = {0, 1, 3, 2, 4, 5, 7, 6};     // childrenVertexKind, MarchingCubes.cuh:721-723 (applied as the reference does)
-    // one thread per node, looping over the corners it owns (an interior cell owns exactly one,
-    // so all lanes stay busy; a thread per (node, corner) leaves 7 of 8 lanes idle in the walk)
-    for (int i = 1 + blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {   // root vertices are dropped (validVertex, main.cu:1634-1638)
-        ushort4 o = offs[i];
-        const int depth0 = o.w;
-        const float w = 1.0f / (float)(1 << depth0);
-        for (int j = 0; j < 8; j++) {
-            int m;
-            if (corner_owner(T, i, j, m) != i) continue;
-            float pos[3] = {(float)((int)o.x + (j & 1)) * w, (float)((int)o.y + ((j >> 1) & 1)) * w, (float)((int)o.z + ((j >> 2) & 1)) * w};
-            float val = 0.f;
-            int now = i;
-            while (now != -1) {
-                accumulate_level(val, T.nbr + 27 * (i64)now, offs[now], x, baseFn, pos);
-                now = parent[now];
-            }
-            now = i;
-            int ex = exceedTab[j], depth = depth0;
-            while (depth < D) {
-                ++depth;
-                int c0 = child0[now];
-                if (c0 < 0) break;
-                now = c0 + ex;
-                accumulate_level(val, T.nbr + 27 * (i64)now, offs[now], x, baseFn, pos);
-            }
-            vval[8 * (i64)i + j] = __fsub_rn(val, iso);
-        }
-    }
-}
-
-// Same values, one WARP per sibling group: the 8 siblings share every ancestor, so the 27
-// neighbour values and the per-axis base-function values of the ancestor levels are fetched once
-// per group into shared memory and reused by all the corners the group owns (the 27 points of
-// the 3x3x3 corner grid of the group, one lane each; a point is evaluated by the group that holds
-// its owner cell).  Each lane still adds its terms in the reference's order: own level, parents
-// up to the root, then the finer nodes at that corner (main.cu:2277-2322).
-constexpr int kVvWarps = 8;
-__global__ void __launch_bounds__(kVvWarps * 32) k_vertex_values_grouped(Topo T, int gFirst, int nGroups, int D, const int* __restrict__ parent, const int* __restrict__ child0,
-                                                                         const ushort4* __restrict__ offs, const float* __restrict__ x,
-                                                                         const float* __restrict__ baseFn, float iso, float* __restrict__ vval) {
-    __shared__ float sX[kVvWarps][27];
-    __shared__ float sB[kVvWarps][3][3][3];      // [axis][point coordinate 0..2][k]
-    __shared__ float sXc[kVvWarps][64];          // solution on the 4x4x4 node cube around the group (own level)
-    __shared__ float sB0[kVvWarps][3][3][4];     // own level: [axis][point coordinate][cube coordinate]
-    const int exceedTab[8] = {0, 1, 3, 2, 4, 5, 7, 6};     // childrenVertexKind, MarchingCubes.cuh:721-723 (applied as the reference does)
-    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    for (int g = gFirst + blockIdx.x * kVvWarps + wp; g < gFirst + nGroups; g += gridDim.x * kVvWarps) {
-        const int gb = 1 + 8 * g;                // first sibling (root vertices are dropped, main.cu:1634-1638)
-        const ushort4 o0 = offs[gb];
-        const int d0 = o0.w;
-        const float w = 1.0f / (float)(1 << d0);
-        // lane -> point (px,py,pz) of the group's corner grid
-        const int px = lane / 9, py = (lane / 3) % 3, pz = lane % 3;
-        bool mine = false;
-        int owner = -1, jo = 0;
-        if (lane < 27) {
-            const int sx = (px + 1) >> 1, sy = (py + 1) >> 1, sz = (pz + 1) >> 1;
-            const int id = gb + ((sx << 2) | (sy << 1) | sz);
-            const int j = (px - sx) | ((py - sy) << 1) | ((pz - sz) << 2);
-            int m;
-            owner = corner_owner(T, id, j, m);
-            mine = owner >= gb && owner < gb + 8;
-            jo = j ^ m;
-        }
-        const float pos[3] = {(float)((int)o0.x + px) * w, (float)((int)o0.y + py) * w, (float)((int)o0.z + pz) * w};
-        float val = 0.f;
-        // own level: every neighbour of every sibling lies in the 4x4x4 cube around the group
-        __syncwarp();
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int e = lane + 32 * h, ux = e >> 4, uy = (e >> 2) & 3, uz = e & 3;
-            const int sx = ux >> 1, sy = uy >> 1, sz = uz >> 1;
-            const int j = 9 * (ux - sx) + 3 * (uy - sy) + (uz - sz);          // 9(dx+1)+3(dy+1)+(dz+1) with d = u - 1 - s
-            const int q = T.nbr[27 * (i64)(gb + ((sx << 2) | (sy << 1) | sz)) + j];
-            sXc[wp][e] = q >= 0 ? x[q] : 0.f;
-        }
-        for (int e = lane; e < 36; e += 32) {
-            const int a = e / 12, pc = (e >> 2) % 3, cu = e & 3;
-            const int nn = 1 << d0, ao = (a == 0 ? (int)o0.x : (a == 1 ? (int)o0.y : (int)o0.z)) + cu - 1;
-            const float pp = (float)((a == 0 ? (int)o0.x : (a == 1 ? (int)o0.y : (int)o0.z)) + pc) * w;
-            sB0[wp][a][pc][cu] = (ao >= 0 && ao < nn) ? base_value(baseFn, nn - 1 + ao, pp) : 0.f;
-        }
-        __syncwarp();
-        if (mine) {
-            const int k = owner - gb, sox = (k >> 2) & 1, soy = (k >> 1) & 1, soz = k & 1;
-            float vx[3], vy[3], vz[3];
-#pragma unroll
-            for (int t = 0; t < 3; t++) { vx[t] = sB0[wp][0][px][sox + t]; vy[t] = sB0[wp][1][py][soy + t]; vz[t] = sB0[wp][2][pz][soz + t]; }
-            const float* xc = &sXc[wp][sox * 16 + soy * 4 + soz];
-#pragma unroll
-            for (int j = 0; j < 27; j++)
-                val = __fmaf_rn(__fmul_rn(__fmul_rn(xc[(j / 9) * 16 + ((j / 3) % 3) * 4 + (j % 3)], vx[j / 9]), vy[(j / 3) % 3]), vz[j % 3], val);
-        }
-        // shared ancestor levels d0-1 .. 0
-        int anc = parent[gb];
-        for (int l = d0 - 1; l >= 0; --l) {
-            const ushort4 oa = offs[anc];
-            __syncwarp();
-            if (lane < 27) {
-                int q = T.nbr[27 * (i64)anc + lane];
-                sX[wp][lane] = q >= 0 ? x[q] : 0.f;
-                // lane -> (axis a, point coordinate pc, k)
-                const int a = lane / 9, pc = (lane / 3) % 3, k = lane % 3;
-                const int nn = 1 << l, ao = (a == 0 ? (int)oa.x : (a == 1 ? (int)oa.y : (int)oa.z)) + k - 1;
-                const float pp = (float)((a == 0 ? (int)o0.x : (a == 1 ? (int)o0.y : (int)o0.z)) + pc) * w;
-                sB[wp][a][pc][k] = (ao >= 0 && ao < nn) ? base_value(baseFn, nn - 1 + ao, pp) : 0.f;
-            }
-            __syncwarp();
-            if (mine) {
-                float vx[3], vy[3], vz[3];
-#pragma unroll
-                for (int k = 0; k < 3; k++) { vx[k] = sB[wp][0][px][k]; vy[k] = sB[wp][1][py][k]; vz[k] = sB[wp][2][pz][k]; }
-                RV_ACC27(val, sX[wp], vx, vy, vz);
-            }
-            anc = parent[anc];
-        }
-        if (mine) {
-            int now = owner, depth = d0;
-            const int ex = exceedTab[jo];
-            while (depth < D) {
-                ++depth;
-                int c0 = child0[now];
-                if (c0 < 0) break;
-                now = c0 + ex;
-                accumulate_level(val, T.nbr + 27 * (i64)now, offs[now], x, baseFn, pos);
-            }
-            vval[8 * (i64)owner + jo] = __fsub_rn(val, iso);
-        }
-    }
-}
-
-// Streaming version of the kernel above (the one stage_extract launches).  Sibling groups are
+// One WARP per contiguous chunk of sibling groups.  The 8 siblings of a group share every
+// ancestor, so the 27 neighbour values of the ancestor levels are staged once per group in shared
+// memory and reused by all the corners the group owns (the 27 points of its 3x3x3 corner grid; a
+// point is evaluated by the group that holds its owner cell).  Each point still adds its terms in
+// the reference's order: own level, parents up to the root, then the finer nodes at that corner
+// (main.cu:2277-2322).  Sibling groups are
 // numbered in Morton order inside a depth, so consecutive groups share almost all ancestors: a
 // warp walks a CONTIGUOUS chunk of groups and keeps the 27 neighbour values of every ancestor
 // level in shared memory, re-gathering only the levels whose ancestor changed (1.3 levels per
@@ -1125,30 +995,6 @@ __device__ __forceinline__ void rv_cell_values(const RGeom& G, int r, int cx, in
         v[q] = rv_point_value(G, r, cx + (j & 1), cy + ((j >> 1) & 1), cz + ((j >> 2) & 1));
     }
 }
-__global__ void __launch_bounds__(256) k_rv_classify(RGeom G, unsigned char* __restrict__ cat, unsigned char* __restrict__ ntri, unsigned short* __restrict__ emask) {
-    const i64 total = (i64)G.nr * G.per;
-    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
-        const int r = (int)(t / G.per);
-        const unsigned l = (unsigned)(t - (i64)r * G.per);
-        const int cx = (int)compact3(l >> 2), cy = (int)compact3(l >> 1), cz = (int)compact3(l);
-        float v[8];
-        rv_cell_values(G, r, cx, cy, cz, v);
-        int c = 0;
-#pragma unroll
-        for (int q = 0; q < 8; q++) if (v[q] < 0.f) c |= 1 << q;
-        unsigned m = 0;
-#pragma unroll
-        for (int e = 0; e < 12; e++) {
-            if (__fmul_rn(v[cEdgeVertex[e][0]], v[cEdgeVertex[e][1]]) <= 0.f) {
-                int e2;
-                if (rv_edge_owner(G, r, cx, cy, cz, e, e2) == t) m |= 1u << e;
-            }
-        }
-        cat[t] = (unsigned char)c;
-        ntri[t] = cMcCount[c];
-        emask[t] = (unsigned short)m;
-    }
-}
 // sign summary of a brick's own 512 corner-7 values: 1 all > 0, 2 all < 0, 0 otherwise (one warp per brick)
 __global__ void __launch_bounds__(256) k_rv_brick_sign(const float* __restrict__ val7, int nBricks, unsigned char* __restrict__ sign) {
     const int lane = threadIdx.x & 31;
@@ -1296,55 +1142,6 @@ __global__ void __launch_bounds__(512) k_rv_emit_brick(RGeom G, const int* __res
         outT[3 * (i64)tb + j] = brickVBase[(int)(ow >> 9)] + (int)vpre[ow] + __popc((unsigned)emask[ow] & ((1u << e2) - 1u));
     }
 }
-__global__ void __launch_bounds__(256) k_rv_emit_vertices(RGeom G, const unsigned short* __restrict__ emask, const int* __restrict__ vbase, float* __restrict__ outV) {
-    const float w = 1.0f / (float)(1 << G.D);
-    const i64 total = (i64)G.nr * G.per;
-    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
-        unsigned m = emask[t];
-        if (!m) continue;
-        const int r = (int)(t / G.per);
-        const unsigned l = (unsigned)(t - (i64)r * G.per);
-        const int cx = (int)compact3(l >> 2), cy = (int)compact3(l >> 1), cz = (int)compact3(l);
-        float v[8];
-        rv_cell_values(G, r, cx, cy, cz, v);
-        const ushort4 ro = G.offs[G.roots[r]];
-        const int ox = ((int)ro.x << G.lv) + cx, oy = ((int)ro.y << G.lv) + cy, oz = ((int)ro.z << G.lv) + cz;
-        int k = 0;
-        for (int e = 0; e < 12; e++) {
-            if (!(m & (1u << e))) continue;
-            int r1 = cEdgeVertex[e][0], r2 = cEdgeVertex[e][1], dim = e >> 2;
-            int b1 = ring_to_bits(r1), b2 = ring_to_bits(r2);
-            float p1[3] = {(float)(ox + (b1 & 1)) * w, (float)(oy + ((b1 >> 1) & 1)) * w, (float)(oz + ((b1 >> 2) & 1)) * w};
-            float p2d = (float)((dim == 0 ? ox + (b2 & 1) : (dim == 1 ? oy + ((b2 >> 1) & 1) : oz + ((b2 >> 2) & 1)))) * w;
-            float f1 = v[r1], f2 = v[r2];
-            float pivot = __fdiv_rn(f1, __fsub_rn(f1, f2));
-            float another = __fsub_rn(1.0f, pivot);
-            float out[3] = {p1[0], p1[1], p1[2]};
-            out[dim] = __fmaf_rn(p2d, pivot, __fmul_rn(p1[dim], another));
-            i64 a = 3 * (i64)(vbase[t] + k);
-            outV[a] = out[0]; outV[a + 1] = out[1]; outV[a + 2] = out[2];
-            k++;
-        }
-    }
-}
-__global__ void __launch_bounds__(256) k_rv_emit_triangles(RGeom G, const unsigned char* __restrict__ cat, const unsigned char* __restrict__ ntri, const int* __restrict__ tbase,
-                                                           const unsigned short* __restrict__ emask, const int* __restrict__ vbase, int* __restrict__ outT) {
-    const i64 total = (i64)G.nr * G.per;
-    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
-        int nt = ntri[t];
-        if (!nt) continue;
-        const int r = (int)(t / G.per);
-        const unsigned l = (unsigned)(t - (i64)r * G.per);
-        const int cx = (int)compact3(l >> 2), cy = (int)compact3(l >> 1), cz = (int)compact3(l);
-        const int c = cat[t];
-        for (int j = 0; j < 3 * nt; j++) {
-            int e = cMcTri[c][j], e2;
-            i64 ow = rv_edge_owner(G, r, cx, cy, cz, e, e2);
-            outT[3 * (i64)tbase[t] + j] = vbase[ow] + __popc((unsigned)emask[ow] & ((1u << e2) - 1u));
-        }
-    }
-}
-
 struct PassOut {
     DBuf<float> v;
     DBuf<int> t;
