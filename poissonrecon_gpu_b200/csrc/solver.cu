@@ -176,6 +176,61 @@ __device__ __forceinline__ void warp_add(double part, double* sAcc, int d, int l
     if (lane == 0 && part != 0.0) atomicAdd(&sAcc[d], part);
 }
 
+// Streaming phases: two input vectors are read through a per-thread ring of kStreamQ 16-byte
+// cp.async copies into the warp's (otherwise idle) SpMV buffers, so that kStreamQ x 2 x 512 bytes
+// per warp are in flight at any time (twice what register staging allowed with 12 warps of 168
+// registers).  Work unit = one 32-lane batch of float4; the batches of all active depths form
+// one flat list (pre[d] = first batch of depth d), swept forwards or backwards (zig-zag).
+// A thread reads back exactly the 16 bytes it copied, so no warp-level synchronisation is needed.
+constexpr int kStreamQ = 8;
+struct BatchCursor {
+    int d, lo, hi;
+    __device__ __forceinline__ void init(const int* pre) { d = 1; lo = pre[1]; hi = pre[2]; }
+    // -> float index of this lane's float4 in batch u of the flat list (-1: past the end of the depth's rows)
+    __device__ __forceinline__ int locate(const int* pre, const int* row0, const int* row1, int u, int lane) {
+        while (u >= hi) { d++; lo = hi; hi = pre[d + 1]; }
+        while (u < lo) { d--; hi = lo; lo = pre[d]; }
+        const int c4 = (u - lo) * 32 + lane;
+        return c4 < ((row1[d] - row0[d]) >> 2) ? row0[d] + 4 * c4 : -1;
+    }
+};
+template <class F>
+__device__ __forceinline__ void stream_pairs(const int* pre, int total, const int* row0, const int* row1, const float* __restrict__ A0, const float* __restrict__ A1,
+                                             bool rev, float* ring /* this warp's smem */, int gwarp, int nwarps, int lane, F&& consume) {
+    const unsigned ringS = (unsigned)__cvta_generic_to_shared(ring);
+    BatchCursor ci, cc;
+    ci.init(pre); cc.init(pre);
+    int bi = gwarp;                                    // next batch to issue
+    auto issue = [&](int slot) {
+        if (bi < total) {
+            const int i = ci.locate(pre, row0, row1, rev ? total - 1 - bi : bi, lane);
+            if (i >= 0) {
+                const unsigned dst = ringS + 16u * (unsigned)(slot * 32 + lane);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(A0 + i) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 16u * 32u * kStreamQ), "l"(A1 + i) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        bi += nwarps;
+    };
+#pragma unroll
+    for (int q = 0; q < kStreamQ; q++) issue(q);
+    int slot = 0;
+    for (int b = gwarp; b < total; b += nwarps) {
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(kStreamQ - 1) : "memory");
+        const int i = cc.locate(pre, row0, row1, rev ? total - 1 - b : b, lane);
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+        if (i >= 0) {
+            v0 = *reinterpret_cast<const float4*>(ring + 4 * (slot * 32 + lane));
+            v1 = *reinterpret_cast<const float4*>(ring + 4 * ((kStreamQ + slot) * 32 + lane));
+        }
+        consume(cc.d, i, v0, v1);           // called by ALL lanes (i < 0: no element), the depth is warp-uniform
+        issue(slot);
+        slot = slot + 1 == kStreamQ ? 0 : slot + 1;
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
 extern __shared__ __align__(16) float sDyn[];   // [kCgWarps][2][kWarpBufFloats]
 
 template <bool MG>
@@ -188,6 +243,7 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
     __shared__ int sStep[kMaxDepth + 3];      // sStep[d] = first flat SpMV step of depth d (active depths only), sStep[D+1] = total
     __shared__ int sPend[kMaxDepth + 1];      // x of depth d still lacks alpha_{k-1} p_{k-1} (applied under the next SpMV)
     __shared__ int sXup[kMaxDepth + 3];       // sXup[d] = first flat 32-lane batch of the pending x updates of depth d
+    __shared__ int sAct4[kMaxDepth + 3];      // the same over the ACTIVE depths (streaming phases)
     const int D = P.D, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gwarp = blockIdx.x * kCgWarps + warp, nwarps = gridDim.x * kCgWarps;
     const int gthread = blockIdx.x * kCgBlock + tid, nthreads = gridDim.x * kCgBlock;
@@ -291,6 +347,12 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
                 sStep[d + 1] = acc;
             }
             acc = 0;
+            sAct4[0] = 0; sAct4[1] = 0;
+            for (int d = 1; d <= D; d++) {
+                if (sActive[d]) acc += (((P.row1[d] - P.row0[d]) >> 2) + 31) >> 5;
+                sAct4[d + 1] = acc;
+            }
+            acc = 0;
             sXup[0] = 0; sXup[1] = 0;
             for (int d = 1; d <= D; d++) {
                 if (sPend[d]) acc += (((P.row1[d] - P.row0[d]) >> 2) + 31) >> 5;
@@ -306,32 +368,17 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
 
         // ---------------- phase C: p = r + beta p   (beta = 0 and p = 0 in the first iteration)
         const bool revC = P.zigzag && (phase++ & 1) != 0;
-        for (int dd = 1; dd <= D; dd++) {
-            const int d = revC ? D + 1 - dd : dd;
-            if (!sActive[d]) continue;
-            const float be = sBeta[d];
-            const int i0 = P.row0[d], n4 = (P.row1[d] - i0) >> 2;
-            for (int c = gthread; c < n4; c += kStreamUnroll * nthreads) {
-                float4 rv[kStreamUnroll], pv[kStreamUnroll];
-#pragma unroll
-                for (int k = 0; k < kStreamUnroll; k++) {
-                    const int ck = c + k * nthreads, ik = i0 + 4 * (revC ? n4 - 1 - ck : ck);
-                    if (ck < n4) { rv[k] = *reinterpret_cast<const float4*>(P.r + ik); pv[k] = *reinterpret_cast<const float4*>(pOld + ik); }
-                }
-#pragma unroll
-                for (int k = 0; k < kStreamUnroll; k++) {
-                    const int ck = c + k * nthreads, ik = i0 + 4 * (revC ? n4 - 1 - ck : ck);
-                    if (ck < n4) {
-                        float4 o;
-                        o.x = __fadd_rn(rv[k].x, __fmul_rn(be, pv[k].x));
-                        o.y = __fadd_rn(rv[k].y, __fmul_rn(be, pv[k].y));
-                        o.z = __fadd_rn(rv[k].z, __fmul_rn(be, pv[k].z));
-                        o.w = __fadd_rn(rv[k].w, __fmul_rn(be, pv[k].w));
-                        *reinterpret_cast<float4*>(pNew + ik) = o;
-                    }
-                }
-            }
-        }
+        stream_pairs(sAct4, sAct4[D + 1], P.row0, P.row1, P.r, pOld, revC, wbuf, gwarp, nwarps, lane,
+                     [&](int d, int i, const float4& rv, const float4& pv) {
+                         if (i < 0) return;
+                         const float be = sBeta[d];
+                         float4 o;
+                         o.x = __fadd_rn(rv.x, __fmul_rn(be, pv.x));
+                         o.y = __fadd_rn(rv.y, __fmul_rn(be, pv.y));
+                         o.z = __fadd_rn(rv.z, __fmul_rn(be, pv.z));
+                         o.w = __fadd_rn(rv.w, __fmul_rn(be, pv.w));
+                         *reinterpret_cast<float4*>(pNew + i) = o;
+                     });
         cg_sync<MG>(grid, P, epoch, cur, -1, nullptr);
         // ---------------- phase A: Ap = A p ; p.Ap over the flat step list of all active depths
         {
@@ -531,37 +578,27 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
         __syncthreads();
         // ---------------- phase B: r -= alpha Ap ; r.r   (x += alpha p is applied under the next SpMV, or by the sweep after the loop)
         const bool revB = P.zigzag && (phase++ & 1) != 0;
-        for (int dd = 1; dd <= D; dd++) {
-            const int d = revB ? D + 1 - dd : dd;
-            if (!sActive[d]) continue;
-            const float al = sAlpha[d];
-            const int i0 = P.row0[d], n4 = (P.row1[d] - i0) >> 2;
+        {
             double part = 0.0;
-            for (int c = gthread; c < n4; c += kStreamUnrollB * nthreads) {
-                float4 av[kStreamUnrollB], rv[kStreamUnrollB];
-#pragma unroll
-                for (int k = 0; k < kStreamUnrollB; k++) {
-                    const int ck = c + k * nthreads, ik = i0 + 4 * (revB ? n4 - 1 - ck : ck);
-                    if (ck < n4) {
-                        av[k] = *reinterpret_cast<const float4*>(P.Ap + ik);
-                        rv[k] = *reinterpret_cast<const float4*>(P.r + ik);
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < kStreamUnrollB; k++) {
-                    const int ck = c + k * nthreads, ik = i0 + 4 * (revB ? n4 - 1 - ck : ck);
-                    if (ck < n4) {
-                        float4 ro;
-                        ro.x = __fmaf_rn(-al, av[k].x, rv[k].x); ro.y = __fmaf_rn(-al, av[k].y, rv[k].y); ro.z = __fmaf_rn(-al, av[k].z, rv[k].z); ro.w = __fmaf_rn(-al, av[k].w, rv[k].w);
-                        *reinterpret_cast<float4*>(P.r + ik) = ro;
-                        part += (double)(ro.x * ro.x);
-                        part += (double)(ro.y * ro.y);
-                        part += (double)(ro.z * ro.z);
-                        part += (double)(ro.w * ro.w);
-                    }
-                }
-            }
-            warp_add(part, sAcc, d, lane);
+            int partDepth = 0;
+            stream_pairs(sAct4, sAct4[D + 1], P.row0, P.row1, P.Ap, P.r, revB, wbuf, gwarp, nwarps, lane,
+                         [&](int d, int i, const float4& av, const float4& rv) {
+                             if (d != partDepth) {           // (warp-uniform: a batch never mixes depths)
+                                 if (partDepth) warp_add(part, sAcc, partDepth, lane);
+                                 part = 0.0;
+                                 partDepth = d;
+                             }
+                             if (i < 0) return;
+                             const float al = sAlpha[d];
+                             float4 ro;
+                             ro.x = __fmaf_rn(-al, av.x, rv.x); ro.y = __fmaf_rn(-al, av.y, rv.y); ro.z = __fmaf_rn(-al, av.z, rv.z); ro.w = __fmaf_rn(-al, av.w, rv.w);
+                             *reinterpret_cast<float4*>(P.r + i) = ro;
+                             part += (double)(ro.x * ro.x);
+                             part += (double)(ro.y * ro.y);
+                             part += (double)(ro.z * ro.z);
+                             part += (double)(ro.w * ro.w);
+                         });
+            if (partDepth) warp_add(part, sAcc, partDepth, lane);
         }
         __syncthreads();
         if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&dRRn[tid], sAcc[tid]);
