@@ -182,16 +182,21 @@ __device__ __forceinline__ void warp_add(double part, double* sAcc, int d, int l
 // registers).  Work unit = one 32-lane batch of float4; the batches of all active depths form
 // one flat list (pre[d] = first batch of depth d), swept forwards or backwards (zig-zag).
 // A thread reads back exactly the 16 bytes it copied, so no warp-level synchronisation is needed.
-constexpr int kStreamQ = 8;
+constexpr int kStreamQ = 12;
 struct BatchCursor {
-    int d, lo, hi;
-    __device__ __forceinline__ void init(const int* pre) { d = 1; lo = pre[1]; hi = pre[2]; }
+    int d, lo, hi, r0, n4;          // current depth, its batch range, its first row and float4 count
+    __device__ __forceinline__ void init(const int* pre, const int* row0, const int* row1) {
+        d = 1; lo = pre[1]; hi = pre[2]; r0 = row0[1]; n4 = (row1[1] - row0[1]) >> 2;
+    }
     // -> float index of this lane's float4 in batch u of the flat list (-1: past the end of the depth's rows)
     __device__ __forceinline__ int locate(const int* pre, const int* row0, const int* row1, int u, int lane) {
-        while (u >= hi) { d++; lo = hi; hi = pre[d + 1]; }
-        while (u < lo) { d--; hi = lo; lo = pre[d]; }
+        if (u >= hi || u < lo) {
+            while (u >= hi) { d++; lo = hi; hi = pre[d + 1]; }
+            while (u < lo) { d--; hi = lo; lo = pre[d]; }
+            r0 = row0[d]; n4 = (row1[d] - r0) >> 2;
+        }
         const int c4 = (u - lo) * 32 + lane;
-        return c4 < ((row1[d] - row0[d]) >> 2) ? row0[d] + 4 * c4 : -1;
+        return c4 < n4 ? r0 + 4 * c4 : -1;
     }
 };
 template <class F>
@@ -199,7 +204,7 @@ __device__ __forceinline__ void stream_pairs(const int* pre, int total, const in
                                              bool rev, float* ring /* this warp's smem */, int gwarp, int nwarps, int lane, F&& consume) {
     const unsigned ringS = (unsigned)__cvta_generic_to_shared(ring);
     BatchCursor ci, cc;
-    ci.init(pre); cc.init(pre);
+    ci.init(pre, row0, row1); cc.init(pre, row0, row1);
     int bi = gwarp;                                    // next batch to issue
     auto issue = [&](int slot) {
         if (bi < total) {
