@@ -1216,12 +1216,14 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
         // multi-GPU: the bricks of the pass are split evenly, the other ranks' values are pulled over NVLink
         const i64 nBricks = total / 512;
         const int W = c.mg.world, me = c.mg.rank;
-        const i64 b0 = mg ? (nBricks * me) / W : 0, b1 = mg ? (nBricks * (me + 1)) / W : nBricks;
+        // (small passes are evaluated on every rank: two box-wide barriers cost more than their bricks)
+        const bool shardPass = mg && nBricks >= 16384;
+        const i64 b0 = shardPass ? (nBricks * me) / W : 0, b1 = shardPass ? (nBricks * (me + 1)) / W : nBricks;
         if (b1 > b0) PRB_LAUNCH(c, k_rv_brick_values, (unsigned)(b1 - b0), 64, 0, G, (unsigned)b0);
-        if (mg) {
+        if (shardPass) {
             PRB_TRY(mg_barrier(c));
-            for (int q = 0; q < W; q++) {
-                if (q == me) continue;
+            for (int qi = 1; qi < W; qi++) {          // start with the next rank: the peers are not all pulled from in the same order
+                const int q = (me + qi) % W;
                 const i64 a = (nBricks * q) / W, b = (nBricks * (q + 1)) / W;
                 const float* src = (const float*)(c.mg.peer[q] + c.mgVal7Off);
                 if (b > a) PRB_CUDA(cudaMemcpyAsync(val7p + 512 * a, src + 512 * a, sizeof(float) * 512 * (size_t)(b - a), cudaMemcpyDeviceToDevice, st));
@@ -1383,8 +1385,8 @@ int stage_extract(Context& c) {
         }
         if (mg) {
             PRB_TRY(mg_barrier(c));
-            for (int q = 0; q < W; q++) {
-                if (q == me) continue;
+            for (int qi = 1; qi < W; qi++) {          // start with the next rank: the peers are not all pulled from in the same order
+                const int q = (me + qi) % W;
                 const i64 a = (nGroups * q) / W, b = (nGroups * (q + 1)) / W;
                 const float* src = (const float*)(c.mg.peer[q] + c.mgVvalOff);
                 if (b > a) PRB_CUDA(cudaMemcpyAsync(c.vvalPtr + 8 * (1 + 8 * a), src + 8 * (1 + 8 * a), sizeof(float) * 64 * (size_t)(b - a), cudaMemcpyDeviceToDevice, st));

@@ -734,8 +734,8 @@ int stage_solve(Context& c) {
         c.mg.epoch = (unsigned)hIters[15];
         // collect the other ranks' parts of the solution (pull over NVLink), then let nobody run ahead
         PRB_TRY(mg_barrier(c));
-        for (int q = 0; q < c.mg.world; q++) {
-            if (q == c.mg.rank) continue;
+        for (int qi = 1; qi < c.mg.world; qi++) {     // start with the next rank: the peers are not all pulled from in the same order
+            const int q = (c.mg.rank + qi) % c.mg.world;
             const float* px = (const float*)(c.mg.peer[q] + c.mgXOff) + 7;
             for (int d = c.shardFrom; d <= D; d++) {
                 size_t n = (size_t)(c.rowLo[d][q + 1] - c.rowLo[d][q]);
