@@ -106,7 +106,9 @@ int prb_set_array(prb_context* ctx, const char* name, const void* src, int64_t b
 int prb_run_stage(prb_context* ctx, const char* name);
 
 /* Options: "cg_tol" (default 1e-5, CG_CUDA.cuh:347), "cg_max_iter" (10000, CG_CUDA.cuh:263),
- * "refine" (1 = run the refinement passes, main.cu:3799-4564). */
+ * "refine" (1 = run the refinement passes, main.cu:3799-4564), "refine_implicit" (1; 0 = materialise
+ * the virtual subtrees of every pass: cross-check path), "cg_zigzag" (1 = the CG phases sweep memory
+ * in alternating directions for L2 reuse; results do not depend on it). */
 int prb_set_option(prb_context* ctx, const char* key, double value);
 
 /* ---- Multi-GPU (new: the reference is single-GPU, devID = 0 hard-coded at CG_CUDA.cuh:356).
