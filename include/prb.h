@@ -108,7 +108,8 @@ int prb_run_stage(prb_context* ctx, const char* name);
 /* Options: "cg_tol" (default 1e-5, CG_CUDA.cuh:347), "cg_max_iter" (10000, CG_CUDA.cuh:263),
  * "refine" (1 = run the refinement passes, main.cu:3799-4564), "refine_implicit" (1; 0 = materialise
  * the virtual subtrees of every pass: cross-check path), "cg_zigzag" (1 = the CG phases sweep memory
- * in alternating directions for L2 reuse; results do not depend on it). */
+ * in alternating directions for L2 reuse; results do not depend on it), "refine_bound_check" (0; 1 = evaluate
+ * every refinement brick and fail if a certified sign is wrong: test mode). */
 int prb_set_option(prb_context* ctx, const char* key, double value);
 
 /* ---- Multi-GPU (new: the reference is single-GPU, devID = 0 hard-coded at CG_CUDA.cuh:356).

@@ -157,6 +157,8 @@ struct Context {
     double cgTol = 1e-5;
     int cgMaxIter = 10000;
     int cgZigzag = 1;
+    int refineBoundCheck = 0;      // 1: evaluate every refinement brick and verify the certified signs (tests)
+    long long boundChecked = 0, boundEvaluated = 0;
     int doRefine = 1;
     int refineImplicit = 1;        // 0: materialised virtual subtrees for every pass (debug / cross-check)
     int smCount = kSMs;

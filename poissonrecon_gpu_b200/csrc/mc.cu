@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "mg_device.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include "mc_case_table.h"
 #include "scan.cuh"
 
@@ -777,13 +778,13 @@ __device__ __noinline__ float rv_fine_levels(const RGeom& G, const int* __restri
     return val;
 }
 
-__global__ void __launch_bounds__(64) k_rv_brick_values(RGeom G, unsigned brick0) {
+__global__ void __launch_bounds__(64) k_rv_brick_values(RGeom G, const int* __restrict__ list) {
     __shared__ __align__(16) float sX[kMaxDepth + 1][28];
     __shared__ int sIds[27];
     __shared__ int sAny[kMaxDepth + 1];
     __shared__ int sNeedFine;
     const int tid = threadIdx.x;
-    const i64 cell0 = ((i64)blockIdx.x + brick0) * 512;
+    const i64 cell0 = (i64)(list ? list[blockIdx.x] : (int)blockIdx.x) * 512;
     const int r = (int)(cell0 / G.per);
     const unsigned l0 = (unsigned)(cell0 - (i64)r * G.per);
     const int L = G.D - 3;                                   // level of the brick
@@ -995,6 +996,158 @@ __device__ __forceinline__ void rv_cell_values(const RGeom& G, int r, int cx, in
         v[q] = rv_point_value(G, r, cx + (j & 1), cy + ((j >> 1) & 1), cz + ((j >> 2) & 1));
     }
 }
+// ---- certified signs without evaluation.  Hundreds of thousands (depth 10) to millions (depth 11)
+// of bricks lie far from the surface; evaluating their 512 cells only to find one common sign is
+// most of the refinement cost.  Inside a brick no basis function of a level <= D-3 has a knot, so
+// every level's contribution is ONE tensor-product quadratic there and chi - iso on the brick's closed
+// box (its 9x9x9 grid points, evaluated along the chain of any of its cells) is bounded by its 27 Bernstein coefficients (convex hull property), computed in
+// double from the same piece tables.  The float evaluation the kernels above would perform differs
+// from that polynomial by at most E = sum |x_j| (e_x M_y M_z + M_x e_y M_z + M_x M_y e_z + 1e-4 M_x M_y M_z)
+// (e: evaluation error bound of the cumulative-piece form, 8 ulp of the sum of the absolute monomial
+// values; M: bound of the factor on the interval; 1e-4 covers the <= 330 product / accumulation
+// roundings).  A brick is certified (1: all > 0, 2: all < 0) only when every coefficient clears iso
+// by 2E; bricks with contributions from levels finer than D-3 are never certified.  Certified
+// bricks are not evaluated unless a brick that has to be classified reads them.
+__global__ void __launch_bounds__(256) k_rv_brick_bound(RGeom G, int nBricks, unsigned char* __restrict__ cert) {
+    __shared__ double sBeta[8][9][3];        // [warp][axis*3 + k][Bernstein index]
+    __shared__ double sErr[8][9], sMax[8][9];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int L = G.D - 3;
+    const double w = 1.0 / (double)(1 << G.D);
+    const int ci = lane / 9, cj = (lane / 3) % 3, ck = lane % 3;
+    for (int b = blockIdx.x * 8 + wp; b < nBricks; b += gridDim.x * 8) {
+        const i64 cell0 = (i64)b * 512;
+        const int r = (int)(cell0 / G.per);
+        const unsigned l0 = (unsigned)(cell0 - (i64)r * G.per);
+        const ushort4 ro = G.offs[G.roots[r]];
+        const int g[3] = {((int)ro.x << G.lv) + (int)compact3(l0 >> 2), ((int)ro.y << G.lv) + (int)compact3(l0 >> 1), ((int)ro.z << G.lv) + (int)compact3(l0)};
+        double acc = 0.0, E = 0.0;
+        int cur = -1;
+        if (lane < 27) { int q = G.rootNb[27 * r + lane]; cur = (q >= 0 && q < G.M) ? q : -1; }
+        bool broke = false;
+        for (int lvl = 0; lvl <= L; lvl++) {
+            // the 27 neighbour values of the brick's ancestor at this level
+            float X = 0.f;
+            if (lvl <= G.rd) {
+                if (lane < 27) X = G.rootX[((i64)r * (G.rd + 1) + lvl) * 27 + lane];
+            } else {
+                int c = (int)((l0 >> (3 * (G.D - lvl))) & 7u), pj = 0, cc = 0;
+                if (lane < 27) lut_parent_child(c, lane, pj, cc);
+                int p = __shfl_sync(0xffffffffu, cur, pj);
+                int nxt = -1;
+                if (lane < 27 && p >= 0) { int c0 = G.child0[p]; if (c0 >= 0) nxt = c0 + cc; }
+                if (nxt >= 0) X = G.x[nxt];
+                cur = nxt;
+                if (!__any_sync(0xffffffffu, nxt >= 0)) { broke = true; break; }      // nothing real at this level: nothing below it either
+            }
+            // lanes 0..8: the quadratic of function k of axis a on the brick's own points [t0, t1]
+            __syncwarp();
+            if (lane < 9) {
+                const int a = lane / 3, k = lane % 3;
+                const int nn = 1 << lvl, ao = (g[a] >> (G.D - lvl)) + k - 1;
+                double C0 = 0.0, C1 = 0.0, C2 = 0.0, A = 0.0;
+                const double t0 = (double)g[a] * w, t1 = (double)(g[a] + 8) * w, tm = 0.5 * (t0 + t1);
+                if (ao >= 0 && ao < nn) {
+                    const float* f = G.baseFn + 20 * (i64)(nn - 1 + ao);
+                    bool on = true;
+                    for (int i = 0; i < 4; i++) {
+                        on = on && tm > (double)f[5 * i + 4];
+                        if (on) { C0 += (double)f[5 * i]; C1 += (double)f[5 * i + 1]; C2 += (double)f[5 * i + 2]; }
+                        // (all pieces count for the error bound: a piece whose start sits on the brick's edge may
+                        // switch on at the last grid point, where it is zero up to its own evaluation noise)
+                        A += fabs((double)f[5 * i]) + fabs((double)f[5 * i + 1]) * t1 + fabs((double)f[5 * i + 2]) * t1 * t1;
+                    }
+                }
+                const double b0 = C0 + C1 * t0 + C2 * t0 * t0, b2 = C0 + C1 * t1 + C2 * t1 * t1, b1 = C0 + C1 * tm + C2 * t0 * t1;
+                sBeta[wp][lane][0] = b0; sBeta[wp][lane][1] = b1; sBeta[wp][lane][2] = b2;
+                sErr[wp][lane] = 8.0 * 1.1920929e-7 * A;
+                sMax[wp][lane] = fmax(fabs(b0), fmax(fabs(b1), fabs(b2)));
+            }
+            __syncwarp();
+            // lanes 0..26: Bernstein coefficient (ci, cj, ck) += sum_j X_j bx[jx][ci] by[jy][cj] bz[jz][ck]; lane j also the error term of x_j
+            double term = 0.0;
+            if (lane < 27) {
+                const double ax = fabs((double)X);
+                const int jx = lane / 9, jy = (lane / 3) % 3, jz = lane % 3;
+                const double mx = sMax[wp][jx], my = sMax[wp][3 + jy], mz = sMax[wp][6 + jz];
+                term = ax * (sErr[wp][jx] * my * mz + mx * sErr[wp][3 + jy] * mz + mx * my * sErr[wp][6 + jz] + 1e-4 * mx * my * mz);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
+            E += term;
+            // separable contraction over (jz, jy, jx): lane (a, b, c) = (lane / 9, (lane / 3) % 3, lane % 3)
+            {
+                const int l3 = lane < 27 ? lane - ck : 0;           // 9 a + 3 b
+                double u = 0.0, v = 0.0, cc = 0.0;
+#pragma unroll
+                for (int jz = 0; jz < 3; jz++) u += (double)__shfl_sync(0xffffffffu, X, l3 + jz) * sBeta[wp][6 + jz][ck];          // (jx, jy, ck)
+                const int l9 = lane < 27 ? 9 * ci + ck : 0;
+#pragma unroll
+                for (int jy = 0; jy < 3; jy++) v += __shfl_sync(0xffffffffu, u, l9 + 3 * jy) * sBeta[wp][3 + jy][cj];             // (jx, cj, ck)
+                const int l1 = lane < 27 ? 3 * cj + ck : 0;
+#pragma unroll
+                for (int jx = 0; jx < 3; jx++) cc += __shfl_sync(0xffffffffu, v, l1 + 9 * jx) * sBeta[wp][jx][ci];                // (ci, cj, ck)
+                if (lane < 27) acc += cc;
+            }
+        }
+        // levels finer than the brick level (children of the level-L neighbours): never certified
+        const bool finer = !broke && __any_sync(0xffffffffu, lane < 27 && cur >= 0 && G.child0[cur] >= 0);
+        double lo = lane < 27 ? acc : 1e300, hi = lane < 27 ? acc : -1e300;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+        if (lane == 0) {
+            const double iso = (double)G.iso;
+            const double margin = 2.0 * E + 1e-6 * (fabs(iso) + fmax(fabs(lo), fabs(hi))) + 1e-30;
+            unsigned char c = 0;
+            if (!finer) { if (lo - iso > margin) c = 1; else if (hi - iso < -margin) c = 2; }
+            cert[b] = c;
+        }
+    }
+}
+// brick holding the virtual cell (x, y, z) of root r, coordinates in [-n, 2n) (-1: that cell is not virtual)
+__device__ __forceinline__ int rv_brick_of(const RGeom& G, int r, int x, int y, int z) {
+    int r2;
+    if (!rv_locate(G, r, x, y, z, r2)) return -1;
+    return (int)(((i64)r2 * G.per + rv_morton(x, y, z)) >> 9);
+}
+// The 9x9x9 grid of brick b' takes its values from virtual cells of b' and of the 7 bricks below it (in its
+// root or in a virtual neighbour root); every one of them is evaluated along the chain of a cell of the
+// brick that holds it, inside that brick's closed box.  b' has to be classified unless all of those bricks
+// (that exist) are certified with one common sign.
+__global__ void __launch_bounds__(256) k_rv_brick_full(RGeom G, int nBricks, const unsigned char* __restrict__ cert, unsigned char* __restrict__ full) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nBricks; b += gridDim.x * blockDim.x) {
+        const i64 cell0 = (i64)b * 512;
+        const int r = (int)(cell0 / G.per);
+        const unsigned l0 = (unsigned)(cell0 - (i64)r * G.per);
+        const int bx = (int)compact3(l0 >> 2), by = (int)compact3(l0 >> 1), bz = (int)compact3(l0);
+        const int s0 = cert[b];
+        bool same = s0 != 0;
+        for (int q = 1; q < 8 && same; q++) {
+            const int src = rv_brick_of(G, r, bx - ((q & 1) ? 8 : 0), by - ((q & 2) ? 8 : 0), bz - ((q & 4) ? 8 : 0));
+            if (src >= 0) same = cert[src] == s0;
+        }
+        full[b] = same ? 0 : 1;
+    }
+}
+// brick b has to be evaluated when a brick that is classified reads it: itself or one of the 7 bricks above it
+__global__ void __launch_bounds__(256) k_rv_brick_needed(RGeom G, int nBricks, const unsigned char* __restrict__ full, int* __restrict__ needed) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nBricks; b += gridDim.x * blockDim.x) {
+        const i64 cell0 = (i64)b * 512;
+        const int r = (int)(cell0 / G.per);
+        const unsigned l0 = (unsigned)(cell0 - (i64)r * G.per);
+        const int bx = (int)compact3(l0 >> 2), by = (int)compact3(l0 >> 1), bz = (int)compact3(l0);
+        bool need = false;
+        for (int q = 0; q < 8 && !need; q++) {
+            const int dst = rv_brick_of(G, r, bx + ((q & 1) ? 8 : 0), by + ((q & 2) ? 8 : 0), bz + ((q & 4) ? 8 : 0));
+            if (dst >= 0) need = full[dst] != 0;
+        }
+        needed[b] = need ? 1 : 0;
+    }
+}
+__global__ void __launch_bounds__(256) k_rv_bound_check(int nBricks, const unsigned char* __restrict__ cert, const unsigned char* __restrict__ sign, int* __restrict__ bad) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nBricks; b += gridDim.x * blockDim.x)
+        if (cert[b] != 0 && cert[b] != sign[b]) atomicAdd(bad, 1);
+}
 // sign summary of a brick's own 512 corner-7 values: 1 all > 0, 2 all < 0, 0 otherwise (one warp per brick)
 __global__ void __launch_bounds__(256) k_rv_brick_sign(const float* __restrict__ val7, int nBricks, unsigned char* __restrict__ sign) {
     const int lane = threadIdx.x & 31;
@@ -1018,7 +1171,7 @@ __global__ void __launch_bounds__(256) k_rv_brick_sign(const float* __restrict__
 // exclusive prefix of the vertex count INSIDE the brick; per brick: vertex and triangle totals.  The
 // pass-wide offsets then come from a scan over bricks (hundreds of thousands) instead of cells
 // (hundreds of millions), and only the active bricks are visited again for the emission.
-__global__ void __launch_bounds__(512) k_rv_classify_brick(RGeom G, const unsigned char* __restrict__ bsign, unsigned char* __restrict__ cat, unsigned short* __restrict__ emask,
+__global__ void __launch_bounds__(512) k_rv_classify_brick(RGeom G, const unsigned char* __restrict__ bsign /* full[] flags */, unsigned char* __restrict__ cat, unsigned short* __restrict__ emask,
                                                            unsigned short* __restrict__ vpre, int* __restrict__ brickV, int* __restrict__ brickT, int nBricks) {
     __shared__ int sScan[33];
     __shared__ float sV[9 * 9 * 9];
@@ -1030,20 +1183,10 @@ __global__ void __launch_bounds__(512) k_rv_classify_brick(RGeom G, const unsign
     const int r = (int)(cell0 / G.per);
     const unsigned l0 = (unsigned)(cell0 - (i64)r * G.per);
     const int bx = (int)compact3(l0 >> 2), by = (int)compact3(l0 >> 1), bz = (int)compact3(l0);   // root-local origin of the brick
-    // the 9x9x9 grid of a brick inside its root takes its values from this brick and the 7 bricks below it
-    // (x-8, y-8, z-8 combinations): when all eight are uniformly of one strict sign, so is the grid
-    if (bx >= 8 && by >= 8 && bz >= 8) {
-        bool ok = true;                        // threads 0..7 look at one brick each (one memory latency, not eight)
-        if (tid < 8) {
-            const unsigned ln = rv_morton(bx - ((tid & 1) ? 8 : 0), by - ((tid & 2) ? 8 : 0), bz - ((tid & 4) ? 8 : 0));
-            const int sq = bsign[(int)(((i64)r * G.per + ln) >> 9)];
-            const int s0 = __shfl_sync(0xffu, sq, 0);
-            ok = sq != 0 && sq == s0;
-        }
-        if (__syncthreads_and(ok)) {
-            if (tid == 0) { brickV[brick] = 0; brickT[brick] = 0; }
-            continue;
-        }
+    // bricks whose grid is certified to be of one strict sign (k_rv_brick_bound / k_rv_brick_full) produce nothing
+    if (!bsign[brick]) {
+        if (tid == 0) { brickV[brick] = 0; brickT[brick] = 0; }
+        continue;
     }
     const int cx = (int)compact3((unsigned)tid >> 2), cy = (int)compact3((unsigned)tid >> 1), cz = (int)compact3((unsigned)tid);
     const float own = G.val7[cell0 + tid];
@@ -1194,14 +1337,8 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     DBuf<unsigned short>& emask = c.wsEmask;
     PRB_TRY(rootNb.alloc(27 * (size_t)nr, st));
     PRB_TRY(rootX.alloc((size_t)nr * (rd + 1) * 27, st));
-    float* val7p = nullptr;
-    if (mg) {
-        if (!c.mgVal7 || (size_t)total > c.mgVal7Cap) { set_error("multi-GPU arena too small for the refinement pass values"); return PRB_ERR_NOMEM; }
-        val7p = c.mgVal7;
-    } else {
-        PRB_TRY(c.wsVal7.ensure((size_t)total, st));
-        val7p = c.wsVal7.p;
-    }
+    PRB_TRY(c.wsVal7.ensure((size_t)total, st));
+    float* val7p = c.wsVal7.p;
     PRB_TRY(low.ensure((size_t)nr * 3 * n1 * n1, st));
     PRB_LAUNCH(c, k_set_rootmap, grid_for(c, nr, 256), 256, 0, dRoots, nr, 0, 0, rootMap.p);
     PRB_LAUNCH(c, k_rv_roots, div_up((i64)nr * 32, 256), 256, 0, nr, rd, c.M, dRoots, rootMap.p, c.neighs.p, c.parent.p, c.xv, rootNb.p, rootX.p);
@@ -1212,27 +1349,49 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     PRB_TRY(ensure_bv_tables(c));
     G.bvCell = (const float4*)c.dBvCell.p;
     G.iso = c.iso; G.val7 = val7p; G.low = low.p;
-    {
-        // multi-GPU: the bricks of the pass are split evenly, the other ranks' values are pulled over NVLink
-        const i64 nBricks = total / 512;
-        const int W = c.mg.world, me = c.mg.rank;
-        // (small passes are evaluated on every rank: two box-wide barriers cost more than their bricks)
-        const bool shardPass = mg && nBricks >= 16384;
-        const i64 b0 = shardPass ? (nBricks * me) / W : 0, b1 = shardPass ? (nBricks * (me + 1)) / W : nBricks;
-        if (b1 > b0) PRB_LAUNCH(c, k_rv_brick_values, (unsigned)(b1 - b0), 64, 0, G, (unsigned)b0);
-        if (shardPass) {
-            PRB_TRY(mg_barrier(c));
-            for (int qi = 1; qi < W; qi++) {          // start with the next rank: the peers are not all pulled from in the same order
-                const int q = (me + qi) % W;
-                const i64 a = (nBricks * q) / W, b = (nBricks * (q + 1)) / W;
-                const float* src = (const float*)(c.mg.peer[q] + c.mgVal7Off);
-                if (b > a) PRB_CUDA(cudaMemcpyAsync(val7p + 512 * a, src + 512 * a, sizeof(float) * 512 * (size_t)(b - a), cudaMemcpyDeviceToDevice, st));
-            }
-            PRB_TRY(mg_barrier(c));     // nobody overwrites its values (next pass) while a peer still reads them
-        }
-    }
-    PRB_LAUNCH(c, k_rv_low_values, grid_for(c, (i64)nr * 3 * n1 * n1, 128, 16), 128, 0, G);
     const int nBricks = (int)(total / 512);
+    // certified signs -> bricks to classify -> bricks to evaluate (every rank evaluates the same short list:
+    // it is a few per cent of the pass, less than a rank's share of all bricks plus the peer pulls would be)
+    DBuf<unsigned char> cert, full;
+    DBuf<int> needFlag, needExcl, needList;
+    PRB_TRY(cert.alloc((size_t)nBricks, st)); PRB_TRY(full.alloc((size_t)nBricks, st));
+    PRB_TRY(needFlag.alloc((size_t)nBricks, st)); PRB_TRY(needExcl.alloc((size_t)nBricks, st));
+    PRB_LAUNCH(c, k_rv_brick_bound, grid_for(c, (i64)nBricks * 32, 256, 8), 256, 0, G, nBricks, cert.p);
+    PRB_LAUNCH(c, k_rv_brick_full, grid_for(c, nBricks, 256), 256, 0, G, nBricks, cert.p, full.p);
+    PRB_LAUNCH(c, k_rv_brick_needed, grid_for(c, nBricks, 256), 256, 0, G, nBricks, full.p, needFlag.p);
+    i64 nNeeded = 0;
+    PRB_TRY(exclusive_scan(c, needFlag.p, needExcl.p, nBricks, &nNeeded));
+    if (getenv("PRB_DEBUG_BRICKS")) {
+        std::vector<unsigned char> hc((size_t)nBricks), hf((size_t)nBricks);
+        cudaMemcpyAsync(hc.data(), cert.p, (size_t)nBricks, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(hf.data(), full.p, (size_t)nBricks, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        long cc[3] = {0, 0, 0}, nf = 0;
+        for (int b = 0; b < nBricks; b++) { cc[hc[b]]++; nf += hf[b]; }
+        fprintf(stderr, "[bricks] rd=%d nr=%d bricks=%d cert0=%ld cert+=%ld cert-=%ld full=%ld needed=%lld\n", rd, nr, nBricks, cc[0], cc[1], cc[2], nf, (long long)nNeeded);
+    }
+    if (c.refineBoundCheck) {
+        // debug / test mode: evaluate everything and verify every certificate against the real values
+        PRB_LAUNCH(c, k_rv_brick_values, (unsigned)nBricks, 64, 0, G, (const int*)nullptr);
+        DBuf<unsigned char> sign;
+        DBuf<int> bad;
+        PRB_TRY(sign.alloc((size_t)nBricks, st)); PRB_TRY(bad.alloc(1, st));
+        PRB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+        PRB_LAUNCH(c, k_rv_brick_sign, grid_for(c, (i64)nBricks * 32, 256), 256, 0, val7p, nBricks, sign.p);
+        PRB_LAUNCH(c, k_rv_bound_check, grid_for(c, nBricks, 256), 256, 0, nBricks, cert.p, sign.p, bad.p);
+        int hb = 0;
+        PRB_CUDA(cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PRB_CUDA(cudaStreamSynchronize(st));
+        sign.release(); bad.release();
+        c.boundChecked += nBricks; c.boundEvaluated += nNeeded;
+        if (hb) { set_error("refinement: " + std::to_string(hb) + " bricks certified with the wrong sign (depth " + std::to_string(rd) + " pass)"); return PRB_ERR_STATE; }
+    } else if (nNeeded) {
+        PRB_TRY(needList.alloc((size_t)nNeeded, st));
+        PRB_LAUNCH(c, k_compact_ids, grid_for(c, nBricks, 256), 256, 0, needFlag.p, needExcl.p, nBricks, needList.p);
+        PRB_LAUNCH(c, k_rv_brick_values, (unsigned)nNeeded, 64, 0, G, (const int*)needList.p);
+    }
+    cert.release(); needFlag.release(); needExcl.release(); needList.release();
+    PRB_LAUNCH(c, k_rv_low_values, grid_for(c, (i64)nr * 3 * n1 * n1, 128, 16), 128, 0, G);
     PRB_TRY(cat.ensure((size_t)total, st));
     PRB_TRY(emask.ensure((size_t)total, st));
     PRB_TRY(c.wsVpre.ensure((size_t)total, st));
@@ -1240,11 +1399,8 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     PRB_TRY(brickV.alloc((size_t)nBricks, st)); PRB_TRY(brickT.alloc((size_t)nBricks, st));
     PRB_TRY(brickVBase.alloc((size_t)nBricks, st)); PRB_TRY(brickTBase.alloc((size_t)nBricks, st));
     PRB_TRY(bflag.alloc((size_t)nBricks, st)); PRB_TRY(bexcl.alloc((size_t)nBricks, st));
-    DBuf<unsigned char> bsign;
-    PRB_TRY(bsign.alloc((size_t)nBricks, st));
-    PRB_LAUNCH(c, k_rv_brick_sign, grid_for(c, (i64)nBricks * 32, 256), 256, 0, val7p, nBricks, bsign.p);
-    PRB_LAUNCH(c, k_rv_classify_brick, (unsigned)std::min(nBricks, c.smCount * 4), 512, 0, G, bsign.p, cat.p, emask.p, c.wsVpre.p, brickV.p, brickT.p, nBricks);
-    bsign.release();
+    PRB_LAUNCH(c, k_rv_classify_brick, (unsigned)std::min(nBricks, c.smCount * 4), 512, 0, G, full.p, cat.p, emask.p, c.wsVpre.p, brickV.p, brickT.p, nBricks);
+    full.release();
     PRB_LAUNCH(c, k_brick_flags, grid_for(c, nBricks, 256), 256, 0, brickV.p, brickT.p, nBricks, bflag.p);
     i64 totV = 0, totT = 0, nActive = 0;
     PRB_TRY(exclusive_scan(c, brickV.p, brickVBase.p, nBricks, nullptr));
@@ -1433,20 +1589,6 @@ int stage_extract(Context& c) {
             firstOfDepth[D + 1] = (int)nSub;
         }
         const int finerDepth = 3;    // main.cu:3886
-        if (mg && !c.mgVal7) {
-            // one arena buffer for the values of the largest implicit pass (same size on every rank)
-            i64 maxTotal = 0;
-            for (int d = 1; d < D; d++) {
-                if (D - d < 3 || D - d > 10) continue;
-                i64 nr = (d < finerDepth) ? (firstOfDepth[d + 1] > firstOfDepth[d] ? 1 : 0) : (firstOfDepth[d + 1] - firstOfDepth[d]);
-                maxTotal = std::max(maxTotal, nr << (3 * (D - d)));
-            }
-            if (maxTotal > 0) {
-                c.mgVal7 = c.mg.alloc<float>((size_t)maxTotal, &c.mgVal7Off);
-                if (!c.mgVal7) { set_error("multi-GPU arena too small for the refinement pass values (4 bytes per virtual cell of the largest pass)"); return PRB_ERR_NOMEM; }
-                c.mgVal7Cap = (size_t)maxTotal;
-            }
-        }
         for (int d = 1; d < finerDepth && d < D; d++)                      // coarse roots: one pass each (main.cu:3887-4202)
             for (int q = firstOfDepth[d]; q < firstOfDepth[d + 1]; q++) PRB_TRY(refine_pass(c, subIds.p + q, 1, d, true, rootMap, outs));
         for (int d = finerDepth; d < D; d++)                               // batched per depth (main.cu:4211-4561)

@@ -117,6 +117,14 @@ def test_small_configs_free_and_forced(name, oracle_cls):
     pr.run()
     compare_free(pr, o, D)
     compare_forced(pr, o, D)
+    # refinement passes: every certified brick sign is verified against the evaluated values
+    # (prb_run fails if one is wrong) and the mesh does not depend on the skipping
+    v, t = pr.mesh()
+    pr.set_option("refine_bound_check", 1)
+    pr.set_points(p, n)
+    pr.run()
+    v2, t2 = pr.mesh()
+    assert np.array_equal(t, t2) and np.array_equal(v, v2)
     pr.close()
 
 
@@ -249,6 +257,13 @@ def test_full_size_properties(config):
     assert pr.get("passes", "<i4").tolist() == pr.get("passes", "<i4").tolist()
     assert np.array_equal(t, t3) and np.array_equal(v, v3)
     pr.set_option("refine_implicit", 1)
+    # certified brick signs (k_rv_brick_bound) checked against a full evaluation of every brick
+    pr.set_option("refine_bound_check", 1)
+    pr.set_points(p, n)
+    pr.run()
+    v4, t4 = pr.mesh()
+    assert np.array_equal(t, t4) and np.array_equal(v, v4)
+    pr.set_option("refine_bound_check", 0)
     # the reconstructed surface interpolates the samples: vertices lie near the sampled shape
     c, s = np.array(st["center"], np.float32), np.float32(st["scale"])
     w = v * s + c
