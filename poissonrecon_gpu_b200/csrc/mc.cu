@@ -945,7 +945,7 @@ __device__ float rv_eval_slow(const RGeom& G, int r, int cx, int cy, int cz, int
     return __fsub_rn(val, G.iso);
 }
 // grid points on the lower faces of every root: evaluated here when this root owns them
-__global__ void __launch_bounds__(128) k_rv_low_values(RGeom G) {
+__global__ void __launch_bounds__(128) k_rv_low_values(RGeom G, const unsigned char* __restrict__ needed /* per brick (k_rv_brick_needed needLow), or null: all */) {
     const int n1 = G.n + 1;
     const i64 total = (i64)G.nr * 3 * n1 * n1;
     for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
@@ -955,6 +955,8 @@ __global__ void __launch_bounds__(128) k_rv_low_values(RGeom G) {
         int r2, ox, oy, oz, jb;
         rv_point_owner(G, r, gx, gy, gz, r2, ox, oy, oz, jb);
         if (r2 != r || jb == 7) continue;
+        // only the bricks that are staged for classification read grid values: the point lies in the closed box of its owner's brick
+        if (needed && !needed[(int)(((i64)r * G.per + rv_morton(ox, oy, oz)) >> 9)]) continue;
         G.low[t] = rv_eval_slow(G, r, ox, oy, oz, jb);
     }
 }
@@ -1130,7 +1132,9 @@ __global__ void __launch_bounds__(256) k_rv_brick_full(RGeom G, int nBricks, con
     }
 }
 // brick b has to be evaluated when a brick that is classified reads it: itself or one of the 7 bricks above it
-__global__ void __launch_bounds__(256) k_rv_brick_needed(RGeom G, int nBricks, const unsigned char* __restrict__ full, int* __restrict__ needed) {
+// (needLow: the lower-face grid points owned by a cell of b are read by any classified brick that touches the
+// point, which can lie on either side of b in every axis: the whole 3x3x3 neighbourhood counts)
+__global__ void __launch_bounds__(256) k_rv_brick_needed(RGeom G, int nBricks, const unsigned char* __restrict__ full, int* __restrict__ needed, unsigned char* __restrict__ needLow) {
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nBricks; b += gridDim.x * blockDim.x) {
         const i64 cell0 = (i64)b * 512;
         const int r = (int)(cell0 / G.per);
@@ -1142,6 +1146,13 @@ __global__ void __launch_bounds__(256) k_rv_brick_needed(RGeom G, int nBricks, c
             if (dst >= 0) need = full[dst] != 0;
         }
         needed[b] = need ? 1 : 0;
+        bool low = need;
+        if (!low && (bx == 0 || by == 0 || bz == 0))
+            for (int q = 0; q < 27 && !low; q++) {
+                const int dst = rv_brick_of(G, r, bx + 8 * (q / 9 - 1), by + 8 * ((q / 3) % 3 - 1), bz + 8 * (q % 3 - 1));
+                if (dst >= 0) low = full[dst] != 0;
+            }
+        needLow[b] = low ? 1 : 0;
     }
 }
 __global__ void __launch_bounds__(256) k_rv_bound_check(int nBricks, const unsigned char* __restrict__ cert, const unsigned char* __restrict__ sign, int* __restrict__ bad) {
@@ -1352,13 +1363,13 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     const int nBricks = (int)(total / 512);
     // certified signs -> bricks to classify -> bricks to evaluate (every rank evaluates the same short list:
     // it is a few per cent of the pass, less than a rank's share of all bricks plus the peer pulls would be)
-    DBuf<unsigned char> cert, full;
+    DBuf<unsigned char> cert, full, needLow;
     DBuf<int> needFlag, needExcl, needList;
-    PRB_TRY(cert.alloc((size_t)nBricks, st)); PRB_TRY(full.alloc((size_t)nBricks, st));
+    PRB_TRY(cert.alloc((size_t)nBricks, st)); PRB_TRY(full.alloc((size_t)nBricks, st)); PRB_TRY(needLow.alloc((size_t)nBricks, st));
     PRB_TRY(needFlag.alloc((size_t)nBricks, st)); PRB_TRY(needExcl.alloc((size_t)nBricks, st));
     PRB_LAUNCH(c, k_rv_brick_bound, grid_for(c, (i64)nBricks * 32, 256, 8), 256, 0, G, nBricks, cert.p);
     PRB_LAUNCH(c, k_rv_brick_full, grid_for(c, nBricks, 256), 256, 0, G, nBricks, cert.p, full.p);
-    PRB_LAUNCH(c, k_rv_brick_needed, grid_for(c, nBricks, 256), 256, 0, G, nBricks, full.p, needFlag.p);
+    PRB_LAUNCH(c, k_rv_brick_needed, grid_for(c, nBricks, 256), 256, 0, G, nBricks, full.p, needFlag.p, needLow.p);
     i64 nNeeded = 0;
     PRB_TRY(exclusive_scan(c, needFlag.p, needExcl.p, nBricks, &nNeeded));
     if (getenv("PRB_DEBUG_BRICKS")) {
@@ -1390,8 +1401,8 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
         PRB_LAUNCH(c, k_compact_ids, grid_for(c, nBricks, 256), 256, 0, needFlag.p, needExcl.p, nBricks, needList.p);
         PRB_LAUNCH(c, k_rv_brick_values, (unsigned)nNeeded, 64, 0, G, (const int*)needList.p);
     }
-    cert.release(); needFlag.release(); needExcl.release(); needList.release();
-    PRB_LAUNCH(c, k_rv_low_values, grid_for(c, (i64)nr * 3 * n1 * n1, 128, 16), 128, 0, G);
+    PRB_LAUNCH(c, k_rv_low_values, grid_for(c, (i64)nr * 3 * n1 * n1, 128, 16), 128, 0, G, c.refineBoundCheck ? (const unsigned char*)nullptr : (const unsigned char*)needLow.p);
+    cert.release(); needFlag.release(); needExcl.release(); needList.release(); needLow.release();
     PRB_TRY(cat.ensure((size_t)total, st));
     PRB_TRY(emask.ensure((size_t)total, st));
     PRB_TRY(c.wsVpre.ensure((size_t)total, st));
