@@ -186,7 +186,7 @@ struct Context {
     BSplineTables tab;
     DBuf<float> dMaxDepthFn, dBaseFn, dDfT, dStencil;
     DBuf<int> dDfOffset;
-    DBuf<float> dBvAnc, dBvOwn, dBvCell;    // base-function values at cell corners per (depth, ancestor level) (mc.cu k_build_bv)
+    DBuf<float> dBvAnc, dBvOwn, dBvCell, dBvGrid;    // base-function values at cell corners per (depth, ancestor level) (mc.cu k_build_bv)
     int bvAncOff[kMaxDepth + 1] = {0}, bvOwnOff[kMaxDepth + 1] = {0};
     // ---- fields
     DBuf<float> V;                 // [M_D][3]

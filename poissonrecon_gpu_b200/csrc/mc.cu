@@ -237,10 +237,26 @@ struct BvTables {
     const float4* anc;            // [d0][l < d0][g < 2^(d0-1)][pc < 3] -> (k = 0, 1, 2, unused)
     const float4* own;            // [d0][g][pc] -> cube coordinate 0..3
     const float4* cellD;          // [l <= D][gc < 2^D] -> (k = 0, 1, 2, unused): level-l functions around depth-D cell gc at its UPPER corner (gc+1) w
+    const float4* gridLo;         // [l <= D][P <= 2^D] -> level-l functions around node P >> (D-l), at the depth-D grid point P w
     int ancOff[kMaxDepth + 1];    // first float4 of depth d0
     int ownOff[kMaxDepth + 1];
 };
-__global__ void __launch_bounds__(256) k_build_bv(int D, const float* __restrict__ baseFn, BvTables B, float4* __restrict__ anc, float4* __restrict__ own, float4* __restrict__ cellD) {
+__global__ void __launch_bounds__(256) k_build_bv(int D, const float* __restrict__ baseFn, BvTables B, float4* __restrict__ anc, float4* __restrict__ own, float4* __restrict__ cellD,
+                                                  float4* __restrict__ gridLo) {
+    {
+        const float w = 1.0f / (float)(1 << D);
+        const int np = (1 << D) + 1, n = (D + 1) * np;
+        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+            const int l = t / np, P = t - l * np, nn = 1 << l;
+            const float pos = (float)P * w;
+            float v[3];
+            for (int k = 0; k < 3; k++) {
+                const int ao = (P >> (D - l)) + k - 1;
+                v[k] = (ao >= 0 && ao < nn) ? base_value(baseFn, nn - 1 + ao, pos) : 0.f;
+            }
+            gridLo[t] = make_float4(v[0], v[1], v[2], 0.f);
+        }
+    }
     {
         const float w = 1.0f / (float)(1 << D);
         const int n = (D + 1) << D;
@@ -282,6 +298,40 @@ __global__ void __launch_bounds__(256) k_build_bv(int D, const float* __restrict
                 own[B.ownOff[d0] + u] = make_float4(v[0], v[1], v[2], v[3]);
             }
         }
+    }
+}
+
+// base-function values of the three level-l functions around node A at the depth-D grid point P (per axis).
+// A point in the closed cell of A comes from a table: the lower-corner one when A == P >> (D-l), the upper-corner
+// one of cell P-1 when the point is the upper end of A's cell.  Any other point (the reference's down-walk
+// follows childrenVertexKind, which for half of the corners is NOT the child that touches the corner) is
+// evaluated in place.  Same base_value() results either way.
+__device__ __forceinline__ float4 bv_grid(const float4* __restrict__ gridLo, const float4* __restrict__ cellD, const float* __restrict__ baseFn, int D, int l, int P, int A) {
+    const int sh = D - l;
+    if ((P >> sh) == A) return gridLo[l * ((1 << D) + 1) + P];
+    if (P >= 1 && ((P - 1) >> sh) == A) return cellD[(l << D) + P - 1];
+    const int nn = 1 << l;
+    const float pos = (float)P * (1.0f / (float)(1 << D));
+    float v[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int ao = A + k - 1;
+        v[k] = (ao >= 0 && ao < nn) ? base_value(baseFn, nn - 1 + ao, pos) : 0.f;
+    }
+    return make_float4(v[0], v[1], v[2], 0.f);
+}
+// accumulate_level for a point on the depth-D grid: table look-ups instead of nine polynomial evaluations
+__device__ __forceinline__ void accumulate_level_grid(float& val, const int* __restrict__ nb, ushort4 o, const float* __restrict__ x,
+                                                      const float4* __restrict__ gridLo, const float4* __restrict__ cellD, const float* __restrict__ baseFn, int D,
+                                                      const int P[3]) {
+    const int d = o.w;
+    const float4 bx = bv_grid(gridLo, cellD, baseFn, D, d, P[0], (int)o.x), by = bv_grid(gridLo, cellD, baseFn, D, d, P[1], (int)o.y),
+                 bz = bv_grid(gridLo, cellD, baseFn, D, d, P[2], (int)o.z);
+    const float vx[3] = {bx.x, bx.y, bx.z}, vy[3] = {by.x, by.y, by.z}, vz[3] = {bz.x, bz.y, bz.z};
+#pragma unroll
+    for (int j = 0; j < 27; j++) {
+        int q = nb[j];
+        if (q >= 0) val = __fmaf_rn(__fmul_rn(__fmul_rn(x[q], vx[j / 9]), vy[(j / 3) % 3]), vz[j % 3], val);
     }
 }
 
@@ -400,7 +450,7 @@ __global__ void __launch_bounds__(kVsWarps * 32) k_vertex_values_stream(Topo T, 
                             int c0 = child0[now];
                             if (c0 < 0) break;
                             now = c0 + ex;
-                            accumulate_level(val, T.nbr + 27 * (i64)now, offs[now], x, baseFn, pos);
+                            accumulate_level(val, T.nbr + 27 * (i64)now, offs[now], x, baseFn, pos);      // (the down-walk leaves the corner for half of the corners: no table)
                         }
                     }
                     vval[8 * (i64)owner + jo] = __fsub_rn(val, iso);
@@ -619,9 +669,9 @@ __global__ void __launch_bounds__(256) k_vmask(VTree V, i64 total, const int* __
 __global__ void __launch_bounds__(128) k_vvertex_values(VTree V, Topo T, const int* __restrict__ vneigh, const unsigned* __restrict__ vmask,
                                                         const ushort4* __restrict__ voffs,
                                                         const int* __restrict__ neighs, const int* __restrict__ parent, const ushort4* __restrict__ offs,
-                                                        const float* __restrict__ x, const float* __restrict__ baseFn, float iso, float* __restrict__ sval) {
+                                                        const float* __restrict__ x, const float4* __restrict__ gridLo, const float4* __restrict__ cellD,
+                                                        const float* __restrict__ baseFn, float iso, float* __restrict__ sval) {
     const int perD = vt_per(V, V.D);
-    const float w = 1.0f / (float)(1 << V.D);
     for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < T.nCells; l += gridDim.x * blockDim.x) {
         const int id = T.cellBase + l;
         const ushort4 o = voffs[l];
@@ -629,7 +679,7 @@ __global__ void __launch_bounds__(128) k_vvertex_values(VTree V, Topo T, const i
         for (int j = 0; j < 8; j++) {
             int m;
             if (corner_owner(T, id, j, m) != id) continue;
-            float pos[3] = {(float)((int)o.x + (j & 1)) * w, (float)((int)o.y + ((j >> 1) & 1)) * w, (float)((int)o.z + ((j >> 2) & 1)) * w};
+            const int P[3] = {(int)o.x + (j & 1), (int)o.y + ((j >> 1) & 1), (int)o.z + ((j >> 2) & 1)};     // the corner on the depth-D grid
             float val = 0.f;
             int loc = l - r * perD;
             for (int d = V.D; d >= V.rd; --d) {           // virtual levels D .. rd
@@ -639,17 +689,10 @@ __global__ void __launch_bounds__(128) k_vvertex_values(VTree V, Topo T, const i
                 unsigned mk = vmask[v];
                 if (!mk) continue;
                 const int* nb = vneigh + 27 * (i64)v;
-                int od = V.D - d;
-                int nn = 1 << d, f0 = nn - 1;
-                int ox = (int)o.x >> od, oy = (int)o.y >> od, oz = (int)o.z >> od;
-                float vx[3], vy[3], vz[3];
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    int ax = ox + k - 1, ay = oy + k - 1, az = oz + k - 1;
-                    vx[k] = (ax >= 0 && ax < nn) ? base_value(baseFn, f0 + ax, pos[0]) : 0.f;
-                    vy[k] = (ay >= 0 && ay < nn) ? base_value(baseFn, f0 + ay, pos[1]) : 0.f;
-                    vz[k] = (az >= 0 && az < nn) ? base_value(baseFn, f0 + az, pos[2]) : 0.f;
-                }
+                const int od = V.D - d;
+                const float4 bx = bv_grid(gridLo, cellD, baseFn, V.D, d, P[0], (int)o.x >> od), by = bv_grid(gridLo, cellD, baseFn, V.D, d, P[1], (int)o.y >> od),
+                             bz = bv_grid(gridLo, cellD, baseFn, V.D, d, P[2], (int)o.z >> od);
+                const float vx[3] = {bx.x, bx.y, bx.z}, vy[3] = {by.x, by.y, by.z}, vz[3] = {bz.x, bz.y, bz.z};
 #pragma unroll
                 for (int jj = 0; jj < 27; jj++) {
                     if (!(mk & (1u << jj))) continue;
@@ -660,7 +703,7 @@ __global__ void __launch_bounds__(128) k_vvertex_values(VTree V, Topo T, const i
             }
             int now = parent[V.roots[r]];                 // real ancestors
             while (now != -1) {
-                accumulate_level(val, neighs + 27 * (i64)now, offs[now], x, baseFn, pos);
+                accumulate_level_grid(val, neighs + 27 * (i64)now, offs[now], x, gridLo, cellD, baseFn, V.D, P);
                 now = parent[now];
             }
             sval[8 * (i64)l + j] = __fsub_rn(val, iso);
@@ -1482,7 +1525,8 @@ static int refine_pass(Context& c, const int* dRoots, int nr, int rd, bool singl
     DBuf<unsigned> vmask;
     PRB_TRY(vmask.alloc((size_t)total, st));
     PRB_LAUNCH(c, k_vmask, grid_for(c, total, 256), 256, 0, V, total, vneigh.p, vmask.p);
-    PRB_LAUNCH(c, k_vvertex_values, grid_for(c, nD, 128, 16), 128, 0, V, T, vneigh.p, vmask.p, voffs.p, c.neighs.p, c.parent.p, c.offs.p, c.xv, c.dBaseFn.p, c.iso, sval.p);
+    PRB_TRY(ensure_bv_tables(c));
+    PRB_LAUNCH(c, k_vvertex_values, grid_for(c, nD, 128, 16), 128, 0, V, T, vneigh.p, vmask.p, voffs.p, c.neighs.p, c.parent.p, c.offs.p, c.xv, (const float4*)c.dBvGrid.p, (const float4*)c.dBvCell.p, c.dBaseFn.p, c.iso, sval.p);
     outs.emplace_back();
     PassOut& po = outs.back();
     PRB_TRY(run_mc_on_cells(c, T, sval.p, T.cellBase, voffs.p, false, nullptr, po));
@@ -1511,10 +1555,11 @@ static int ensure_bv_tables(Context& c) {
     PRB_TRY(c.dBvAnc.alloc(4 * na, c.stream));
     PRB_TRY(c.dBvOwn.alloc(4 * no, c.stream));
     PRB_TRY(c.dBvCell.alloc(4 * ((size_t)(D + 1) << D), c.stream));
+    PRB_TRY(c.dBvGrid.alloc(4 * (size_t)(D + 1) * (((size_t)1 << D) + 1), c.stream));
     BvTables B;
-    B.anc = (const float4*)c.dBvAnc.p; B.own = (const float4*)c.dBvOwn.p; B.cellD = (const float4*)c.dBvCell.p;
+    B.anc = (const float4*)c.dBvAnc.p; B.own = (const float4*)c.dBvOwn.p; B.cellD = (const float4*)c.dBvCell.p; B.gridLo = (const float4*)c.dBvGrid.p;
     for (int d = 0; d <= kMaxDepth; d++) { B.ancOff[d] = c.bvAncOff[d]; B.ownOff[d] = c.bvOwnOff[d]; }
-    PRB_LAUNCH(c, k_build_bv, c.smCount * 4, 256, 0, D, c.dBaseFn.p, B, (float4*)c.dBvAnc.p, (float4*)c.dBvOwn.p, (float4*)c.dBvCell.p);
+    PRB_LAUNCH(c, k_build_bv, c.smCount * 4, 256, 0, D, c.dBaseFn.p, B, (float4*)c.dBvAnc.p, (float4*)c.dBvOwn.p, (float4*)c.dBvCell.p, (float4*)c.dBvGrid.p);
     return PRB_OK;
 }
 
@@ -1544,7 +1589,7 @@ int stage_extract(Context& c) {
         if (g1 > g0) {
             PRB_TRY(ensure_bv_tables(c));
             BvTables B;
-            B.anc = (const float4*)c.dBvAnc.p; B.own = (const float4*)c.dBvOwn.p; B.cellD = (const float4*)c.dBvCell.p;
+            B.anc = (const float4*)c.dBvAnc.p; B.own = (const float4*)c.dBvOwn.p; B.cellD = (const float4*)c.dBvCell.p; B.gridLo = (const float4*)c.dBvGrid.p;
             for (int d = 0; d <= kMaxDepth; d++) { B.ancOff[d] = c.bvAncOff[d]; B.ownOff[d] = c.bvOwnOff[d]; }
             const i64 nChunks = ((i64)(g1 - g0) + kVsChunk - 1) / kVsChunk;
             PRB_LAUNCH(c, k_vertex_values_stream, grid_for(c, nChunks * 32, kVsWarps * 32, 8), kVsWarps * 32, 0, R, g0, g1 - g0, D, c.parent.p, c.child0.p, c.offs.p,

@@ -83,7 +83,7 @@ void prb_destroy(prb_context* h) {
     cudaSetDevice(c.device);
     release_all(c);
     c.wsVal7.release(); c.wsLow.release(); c.wsCat.release(); c.wsNtri.release(); c.wsEmask.release(); c.wsVpre.release(); c.wsVbase.release(); c.wsTbase.release();
-    c.dBvAnc.release(); c.dBvOwn.release(); c.dBvCell.release(); c.dMaxDepthFn.release(); c.dBaseFn.release(); c.dDfT.release(); c.dDfOffset.release(); c.dStencil.release();
+    c.dBvAnc.release(); c.dBvOwn.release(); c.dBvCell.release(); c.dBvGrid.release(); c.dMaxDepthFn.release(); c.dBaseFn.release(); c.dDfT.release(); c.dDfOffset.release(); c.dStencil.release();
     cudaStreamSynchronize(c.stream);
     arena_unregister(c.stream);
     for (int r = 0; r < kMaxRanks; r++)
