@@ -1053,15 +1053,23 @@ __device__ __forceinline__ void rv_cell_values(const RGeom& G, int r, int cx, in
 // roundings).  A brick is certified (1: all > 0, 2: all < 0) only when every coefficient clears iso
 // by 2E; bricks with contributions from levels finer than D-3 are never certified.  Certified
 // bricks are not evaluated unless a brick that has to be classified reads them.
-__global__ void __launch_bounds__(256) k_rv_brick_bound(RGeom G, int nBricks, unsigned char* __restrict__ cert) {
+// S = log2 of the box edge in cells: 3 = one brick; 5 = a 4x4x4 block of bricks (64 consecutive bricks in Morton
+// order), certified as a whole first -- far from the surface that settles 64 bricks with one test, and the brick
+// pass (S = 3, `coarse` = the S = 5 certificates) only looks at the rest.  The argument is the same with D-S in
+// place of D-3: no knots of levels <= D-S inside the box, and no contribution from finer levels.
+__global__ void __launch_bounds__(256) k_rv_brick_bound(RGeom G, int S, int nBricks, const unsigned char* __restrict__ coarse, unsigned char* __restrict__ cert) {
     __shared__ double sBeta[8][9][3];        // [warp][axis*3 + k][Bernstein index]
     __shared__ double sErr[8][9], sMax[8][9];
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    const int L = G.D - 3;
+    const int L = G.D - S;
     const double w = 1.0 / (double)(1 << G.D);
     const int ci = lane / 9, cj = (lane / 3) % 3, ck = lane % 3;
     for (int b = blockIdx.x * 8 + wp; b < nBricks; b += gridDim.x * 8) {
-        const i64 cell0 = (i64)b * 512;
+        if (coarse) {
+            const unsigned char cb = coarse[b >> 6];
+            if (cb) { if (lane == 0) cert[b] = cb; continue; }
+        }
+        const i64 cell0 = (i64)b << (3 * S);
         const int r = (int)(cell0 / G.per);
         const unsigned l0 = (unsigned)(cell0 - (i64)r * G.per);
         const ushort4 ro = G.offs[G.roots[r]];
@@ -1091,7 +1099,7 @@ __global__ void __launch_bounds__(256) k_rv_brick_bound(RGeom G, int nBricks, un
                 const int a = lane / 3, k = lane % 3;
                 const int nn = 1 << lvl, ao = (g[a] >> (G.D - lvl)) + k - 1;
                 double C0 = 0.0, C1 = 0.0, C2 = 0.0, A = 0.0;
-                const double t0 = (double)g[a] * w, t1 = (double)(g[a] + 8) * w, tm = 0.5 * (t0 + t1);
+                const double t0 = (double)g[a] * w, t1 = (double)(g[a] + (1 << S)) * w, tm = 0.5 * (t0 + t1);
                 if (ao >= 0 && ao < nn) {
                     const float* f = G.baseFn + 20 * (i64)(nn - 1 + ao);
                     bool on = true;
@@ -1410,7 +1418,16 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     DBuf<int> needFlag, needExcl, needList;
     PRB_TRY(cert.alloc((size_t)nBricks, st)); PRB_TRY(full.alloc((size_t)nBricks, st)); PRB_TRY(needLow.alloc((size_t)nBricks, st));
     PRB_TRY(needFlag.alloc((size_t)nBricks, st)); PRB_TRY(needExcl.alloc((size_t)nBricks, st));
-    PRB_LAUNCH(c, k_rv_brick_bound, grid_for(c, (i64)nBricks * 32, 256, 8), 256, 0, G, nBricks, cert.p);
+    if (lv >= 5) {
+        DBuf<unsigned char> superCert;
+        const int nSuper = nBricks >> 6;
+        PRB_TRY(superCert.alloc((size_t)nSuper, st));
+        PRB_LAUNCH(c, k_rv_brick_bound, grid_for(c, (i64)nSuper * 32, 256, 8), 256, 0, G, 5, nSuper, (const unsigned char*)nullptr, superCert.p);
+        PRB_LAUNCH(c, k_rv_brick_bound, grid_for(c, (i64)nBricks * 32, 256, 8), 256, 0, G, 3, nBricks, (const unsigned char*)superCert.p, cert.p);
+        superCert.release();
+    } else {
+        PRB_LAUNCH(c, k_rv_brick_bound, grid_for(c, (i64)nBricks * 32, 256, 8), 256, 0, G, 3, nBricks, (const unsigned char*)nullptr, cert.p);
+    }
     PRB_LAUNCH(c, k_rv_brick_full, grid_for(c, nBricks, 256), 256, 0, G, nBricks, cert.p, full.p);
     PRB_LAUNCH(c, k_rv_brick_needed, grid_for(c, nBricks, 256), 256, 0, G, nBricks, full.p, needFlag.p, needLow.p);
     i64 nNeeded = 0;
