@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(256) k_rv_roots(int nr, int rd, int M, const i
 // 1.25 instead of 3 instructions per term and cell, with every value computed exactly as in the
 // one-thread-per-cell formulation (same operations in the same order per cell).  Base-function
 // values come from the per-context table BvTables::cellD.
-__device__ __noinline__ float rv_fine_levels(const RGeom& G, const int* __restrict__ sIds, unsigned l, int L, int gx, int gy, int gz) {
+__device__ __noinline__ float rv_fine_levels(const RGeom& G, const int* __restrict__ sIds, const unsigned char* __restrict__ sLut, unsigned l, int L, int gx, int gy, int gz) {
     // levels D, D-1, D-2 below the brick level: per-cell neighbour ids through the real tree
     int ids[3][27];
 #pragma unroll 1
@@ -798,8 +798,7 @@ __device__ __noinline__ float rv_fine_levels(const RGeom& G, const int* __restri
         int c = (int)((l >> (3 * (2 - s))) & 7u);
 #pragma unroll 1
         for (int j = 0; j < 27; j++) {
-            int pj, cc;
-            lut_parent_child(c, j, pj, cc);
+            const int e = sLut[27 * c + j], pj = e & 31, cc = e >> 5;      // lut_parent_child(c, j)
             int p = s == 0 ? sIds[pj] : ids[s - 1][pj];
             int nxt = -1;
             if (p >= 0) { int c0 = G.child0[p]; if (c0 >= 0) nxt = c0 + cc; }
@@ -826,7 +825,13 @@ __global__ void __launch_bounds__(64) k_rv_brick_values(RGeom G, const int* __re
     __shared__ int sIds[27];
     __shared__ int sAny[kMaxDepth + 1];
     __shared__ int sNeedFine;
+    __shared__ unsigned char sLut[216];      // (c, j) -> pj | cc << 5
     const int tid = threadIdx.x;
+    for (int t = tid; t < 216; t += 64) {
+        int pj, cc;
+        lut_parent_child(t / 27, t % 27, pj, cc);
+        sLut[t] = (unsigned char)(pj | (cc << 5));
+    }
     const i64 cell0 = (i64)(list ? list[blockIdx.x] : (int)blockIdx.x) * 512;
     const int r = (int)(cell0 / G.per);
     const unsigned l0 = (unsigned)(cell0 - (i64)r * G.per);
@@ -867,7 +872,7 @@ __global__ void __launch_bounds__(64) k_rv_brick_values(RGeom G, const int* __re
     if (sNeedFine) {
 #pragma unroll 1
         for (int cz = 0; cz < 8; cz++) {
-            float v = rv_fine_levels(G, sIds, lxy + spread3((unsigned)cz), L, gx, gy, bz + cz);
+            float v = rv_fine_levels(G, sIds, sLut, lxy + spread3((unsigned)cz), L, gx, gy, bz + cz);
 #pragma unroll
             for (int k = 0; k < 8; k++) if (k == cz) val[k] = v;
         }
