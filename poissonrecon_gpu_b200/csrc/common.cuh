@@ -221,8 +221,7 @@ struct Context {
     float* mgX = nullptr;                      // solution inside the arena
     size_t mgPOff = 0, mgXOff = 0;
     float* mgVval = nullptr;                   // corner values [M][8] inside the arena
-    float* mgVal7 = nullptr;                   // refinement pass values inside the arena (capacity mgVal7Cap floats)
-    size_t mgVvalOff = 0, mgVal7Off = 0, mgVal7Cap = 0;
+    size_t mgVvalOff = 0;
     float* vvalPtr = nullptr;                  // where the corner values of the current run live (vval.p or mgVval)
 };
 

@@ -114,8 +114,7 @@ int prb_set_points(prb_context* h, const float* xyz, const float* normals, int64
     PRB_CUDA(cudaSetDevice(c.device));
     release_all(c);
     c.mg.reset_allocs();
-    c.mgP = c.mgX = c.mgVval = c.mgVal7 = nullptr;
-    c.mgVal7Cap = 0;
+    c.mgP = c.mgX = c.mgVval = nullptr;
     c.vvalPtr = nullptr;
     c.N = n;
     c.launches = 0;
