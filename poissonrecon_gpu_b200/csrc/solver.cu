@@ -26,7 +26,12 @@
 //     bank-conflict free;
 //   * the row sum runs over the neighbour slots in order j = 0..26 with FMAs, exactly the
 //     reference's CSR order (absent neighbours contribute an exact +0), so A*p is bit-identical;
-//     dots are float products accumulated in double (CG_CUDA.cuh:217-220); alpha, beta are float.
+//     dots are float products accumulated in double (CG_CUDA.cuh:217-220); alpha, beta are float;
+//   * p is double buffered, so x += alpha_{k-1} p_{k-1} is deferred by one iteration and rides along
+//     with the SpMV of iteration k (one float4 batch per step, loaded before and finished after the
+//     step's FMAs); the two streaming phases that remain (p_k = r + beta p_{k-1};  r -= alpha Ap, r.r)
+//     read their inputs through a per-thread cp.async ring in the idle SpMV buffers; every phase sweeps
+//     memory in the direction opposite to the previous one (L2 reuse across the grid syncs).
 // Algorithmic bytes per row per iteration: 57.5 B
 //   (p=r+beta*p: 12, SpMV: 13.5 + 4 + 4, x/r update: 24).
 #include "common.cuh"
@@ -46,7 +51,6 @@ constexpr int kUnitBz = 10, kUnitBy = 36, kCubeUnits = 145, kCubeFloats = 4 * kC
 constexpr int kWarpBufFloats = 4 * kCubeFloats;          // 4 cubes per warp-step
 constexpr int kRounds = 12;                               // 96 half-blocks / 8 lanes
 constexpr int kPrefetchSteps = 2;                         // L2 prefetch distance of the SpMV table, in steps beyond the register pipeline
-constexpr int kStreamUnroll = 4, kStreamUnrollB = 4;     // independent 16-byte loads per array per thread in the streaming phases
 
 // Staging plan of a quarter-warp: in round r (12 rounds x 8 lanes = the 96 half-blocks) lane li
 // copies one 16-byte half-block.  The cost of the gather is the number of distinct 128-byte
