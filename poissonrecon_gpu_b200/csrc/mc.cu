@@ -1437,15 +1437,6 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     PRB_LAUNCH(c, k_rv_brick_needed, grid_for(c, nBricks, 256), 256, 0, G, nBricks, full.p, needFlag.p, needLow.p);
     i64 nNeeded = 0;
     PRB_TRY(exclusive_scan(c, needFlag.p, needExcl.p, nBricks, &nNeeded));
-    if (getenv("PRB_DEBUG_BRICKS")) {
-        std::vector<unsigned char> hc((size_t)nBricks), hf((size_t)nBricks);
-        cudaMemcpyAsync(hc.data(), cert.p, (size_t)nBricks, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(hf.data(), full.p, (size_t)nBricks, cudaMemcpyDeviceToHost, st);
-        cudaStreamSynchronize(st);
-        long cc[3] = {0, 0, 0}, nf = 0;
-        for (int b = 0; b < nBricks; b++) { cc[hc[b]]++; nf += hf[b]; }
-        fprintf(stderr, "[bricks] rd=%d nr=%d bricks=%d cert0=%ld cert+=%ld cert-=%ld full=%ld needed=%lld\n", rd, nr, nBricks, cc[0], cc[1], cc[2], nf, (long long)nNeeded);
-    }
     if (c.refineBoundCheck) {
         // debug / test mode: evaluate everything and verify every certificate against the real values
         PRB_LAUNCH(c, k_rv_brick_values, (unsigned)nBricks, 64, 0, G, (const int*)nullptr);
