@@ -10,9 +10,9 @@ metric is quoted on; it fits one B200).  `value` is measured with the samples al
 in HBM (device pointers into prb_set_points), `e2e` with pinned HOST buffers in and the mesh
 copied back to the host, both through the C ABI (include/prb.h) and both timed with CUDA events
 on the library's own stream.  N > 1: one process per GPU reconstructing the SAME cloud together
-(strong scaling): the octree is replicated, divergence / CG / iso value / corner values /
-refinement values are sharded by Morton range and exchanged over NVLink through peer-mapped
-arenas (DESIGN.md "multi-GPU"); `--replicas` instead runs one independent cloud per GPU.  The CG kernel's roofline line uses the algorithmic 57.5 B per row
+(strong scaling): the octree is replicated, divergence / CG / iso value / corner values are
+sharded by Morton range and exchanged over NVLink through peer-mapped arenas (DESIGN.md
+"multi-GPU"); `--replicas` instead runs one independent cloud per GPU.  The CG kernel's roofline line uses the algorithmic 57.5 B per row
 per iteration of SURVEY.md 8(d) and the CUDA-event duration of the solve stage.
 
 `--impl reference`: the reference has no CPU path and its CUDA build stops at depth 9
@@ -316,7 +316,7 @@ def main():
         "value": value, "unit": "Mpoints/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_total / a.steps,
         "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": a.workload, "points": N if (sharded or world == 1) else N * world, "depth": D, "nodes": st["n_nodes"], "mesh_vertices": nv, "mesh_triangles": nt,
-                   "cg_iters": st["cg_iters"][: D + 1], "parallelism": ("1 GPU" if world == 1 else (f"morton-range shards x{world}: replicated octree, sharded divergence/CG/iso/corner+refinement values, NVLink peer-arena exchange"
+                   "cg_iters": st["cg_iters"][: D + 1], "parallelism": ("1 GPU" if world == 1 else (f"morton-range shards x{world}: replicated octree, sharded divergence/CG/iso/corner values, NVLink peer-arena exchange"
                                                                 if sharded else f"replicas x{world} (one cloud per GPU, no collective)")),
                    "l2": "no flush: every step streams > 3 GB of samples, node slabs and vectors, far beyond the 126 MB L2"},
         "e2e": {"value": e2e, "unit": "Mpoints/s", "h2d_bytes_per_step": 24 * N * world, "d2h_bytes_per_step": 12 * (nv + nt) * world, "ms_per_step": ms_e2e / a.steps,
