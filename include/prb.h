@@ -96,7 +96,7 @@ int prb_get_stream(prb_context* ctx, void** stream);
  * and cap_bytes is large enough) and returns its size in bytes, or a negative error.  Names:
  *   points normals sorted_idx sorted_key base count key pidx pnum parent didx dnum children
  *   neighs p2n vectorfield divergence x pointvalue iso center_scale cg_iters lap_stencil
- *   vvalue_slots vertex_owner_mask passes mesh_v mesh_t subdivide                      */
+ *   vvalue_slots passes mesh_v mesh_t subdivide child0 sg_table df_table               */
 int64_t prb_get_array(prb_context* ctx, const char* name, void* dst, int64_t cap_bytes);
 /* Overwrite an intermediate (teacher forcing in parity tests): vectorfield divergence x iso. */
 int prb_set_array(prb_context* ctx, const char* name, const void* src, int64_t bytes);

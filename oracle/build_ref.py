@@ -20,12 +20,15 @@ git-ignored oracle/_ref/.  The patch does not touch any kernel or algorithm; it 
       zero roots (main.cu:4439-4446, 4521-4527: cudaMemcpy from a null device pointer fails
       silently because CHECK is compiled out, Debug.cuh:8) -- without this the reference reads
       stack garbage as a vertex count.
-The reference is only valid for 5 <= D <= 9.
+The reference is only valid for 5 <= D <= 9.  --depths 10 additionally applies
+patch_widen() ("ref+widen", BASELINE.md 2.1: the packed function index becomes a long long) and
+writes oracle/_ref/ref_poisson_d10_widen; results of that binary are always labelled "ref+widen".
 
 Usage: python oracle/build_ref.py [--depths 8 9] [--tables-only]
 """
 import argparse
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -140,6 +143,43 @@ def patch_main(src):
     return s
 
 
+def patch_widen(src):
+    """'ref+widen' (depth 10 only): the packed per-axis function index
+    fi_x + fi_y*2^(D+1) + fi_z*2^(2(D+1)) (main.cu:889-899) needs 33 bits at maxDepth 10, so the
+    reference's int overflows.  This patch only changes the TYPE of that packed index (and of the
+    two decode divisors) to long long at its encode site and at every decode site
+    (main.cu:1018-1040, 1107-1124, 1173-1197, 1344-1360, 2268-2311, 2339-2364, 2397-2422); no
+    arithmetic, kernel structure or launch configuration changes."""
+    s = src
+    n_total = 0
+
+    def rep(pattern, repl, what, minimum=1):
+        nonlocal s, n_total
+        s, n = re.subn(pattern, repl, s)
+        if n < minimum:
+            raise SystemExit(f"widen patch anchor missing ({what}): {n} < {minimum}")
+        n_total += n
+    rep(r"int \*EncodedNodeIdxInFunction", "long long *EncodedNodeIdxInFunction", "EncodedNodeIdxInFunction decls", 8)
+    # (the unencoded precomputeFunctionIdxOfNode, main.cu:975, keeps its int[3] output)
+    rep(r"__global__ void (__launch_bounds__\(1024\) )?precomputeEncodedFunctionIdxOfNode\(int \*BaseAddressArray_d,OctNode \*NodeArray,int NodeArray_sz,int \*NodeIdxInFunction\)",
+        r"__global__ void \1precomputeEncodedFunctionIdxOfNode(int *BaseAddressArray_d,OctNode *NodeArray,int NodeArray_sz,long long *NodeIdxInFunction)", "encode kernel 1")
+    rep(r"int \*DepthBuffer,int \*NodeIdxInFunction\)", "int *DepthBuffer,long long *NodeIdxInFunction)", "encode kernel 2")
+    rep(r"(\n\s*)int \*NodeIdxInFunction,(\n)", r"\1long long *NodeIdxInFunction,\2", "coarse divergence param")
+    rep(r"\(int \*\*\)&EncodedNodeIdxInFunction", "(long long **)&EncodedNodeIdxInFunction", "malloc cast")
+    rep(r"int encode_idx", "long long encode_idx", "encode_idx locals", 6)
+    rep(r"int decode_offset1=\(1<<\(maxD\+1\)\);", "long long decode_offset1=(1ll<<(maxD+1));", "decode_offset1", 6)
+    rep(r"int decode_offset2=\(1<<\(2\*\(maxD\+1\)\)\);", "long long decode_offset2=(1ll<<(2*(maxD+1)));", "decode_offset2", 6)
+    rep(r"void getEncodedFunctionIdxOfNode\(const int& key,const int &depthD,int \*idx\)",
+        "void getEncodedFunctionIdxOfNode(const int& key,const int &depthD,long long *idx)", "encode signature")
+    rep(r"\*idx = \(\(1<<depthD\)-1\)\*\(1\+\(1<<\(maxDepth\+1\)\)\+\(1<<\(2\*\(maxDepth\+1\)\)\) \);",
+        "*idx = ((1ll<<depthD)-1)*(1+(1ll<<(maxDepth+1))+(1ll<<(2*(maxDepth+1))) );", "encode base (device)")
+    rep(r"sonKeyY \* \(1<<\(depthD-depth\)\) \* \(1<<\(maxDepth\+1\)\) \+", "sonKeyY * (1ll<<(depthD-depth)) * (1ll<<(maxDepth+1)) +", "encode y (device)")
+    rep(r"sonKeyZ \* \(1<<\(depthD-depth\)\) \* \(1<<\(2\*\(maxDepth\+1\)\)\);", "sonKeyZ * (1ll<<(depthD-depth)) * (1ll<<(2*(maxDepth+1)));", "encode z (device)")
+    rep(r"nByte = 1ll \* sizeof\(int\) \* NodeArray_sz;\n(\s*)CHECK\(cudaMalloc\(\(long long \*\*\)&EncodedNodeIdxInFunction",
+        r"nByte = 1ll * sizeof(long long) * NodeArray_sz;\n\1CHECK(cudaMalloc((long long **)&EncodedNodeIdxInFunction", "allocation size")
+    return s
+
+
 def patch_cg(src):
     s = src
     # (4) iteration counter: one store at kernel exit, printed by the host wrapper
@@ -174,13 +214,16 @@ def build_poisson(depth, keep=False):
         with open(mp) as fh:
             src = fh.read()
         with open(mp, "w") as fh:
-            fh.write(patch_main(src))
+            src = patch_main(src)
+            if depth >= 10:
+                src = patch_widen(src)
+            fh.write(src)
         cp = os.path.join(tmp, "CG_CUDA.cuh")
         with open(cp) as fh:
             src = fh.read()
         with open(cp, "w") as fh:
             fh.write(patch_cg(src))
-        out = os.path.join(OUT, f"ref_poisson_d{depth}")
+        out = os.path.join(OUT, f"ref_poisson_d{depth}" + ("_widen" if depth >= 10 else ""))
         cmd = ["nvcc", "-arch=sm_100", "-std=c++17", "-rdc=true", "-w", "-O2", f"-DREF_DEPTH={depth}",
                "main.cu", "CmdLineParser.cu", "Geometry.cu", "plyfile.cu", "Factor.cu", "-o", out]
         subprocess.check_call(cmd, cwd=tmp)
@@ -202,8 +245,8 @@ def main():
     build_tables()
     if not a.tables_only:
         for d in a.depths:
-            if not (5 <= d <= 9):
-                raise SystemExit("the reference is only valid for 5 <= maxDepth <= 9")
+            if not (5 <= d <= 10):
+                raise SystemExit("the reference is only valid for 5 <= maxDepth <= 9 (10 with the 'ref+widen' index-type patch)")
             print("built", build_poisson(d, a.keep))
     return 0
 

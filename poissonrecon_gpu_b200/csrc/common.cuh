@@ -43,11 +43,21 @@ int arena_alloc(void** out, size_t bytes, cudaStream_t st);
 void arena_free(void* p, cudaStream_t st);
 void arena_stats(cudaStream_t st, size_t* reserved, size_t* peak, long* driverCalls);
 
+// Move-only owner of an arena block: an early return (PRB_TRY / PRB_CUDA) gives the block back to the arena.
 template <class T>
 struct DBuf {
     T* p = nullptr;
     size_t n = 0;
     cudaStream_t s = nullptr;
+    DBuf() = default;
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    DBuf(DBuf&& o) noexcept : p(o.p), n(o.n), s(o.s), cap(o.cap) { o.p = nullptr; o.n = 0; o.cap = 0; }
+    DBuf& operator=(DBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; s = o.s; cap = o.cap; o.p = nullptr; o.n = 0; o.cap = 0; }
+        return *this;
+    }
+    ~DBuf() { release(); }
     int alloc(size_t count, cudaStream_t st) {
         release();
         s = st;
@@ -289,6 +299,19 @@ __host__ __device__ inline void other_axes(int o, int& a0, int& a1) {
     a0 = (o == 0) ? 1 : 0;
     a1 = (o == 2) ? 1 : 2;
 }
+
+// Every entry point runs on the context's device and gives the caller's current device back on return.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        ok = cudaSetDevice(device) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); set_error("cudaSetDevice failed"); }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define PRB_DEVICE(c) DeviceGuard guard__((c).device); if (!guard__.ok) return PRB_ERR_CUDA
 
 }  // namespace prb
 

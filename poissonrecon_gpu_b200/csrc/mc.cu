@@ -15,6 +15,7 @@
 #include "mg_device.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include "mc_case_table.h"
 #include "scan.cuh"
 
@@ -25,9 +26,13 @@ __constant__ unsigned char cMcCount[256];
 __constant__ unsigned char cEdgeVertex[12][2];   // ring indices, ascending (MarchingCubes.cuh:693-706)
 __constant__ unsigned char cFaceEdgeMask[6][2];  // 12-bit mask of the 4 edges of each face (MarchingCubes.cuh:734-741), lo/hi byte
 
-static bool g_tablesReady = false;
-static int upload_mc_tables() {
-    if (g_tablesReady) return PRB_OK;
+// __constant__ symbols exist once per DEVICE: readiness is tracked per device (a process may hold contexts on several GPUs)
+static std::mutex g_tablesMu;
+static bool g_tablesReady[64] = {false};
+static int upload_mc_tables(int device) {
+    std::lock_guard<std::mutex> lk(g_tablesMu);
+    if (device < 0 || device >= 64) { set_error("device index out of range"); return PRB_ERR_ARG; }
+    if (g_tablesReady[device]) return PRB_OK;
     signed char tri[256][16];
     unsigned char cnt[256], ev[12][2], fe[6][2];
     for (int c = 0; c < 256; c++) {
@@ -60,7 +65,7 @@ static int upload_mc_tables() {
     PRB_CUDA(cudaMemcpyToSymbol(cMcCount, cnt, sizeof(cnt)));
     PRB_CUDA(cudaMemcpyToSymbol(cEdgeVertex, ev, sizeof(ev)));
     PRB_CUDA(cudaMemcpyToSymbol(cFaceEdgeMask, fe, sizeof(fe)));
-    g_tablesReady = true;
+    g_tablesReady[device] = true;
     return PRB_OK;
 }
 
@@ -1579,7 +1584,7 @@ static int ensure_bv_tables(Context& c) {
 int stage_extract(Context& c) {
     cudaStream_t st = c.stream;
     const int D = c.D, M = c.M;
-    PRB_TRY(upload_mc_tables());
+    PRB_TRY(upload_mc_tables(c.device));
     c.passes.clear();
     c.subdivide.clear();
     c.hMeshValid = false;

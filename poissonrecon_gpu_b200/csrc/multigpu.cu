@@ -30,7 +30,7 @@ int prb_mg_init(prb_context* h, int rank, int world, int64_t arena_bytes, void* 
         return PRB_ERR_ARG;
     }
     Context& c = h->c;
-    PRB_CUDA(cudaSetDevice(c.device));
+    PRB_DEVICE(c);
     if (c.mg.arena) { set_error("prb_mg_init: already initialised"); return PRB_ERR_STATE; }
     PRB_CUDA(cudaMalloc((void**)&c.mg.arena, (size_t)arena_bytes));
     PRB_CUDA(cudaMemset(c.mg.arena, 0, kMgHeaderBytes));
@@ -52,7 +52,7 @@ int prb_mg_set_peer(prb_context* h, int peer_rank, const void* handle /* 64 byte
     Context& c = h->c;
     if (!c.mg.arena || peer_rank < 0 || peer_rank >= c.mg.world) { set_error("prb_mg_set_peer: bad rank or prb_mg_init not called"); return PRB_ERR_ARG; }
     if (peer_rank == c.mg.rank) return PRB_OK;
-    PRB_CUDA(cudaSetDevice(c.device));
+    PRB_DEVICE(c);
     cudaIpcMemHandle_t hd;
     std::memcpy(&hd, handle, 64);
     void* p = nullptr;
@@ -65,7 +65,7 @@ int prb_mg_set_peer(prb_context* h, int peer_rank, const void* handle /* 64 byte
 int prb_mg_barrier(prb_context* h) {
     if (!h) return PRB_ERR_ARG;
     Context& c = h->c;
-    PRB_CUDA(cudaSetDevice(c.device));
+    PRB_DEVICE(c);
     for (int r = 0; r < c.mg.world; r++)
         if (!c.mg.peer[r]) { set_error("prb_mg_barrier: peer arena not set"); return PRB_ERR_STATE; }
     PRB_TRY(mg_barrier(c));

@@ -32,9 +32,9 @@ int fail(int code, const std::string& msg) {
 bool read_file(const char* path, std::vector<char>& buf) {
     FILE* fp = std::fopen(path, "rb");
     if (!fp) return false;
-    std::fseek(fp, 0, SEEK_END);
+    if (std::fseek(fp, 0, SEEK_END) != 0) { std::fclose(fp); return false; }
     long long sz = std::ftell(fp);
-    std::fseek(fp, 0, SEEK_SET);
+    if (sz < 0 || std::fseek(fp, 0, SEEK_SET) != 0) { std::fclose(fp); return false; }     // not seekable (pipe, directory)
     buf.resize((size_t)sz + 1);
     size_t got = sz ? std::fread(buf.data(), 1, (size_t)sz, fp) : 0;
     std::fclose(fp);
@@ -161,6 +161,16 @@ int read_ply(const char* path, std::vector<char>& buf, float*& xyz, float*& nrm,
     }
     n = firstCount;
     if (n < 0) return fail(kErrFormat, "[ERROR] negative vertex count");
+    // the header's count is untrusted: every record takes at least one byte per property (binary) or two
+    // characters per property (ascii), so a count the body cannot hold is rejected BEFORE any allocation
+    // (division, not multiplication: no wrap-around for absurd counts)
+    {
+        size_t minRec = 0;
+        for (auto& p : props) minRec += (fmt == 0) ? 2 : (size_t)(p.isList ? p.countType->size : p.type->size);
+        if (minRec == 0) minRec = 1;
+        const size_t bodyBytes = size - pos;
+        if ((size_t)n > bodyBytes / minRec + 1) return fail(kErrFormat, fmt == 0 ? "[ERROR] truncated ascii ply body" : "[ERROR] truncated binary ply body");
+    }
     xyz = (float*)std::malloc(sizeof(float) * 3 * (size_t)std::max<int64_t>(n, 1));
     nrm = (float*)std::malloc(sizeof(float) * 3 * (size_t)std::max<int64_t>(n, 1));
     if (!xyz || !nrm) return fail(-4, "out of host memory");
@@ -176,7 +186,7 @@ int read_ply(const char* path, std::vector<char>& buf, float*& xyz, float*& nrm,
                     long cnt = std::strtol(s, &e, 10);
                     if (e == s) return fail(kErrFormat, "[ERROR] truncated ascii ply body");
                     s = e;
-                    for (long q = 0; q < cnt; q++) { std::strtod(s, &e); s = e; }
+                    for (long q = 0; q < cnt; q++) { std::strtod(s, &e); if (e == s) return fail(kErrFormat, "[ERROR] truncated ascii ply body"); s = e; }
                     row[j] = 0;
                 } else {
                     row[j] = std::strtod(s, &e);
@@ -195,7 +205,7 @@ int read_ply(const char* path, std::vector<char>& buf, float*& xyz, float*& nrm,
         std::vector<int> off(props.size());
         int stride = 0;
         for (size_t j = 0; j < props.size(); j++) { off[j] = stride; stride += props[j].type->size; }
-        if ((size_t)stride * (size_t)n > avail) return fail(kErrFormat, "[ERROR] truncated binary ply body");
+        if (stride <= 0 || (size_t)n > avail / (size_t)stride) return fail(kErrFormat, "[ERROR] truncated binary ply body");
         bool plainF32 = !swap;
         for (int k = 0; k < 6; k++) plainF32 &= (props[col[k]].type->kind == 2 && props[col[k]].type->size == 4);
         parallel_chunks((size_t)n, 1 << 18, [&](size_t a, size_t b) {
@@ -222,7 +232,10 @@ int read_ply(const char* path, std::vector<char>& buf, float*& xyz, float*& nrm,
             if (props[j].isList) {
                 if (r + props[j].countType->size > end) return fail(kErrFormat, "[ERROR] truncated binary ply body");
                 long long cnt = (long long)load_scalar(r, *props[j].countType, swap);
-                r += props[j].countType->size + cnt * props[j].type->size;
+                r += props[j].countType->size;
+                if (cnt < 0 || (unsigned long long)cnt > (unsigned long long)(end - r) / (unsigned long long)props[j].type->size)
+                    return fail(kErrFormat, "[ERROR] truncated binary ply body");
+                r += cnt * props[j].type->size;
                 row[j] = 0;
             } else {
                 if (r + props[j].type->size > end) return fail(kErrFormat, "[ERROR] truncated binary ply body");

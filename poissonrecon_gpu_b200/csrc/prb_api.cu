@@ -41,7 +41,6 @@ int upload_tables(Context& c) {
 
 using namespace prb;
 
-
 extern "C" {
 
 const char* prb_last_error(void) { return g_lastError.c_str(); }
@@ -57,6 +56,9 @@ int prb_create(int device, int depth, prb_context** out) {
         return PRB_ERR_CUDA;
     }
     if (device < 0 || device >= ndev) { set_error("device index out of range"); return PRB_ERR_ARG; }
+    int prevDev = -1;
+    if (cudaGetDevice(&prevDev) != cudaSuccess) { cudaGetLastError(); prevDev = -1; }
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prevDev};
     PRB_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     PRB_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -67,12 +69,24 @@ int prb_create(int device, int depth, prb_context** out) {
     c.D = depth;
     c.smCount = prop.multiProcessorCount;
     c.deviceMemBytes = prop.totalGlobalMem;
-    PRB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    for (auto& e : c.ev) PRB_CUDA(cudaEventCreate(&e));
+    for (auto& e : c.ev) e = nullptr;
+    auto fail = [&](int code) {            // nothing of a half-built context survives
+        for (auto& e : c.ev) if (e) cudaEventDestroy(e);
+        if (c.stream) { arena_unregister(c.stream); cudaStreamDestroy(c.stream); }
+        c.stream = nullptr;
+        delete h;
+        return code;
+    };
+    if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); c.stream = nullptr; set_error("cudaStreamCreate failed"); return fail(PRB_ERR_CUDA); }
     arena_register(c.stream);
+    for (auto& e : c.ev)
+        if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); e = nullptr; set_error("cudaEventCreate failed"); return fail(PRB_ERR_CUDA); }
     std::memset(&c.stats, 0, sizeof(c.stats));
     int r = upload_tables(c);
-    if (r != PRB_OK) { arena_unregister(c.stream); cudaStreamDestroy(c.stream); delete h; return r; }
+    if (r != PRB_OK) {
+        c.dMaxDepthFn.release(); c.dBaseFn.release(); c.dDfT.release(); c.dDfOffset.release(); c.dStencil.release();
+        return fail(r);
+    }
     *out = h;
     return PRB_OK;
 }
@@ -80,7 +94,7 @@ int prb_create(int device, int depth, prb_context** out) {
 void prb_destroy(prb_context* h) {
     if (!h) return;
     Context& c = h->c;
-    cudaSetDevice(c.device);
+    DeviceGuard guard__(c.device);
     release_all(c);
     c.wsVal7.release(); c.wsLow.release(); c.wsCat.release(); c.wsNtri.release(); c.wsEmask.release(); c.wsVpre.release(); c.wsVbase.release(); c.wsTbase.release();
     c.dBvAnc.release(); c.dBvOwn.release(); c.dBvCell.release(); c.dBvGrid.release(); c.dMaxDepthFn.release(); c.dBaseFn.release(); c.dDfT.release(); c.dDfOffset.release(); c.dStencil.release();
@@ -111,7 +125,7 @@ int prb_set_option(prb_context* h, const char* key, double value) {
 int prb_set_points(prb_context* h, const float* xyz, const float* normals, int64_t n) {
     if (!h || !xyz || !normals || n <= 0) { set_error("prb_set_points: bad argument"); return PRB_ERR_ARG; }
     Context& c = h->c;
-    PRB_CUDA(cudaSetDevice(c.device));
+    PRB_DEVICE(c);
     release_all(c);
     c.mg.reset_allocs();
     c.mgP = c.mgX = c.mgVval = nullptr;
@@ -132,7 +146,7 @@ int prb_build_octree(prb_context* h) {
     if (!h) return PRB_ERR_ARG;
     Context& c = h->c;
     if (c.stage < 1) { set_error("prb_build_octree: no points set"); return PRB_ERR_STATE; }
-    PRB_CUDA(cudaSetDevice(c.device));
+    PRB_DEVICE(c);
     PRB_CUDA(cudaEventRecord(c.ev[1], c.stream));
     PRB_TRY(stage_octree(c));
     PRB_CUDA(cudaEventRecord(c.ev[2], c.stream));
@@ -143,7 +157,7 @@ int prb_splat(prb_context* h) {
     if (!h) return PRB_ERR_ARG;
     Context& c = h->c;
     if (c.stage < 2) { set_error("prb_splat: octree not built"); return PRB_ERR_STATE; }
-    PRB_CUDA(cudaSetDevice(c.device));
+    PRB_DEVICE(c);
     PRB_CUDA(cudaEventRecord(c.ev[2], c.stream));
     PRB_TRY(stage_splat(c));
     PRB_CUDA(cudaEventRecord(c.ev[4], c.stream));
@@ -154,7 +168,7 @@ int prb_solve(prb_context* h) {
     if (!h) return PRB_ERR_ARG;
     Context& c = h->c;
     if (c.stage < 3) { set_error("prb_solve: splat not done"); return PRB_ERR_STATE; }
-    PRB_CUDA(cudaSetDevice(c.device));
+    PRB_DEVICE(c);
     PRB_CUDA(cudaEventRecord(c.ev[4], c.stream));
     PRB_TRY(stage_solve(c));
     PRB_CUDA(cudaEventRecord(c.ev[5], c.stream));
@@ -167,7 +181,7 @@ int prb_extract(prb_context* h) {
     if (!h) return PRB_ERR_ARG;
     Context& c = h->c;
     if (c.stage < 4) { set_error("prb_extract: solve not done"); return PRB_ERR_STATE; }
-    PRB_CUDA(cudaSetDevice(c.device));
+    PRB_DEVICE(c);
     PRB_CUDA(cudaEventRecord(c.ev[6], c.stream));
     PRB_TRY(stage_extract(c));
     PRB_CUDA(cudaEventRecord(c.ev[7], c.stream));
@@ -187,7 +201,7 @@ int prb_run(prb_context* h) {
 int prb_run_stage(prb_context* h, const char* name) {
     if (!h || !name) return PRB_ERR_ARG;
     Context& c = h->c;
-    PRB_CUDA(cudaSetDevice(c.device));
+    PRB_DEVICE(c);
     std::string s(name);
     int need = (s == "divergence") ? 3 : (s == "solve") ? 3 : (s == "iso") ? 4 : (s == "extract") ? 4 : 99;
     if (c.stage < need) { set_error("prb_run_stage: stage not reachable yet"); return PRB_ERR_STATE; }
@@ -213,7 +227,7 @@ int prb_get_mesh(prb_context* h, const float** v, int64_t* nv, const int32_t** t
     if (!h) return PRB_ERR_ARG;
     Context& c = h->c;
     if (c.stage < 5) { set_error("prb_get_mesh: extract not done"); return PRB_ERR_STATE; }
-    PRB_CUDA(cudaSetDevice(c.device));
+    PRB_DEVICE(c);
     if (!c.hMeshValid) {
         PRB_TRY(c.hMeshV.reserve(3 * (size_t)c.nMeshV + 1));
         PRB_TRY(c.hMeshT.reserve(3 * (size_t)c.nMeshT + 1));
@@ -238,7 +252,7 @@ int prb_get_stream(prb_context* h, void** stream) {
 int prb_get_stats(prb_context* h, prb_stats* out) {
     if (!h || !out) return PRB_ERR_ARG;
     Context& c = h->c;
-    PRB_CUDA(cudaSetDevice(c.device));
+    PRB_DEVICE(c);
     PRB_CUDA(cudaStreamSynchronize(c.stream));
     prb_stats& s = c.stats;
     s.n_points = c.N;
@@ -267,7 +281,8 @@ int prb_get_stats(prb_context* h, prb_stats* out) {
 int64_t prb_get_array(prb_context* h, const char* name, void* dst, int64_t cap) {
     if (!h || !name) return PRB_ERR_ARG;
     Context& c = h->c;
-    cudaSetDevice(c.device);
+    DeviceGuard guard__(c.device);
+    if (!guard__.ok) return PRB_ERR_CUDA;
     cudaStreamSynchronize(c.stream);
     std::string s(name);
     const void* dev = nullptr;
@@ -346,7 +361,7 @@ int64_t prb_host_tables(int depth, const char* name, void* dst, int64_t cap) {
 int prb_set_array(prb_context* h, const char* name, const void* src, int64_t bytes) {
     if (!h || !name || !src) return PRB_ERR_ARG;
     Context& c = h->c;
-    PRB_CUDA(cudaSetDevice(c.device));
+    PRB_DEVICE(c);
     PRB_CUDA(cudaStreamSynchronize(c.stream));
     std::string s(name);
     void* dst = nullptr;
