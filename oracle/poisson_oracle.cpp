@@ -937,6 +937,7 @@ struct Oracle {
         meshV.clear(); meshT.clear(); passes.clear();
         mc_main_pass();
         find_subdivide();
+        if (stages == 40) return 0;      // everything except the refinement passes (bench.py: bounded CPU sample at full size)
         refine();
         return 0;
     }
@@ -953,7 +954,7 @@ void* orc_create() {
     return new Oracle();
 }
 void orc_destroy(void* h) { delete (Oracle*)h; }
-// stages: 1 = octree only, 2 = +splat/divergence, 3 = +solve/iso, 4 = everything
+// stages: 1 = octree only, 2 = +splat/divergence, 3 = +solve/iso, 4 = everything, 40 = everything except the refinement passes
 int orc_run(void* h, const float* xyz, const float* nrm, int n, int depth, int stages) { return ((Oracle*)h)->run(xyz, nrm, n, depth, stages); }
 // Teacher forcing for stage-by-stage pinning: overwrite an intermediate with the reference's
 // own values, then re-run a single stage with orc_stage().
@@ -975,7 +976,11 @@ int orc_stage(void* h, const char* name) {
     else if (s == "divergence") o.divergence();
     else if (s == "solve") o.solve();
     else if (s == "iso") o.iso_value();
-    else if (s == "mc") {
+    else if (s == "mc_main") {
+        o.build_vertices(); o.build_edges(); o.build_faces(); o.vertex_values();
+        o.meshV.clear(); o.meshT.clear(); o.passes.clear();
+        o.mc_main_pass(); o.find_subdivide();
+    } else if (s == "mc") {
         o.build_vertices(); o.build_edges(); o.build_faces(); o.vertex_values();
         o.meshV.clear(); o.meshT.clear(); o.passes.clear();
         o.mc_main_pass(); o.find_subdivide(); o.refine();

@@ -202,6 +202,8 @@ struct Context {
     DBuf<float> V;                 // [M_D][3]
     DBuf<float> divg, x;          // x is padded: node i lives at xv[i] = x.p[7 + i] (sibling blocks 32-byte aligned)
     float* xv = nullptr;
+    float* divgv = nullptr;        // divg.p + 7, same padding
+    int divMode = 1;               // 1: block-table / profile divergence (field.cu); 0: first-version kernels through the 27-neighbour rows (cross-check)
     DBuf<float> pointValue;
     float iso = 0;
     int cgIters[kMaxDepth + 1] = {0};

@@ -12,6 +12,7 @@
 // summed by one thread in the reference's order (bit-identical), coarser nodes by a warp or a
 // block with double partial sums.
 #include "common.cuh"
+#include <algorithm>
 
 namespace prb {
 
@@ -294,11 +295,219 @@ __global__ void __launch_bounds__(256) k_divergence_finish(const double* __restr
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) divg[i] = (float)accum[i];
 }
 
+
+// =================================================================================================
+// Divergence, block-table form (default).  The work is split by how many depth-D slots a node sees:
+//   * depths D and D-1 (94 % of the nodes): k_div_fine.  One depth-D SUPER-GROUP (solver.cu / k_sg_table:
+//     the 4x4x4 cube of 8-slot blocks around the children of a sibling group of depth D-1) holds every
+//     slot that the group's 64 depth-D rows AND its 8 depth-(D-1) rows read, so its 512 slots x 12 B
+//     of V are staged once in shared memory (cp.async, zero fill for absent blocks) instead of being
+//     gathered 27 (x 8) times per row through the 108-byte neighbour rows.  A quarter-warp owns a
+//     super-group; lane li owns block li (its 8 leaf rows) and the depth-(D-1) node above that block.
+//     Every row still adds its terms in the reference's order (neighbour j = 0..26, then slot 0..7;
+//     float product, double sum: main.cu:1020-1058), so both depths stay bit-identical: an absent
+//     neighbour contributes an exact +0.0 instead of being skipped.
+//   * depths <= D-2: the terms of a row are V_s . (T[x], T[y], T[z]) with T indexed by the per-axis
+//     offset difference ONLY (no cross-axis factor), so a node n can be summarised by
+//     three "profiles" P_n[axis][t] = sum of V_axis over the depth-D slots under n whose offset along
+//     `axis` is t (t < 2^(D-d)), built bottom-up in double (k_profile_d2, k_profile_up), and
+//     b_o = sum_j sum_axis sum_t T[k (d_axis(j) + 1) + t] P_{n_j}[axis][t]   (k_div_coarse).
+//     27 * 3 * 2^(D-d) multiply-adds per node instead of 27 * 8^(D-d) -- this replaces both the
+//     warp-per-node gather (D-2, D-3) and the atomic scatter (<= D-4) of the first version, and the
+//     reference's per-node host loop for depths 0-4 (main.cu:3419-3458).  Summation order differs from
+//     the reference there (double throughout): <= 1e-7 rel-L2 per depth, tolerance 1e-6 in the tests.
+// Shared-memory layout of a staged cube, in 16-byte groups: block u = (ux, uy, uz) starts at group
+// ux * 113 + uy * 28 + uz * 6 (6 groups = 8 slots x 12 B; the pads make the strides 1, 4, 6 mod 8), so the eight
+// lanes of a quarter-warp -- blocks {1,2}^3 plus a common offset -- always read eight different 16-byte bank groups:
+// every LDS.128 below is conflict free.
+constexpr int kDfWarps = 7;
+constexpr int kDfGx = 113, kDfGy = 28, kDfGz = 6;
+constexpr int kDfCubeFloats = 4 * (4 * kDfGx);         // 452 groups
+__host__ __device__ constexpr int df_block_group(int u) { return (u >> 4) * kDfGx + ((u >> 2) & 3) * kDfGy + (u & 3) * kDfGz; }
+__global__ void __launch_bounds__(kDfWarps * 32, 1) k_div_fine(const float* __restrict__ V, const int* __restrict__ sgTab, const float* __restrict__ rowD, const float* __restrict__ rowDm1,
+                                                               int baseD, int sgFirst, int nSgRange, int leafSg0, int leafSg1, int dm1Sg0, int dm1Sg1, float* __restrict__ divg) {
+    extern __shared__ __align__(16) float sDf[];        // [warp][4 cubes][kDfCubeFloats] then [warp][4][64] table
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, q = lane >> 3, li = lane & 7;
+    float* cube = sDf + (size_t)(wp * 4 + q) * kDfCubeFloats;
+    int* tab = reinterpret_cast<int*>(sDf + (size_t)kDfWarps * 4 * kDfCubeFloats) + (wp * 4 + q) * 64;
+    const unsigned cubeS = (unsigned)__cvta_generic_to_shared(cube);
+    float r0[3], r1[6];
+#pragma unroll
+    for (int t = 0; t < 3; t++) r0[t] = rowD[t];
+#pragma unroll
+    for (int t = 0; t < 6; t++) r1[t] = rowDm1[t];
+    const int myBlock = (1 + (li >> 2)) * 16 + (1 + ((li >> 1) & 1)) * 4 + (1 + (li & 1));
+    const float4* mine = reinterpret_cast<const float4*>(cube) + df_block_group(myBlock);     // group pointer of the lane's own block
+    const int nSteps = (nSgRange + 3) >> 2;
+    for (int st = blockIdx.x * kDfWarps + wp; st < nSteps; st += gridDim.x * kDfWarps) {
+        const int sg = sgFirst + 4 * st + q;
+        const bool have = 4 * st + q < nSgRange;
+        __syncwarp();
+        // ---- table row, then the 384 16-byte chunks of the cube: consecutive lanes copy consecutive chunks
+        if (have) {
+            const int4* src = reinterpret_cast<const int4*>(sgTab + (size_t)sg * 64) + 2 * li;
+            const int4 a = src[0], b = src[1];
+            reinterpret_cast<int4*>(tab)[2 * li] = a;
+            reinterpret_cast<int4*>(tab)[2 * li + 1] = b;
+        }
+        __syncwarp();
+        if (have) {
+#pragma unroll 8
+            for (int it = 0; it < 48; it++) {
+                const int ch = it * 8 + li, blk = ch / 6, part = ch - blk * 6;
+                const int id = tab[blk];
+                const float* src = V + (id >= 0 ? 3 * (size_t)(id - baseD) + 4 * part : 0);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(cubeS + 16u * (unsigned)(df_block_group(blk) + part)), "l"(src), "r"(id >= 0 ? 16 : 0) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncwarp();
+        if (!have) continue;
+        // ---- depth D-1: the node above block li; 27 neighbour blocks x 8 slots, reference order
+        if (sg >= dm1Sg0 && sg < dm1Sg1) {
+            double val = 0.0;
+#pragma unroll
+            for (int j = 0; j < 27; j++) {
+                const int dx = j / 9 - 1, dy = (j / 3) % 3 - 1, dz = j % 3 - 1;
+                const float4* b4 = mine + (dx * kDfGx + dy * kDfGy + dz * kDfGz);
+                float v[24];
+#pragma unroll
+                for (int t = 0; t < 6; t++) { const float4 a = b4[t]; v[4 * t] = a.x; v[4 * t + 1] = a.y; v[4 * t + 2] = a.z; v[4 * t + 3] = a.w; }
+#pragma unroll
+                for (int s = 0; s < 8; s++) {
+                    float dp = __fmul_rn(v[3 * s], r1[2 * (dx + 1) + (s >> 2)]);
+                    dp = __fmaf_rn(v[3 * s + 1], r1[2 * (dy + 1) + ((s >> 1) & 1)], dp);
+                    dp = __fmaf_rn(v[3 * s + 2], r1[2 * (dz + 1) + (s & 1)], dp);
+                    val += (double)dp;
+                }
+            }
+            divg[1 + 8 * (sg - 1) + li] = (float)val;
+        }
+        // ---- depth D: the 8 rows of block li.  The 4x4x4 window of cells around the block is visited in
+        // lexicographic order (x layer by x layer), which is neighbour order j for each of the rows it feeds.  A layer is
+        // the half with x bit sx of the 9 blocks (bx; by, bz): 12 contiguous floats each
+        const int own = tab[myBlock];
+        if (own >= 0 && sg >= leafSg0 && sg < leafSg1) {
+            double val[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) val[c] = 0.0;
+#pragma unroll
+            for (int wx = -1; wx <= 2; wx++) {
+                const int bx = (wx + 2) / 2 - 1, sx = wx & 1;
+                float L[9][12];
+#pragma unroll
+                for (int b = 0; b < 9; b++) {
+                    const float4* b4 = mine + (bx * kDfGx + (b / 3 - 1) * kDfGy + (b % 3 - 1) * kDfGz) + 3 * sx;
+#pragma unroll
+                    for (int t = 0; t < 3; t++) { const float4 a = b4[t]; L[b][4 * t] = a.x; L[b][4 * t + 1] = a.y; L[b][4 * t + 2] = a.z; L[b][4 * t + 3] = a.w; }
+                }
+#pragma unroll
+                for (int wy = -1; wy <= 2; wy++)
+#pragma unroll
+                    for (int wz = -1; wz <= 2; wz++) {
+                        const int b = ((wy + 2) / 2) * 3 + ((wz + 2) / 2), sl = ((wy & 1) << 1) | (wz & 1);
+                        const float vx = L[b][3 * sl], vy = L[b][3 * sl + 1], vz = L[b][3 * sl + 2];
+#pragma unroll
+                        for (int c = 0; c < 8; c++) {
+                            const int dx = wx - ((c >> 2) & 1), dy = wy - ((c >> 1) & 1), dz = wz - (c & 1);
+                            if (dx < -1 || dx > 1 || dy < -1 || dy > 1 || dz < -1 || dz > 1) continue;
+                            float dp = __fmul_rn(vx, r0[dx + 1]);
+                            dp = __fmaf_rn(vy, r0[dy + 1], dp);
+                            dp = __fmaf_rn(vz, r0[dz + 1], dp);
+                            val[c] += (double)dp;
+                        }
+                    }
+            }
+            float4* o = reinterpret_cast<float4*>(divg + own);
+            o[0] = make_float4((float)val[0], (float)val[1], (float)val[2], (float)val[3]);
+            o[1] = make_float4((float)val[4], (float)val[5], (float)val[6], (float)val[7]);
+        }
+    }
+}
+// profiles of depth D-2: 8 lanes per node Q, lane li = child li of Q (depth D-1), whose children are one
+// block of 8 depth-D slots.  P[Q][axis][t], t = 2 (bit of the child) + (bit of the slot)
+__global__ void __launch_bounds__(256) k_profile_d2(const float* __restrict__ V, const int* __restrict__ child0, int base2, int count2, int baseD, double* __restrict__ prof) {
+    const int lane = threadIdx.x & 31, li = lane & 7;
+    const int nWork = (count2 + 3) >> 2;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nWork; w += (gridDim.x * blockDim.x) >> 5) {
+        const int l = 4 * w + (lane >> 3);
+        const bool have = l < count2;
+        double sx[2] = {0.0, 0.0}, sy[2] = {0.0, 0.0}, sz[2] = {0.0, 0.0};
+        if (have) {
+            const int c1 = child0[base2 + l];
+            const int c2 = c1 >= 0 ? child0[c1 + li] : -1;
+            if (c2 >= 0) {
+                const float4* b4 = reinterpret_cast<const float4*>(V + 3 * (size_t)(c2 - baseD));
+                float v[24];
+#pragma unroll
+                for (int t = 0; t < 6; t++) { const float4 a = b4[t]; v[4 * t] = a.x; v[4 * t + 1] = a.y; v[4 * t + 2] = a.z; v[4 * t + 3] = a.w; }
+#pragma unroll
+                for (int s = 0; s < 8; s++) { sx[(s >> 2) & 1] += (double)v[3 * s]; sy[(s >> 1) & 1] += (double)v[3 * s + 1]; sz[s & 1] += (double)v[3 * s + 2]; }
+            }
+        }
+        // x: lanes with the same bit 2 of li; y: same bit 1; z: same bit 0 (fixed butterfly order)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            sx[b] += __shfl_xor_sync(0xffffffffu, sx[b], 1); sx[b] += __shfl_xor_sync(0xffffffffu, sx[b], 2);
+            sy[b] += __shfl_xor_sync(0xffffffffu, sy[b], 1); sy[b] += __shfl_xor_sync(0xffffffffu, sy[b], 4);
+            sz[b] += __shfl_xor_sync(0xffffffffu, sz[b], 2); sz[b] += __shfl_xor_sync(0xffffffffu, sz[b], 4);
+        }
+        if (have) {
+            double* P = prof + 12 * (size_t)l;
+            if ((li & 3) == 0) { P[2 * (li >> 2)] = sx[0]; P[2 * (li >> 2) + 1] = sx[1]; }
+            if ((li & 5) == 0) { P[4 + 2 * ((li >> 1) & 1)] = sy[0]; P[4 + 2 * ((li >> 1) & 1) + 1] = sy[1]; }
+            if ((li & 6) == 0) { P[8 + 2 * (li & 1)] = sz[0]; P[8 + 2 * (li & 1) + 1] = sz[1]; }
+        }
+    }
+}
+// profiles of depth d from those of depth d + 1: entry t of a node = the sum over its four children on side
+// t / (k/2) of the axis of their entries t mod (k/2), ascending child order
+__global__ void __launch_bounds__(256) k_profile_up(const int* __restrict__ child0, int baseHere, int countHere, int baseBelow, int lk /* log2 k */,
+                                                    const double* __restrict__ below, double* __restrict__ here) {
+    const int k = 1 << lk, kh = k >> 1;
+    const i64 total = (i64)countHere * 3 * k;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (i64)gridDim.x * blockDim.x) {
+        const int t = (int)(e & (k - 1)), q = (int)(e >> lk), a = q % 3, l = q / 3;
+        const int c0 = child0[baseHere + l];
+        double s = 0.0;
+        if (c0 >= 0) {
+            const int side = t >> (lk - 1), tt = t & (kh - 1), bit = 2 - a;
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+                if (((c >> bit) & 1) == side) s += below[((size_t)(c0 + c - baseBelow) * 3 + a) * kh + tt];
+        }
+        here[e] = s;
+    }
+}
+// b_o for the nodes of ONE depth d <= D-2 from the profiles of their 27 neighbours: one warp per node, the 27 x 3 x k
+// products flattened over the lanes, fixed-order warp reduction
+__global__ void __launch_bounds__(256) k_div_coarse(const int* __restrict__ neighs, const double* __restrict__ prof, const float* __restrict__ row, int base, int count, int lk,
+                                                    float* __restrict__ divg) {
+    const int lane = threadIdx.x & 31, k = 1 << lk;
+    const int total = 81 << lk;
+    for (int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; l < count; l += (gridDim.x * blockDim.x) >> 5) {
+        const int* nb = neighs + 27 * (i64)(base + l);
+        double acc = 0.0;
+        for (int e = lane; e < total; e += 32) {
+            const int t = e & (k - 1), q = e >> lk, j = q / 3, a = q - 3 * j;
+            const int n = nb[j];
+            if (n < 0) continue;
+            const int dj = a == 0 ? j / 9 : (a == 1 ? (j / 3) % 3 : j % 3);          // d_axis(j) + 1
+            acc += (double)row[(dj << lk) + t] * prof[((size_t)(n - base) * 3 + a) * k + t];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) divg[base + l] = (float)acc;
+    }
+}
+
 int stage_splat(Context& c) {
     const int D = c.D;
     cudaStream_t st = c.stream;
     PRB_TRY(c.V.alloc(3 * (size_t)c.cnt[D], st));
-    PRB_TRY(c.divg.alloc((size_t)c.M, st));
+    PRB_TRY(c.divg.alloc((size_t)c.M + 16, st));       // padded like x: node 1 (every sibling block) on a 32-byte boundary
+    c.divgv = c.divg.p + 7;
     float width = (float)(1.0 / (1 << D));
     {
         DBuf<float> W;
@@ -313,7 +522,49 @@ int stage_splat(Context& c) {
     return PRB_OK;
 }
 
+static int stage_divergence_blocks(Context& c) {
+    const int D = c.D;
+    cudaStream_t st = c.stream;
+    const bool mg = c.mg.active();
+    auto sg_start = [&](int d) { return d <= 1 ? 0 : 1 + (c.base[d - 1] - 1) / 8; };      // first super-group of depth d
+    // ---- depths D and D-1 (multi-GPU: the super-groups that hold this rank's rows of either depth)
+    {
+        int leaf0 = sg_start(D), leaf1 = sg_start(D + 1), dm0 = leaf0, dm1 = leaf1;
+        if (mg && D >= c.shardFrom) { leaf0 = c.sgLo[D][c.mg.rank]; leaf1 = c.sgLo[D][c.mg.rank + 1]; }
+        if (mg && D - 1 >= c.shardFrom) {
+            const int ra = c.rowLo[D - 1][c.mg.rank], rb = c.rowLo[D - 1][c.mg.rank + 1];
+            dm0 = rb > ra ? 1 + (ra - 1) / 8 : leaf0;
+            dm1 = rb > ra ? 1 + (rb - 1 + 7) / 8 : leaf0;
+        }
+        const int first = std::min(leaf0, dm0), last = std::max(leaf1, dm1);
+        if (last > first) {
+            const size_t smem = (size_t)kDfWarps * 4 * kDfCubeFloats * sizeof(float) + (size_t)kDfWarps * 4 * 64 * sizeof(int);
+            PRB_CUDA(cudaFuncSetAttribute(k_div_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int steps = (last - first + 3) / 4;
+            const int grid = std::max(1, std::min(c.smCount, (steps + kDfWarps - 1) / kDfWarps));
+            PRB_LAUNCH(c, k_div_fine, grid, kDfWarps * 32, smem, c.V.p, c.sgTab.p, c.dDfT.p + c.tab.dfOffset[D], c.dDfT.p + c.tab.dfOffset[D - 1], c.base[D], first, last - first,
+                       leaf0, leaf1, dm0, dm1, c.divgv);
+        }
+    }
+    if (D < 2) return PRB_OK;
+    // ---- depths <= D-2 through the per-axis profiles (every rank computes all of them: 6 % of the nodes)
+    std::vector<size_t> off(D + 1, 0);
+    size_t total = 0;
+    for (int d = D - 2; d >= 0; --d) { off[d] = total; total += (size_t)c.cnt[d] * 3 * ((size_t)1 << (D - d)); }
+    DBuf<double> prof;
+    PRB_TRY(prof.alloc(total, st));
+    PRB_LAUNCH(c, k_profile_d2, grid_for(c, (i64)c.cnt[D - 2] * 8, 256), 256, 0, c.V.p, c.child0.p, c.base[D - 2], c.cnt[D - 2], c.base[D], prof.p + off[D - 2]);
+    for (int d = D - 3; d >= 0; --d)
+        PRB_LAUNCH(c, k_profile_up, grid_for(c, (i64)c.cnt[d] * 3 * ((i64)1 << (D - d)), 256), 256, 0, c.child0.p, c.base[d], c.cnt[d], c.base[d + 1], D - d, prof.p + off[d + 1], prof.p + off[d]);
+    for (int d = D - 2; d >= 0; --d)
+        PRB_LAUNCH(c, k_div_coarse, grid_for(c, (i64)c.cnt[d] * 32, 256), 256, 0, c.neighs.p, prof.p + off[d], c.dDfT.p + c.tab.dfOffset[d], c.base[d], c.cnt[d], D - d, c.divgv);
+    prof.release();
+    PRB_CUDA(cudaGetLastError());
+    return PRB_OK;
+}
+
 int stage_divergence(Context& c) {
+    if (c.divMode == 1) return stage_divergence_blocks(c);
     const int D = c.D;
     cudaStream_t st = c.stream;
     // depths with up to 8^4 slots under a node and deeper trees of slots go through the scatter
@@ -334,7 +585,7 @@ int stage_divergence(Context& c) {
         if (nItems > 0)
             PRB_LAUNCH(c, k_divergence_scatter, (int)nItems, 256, 0, c.V.p, c.offs.p, c.neighs.p, c.didx.p, c.dnum.p, c.dDfT.p, c.dDfOffset.p, itemBase.p,
                        nCoarse, c.base[D], D, accum.p);
-        PRB_LAUNCH(c, k_divergence_finish, grid_for(c, nCoarse, 256), 256, 0, accum.p, nCoarse, c.divg.p);
+        PRB_LAUNCH(c, k_divergence_finish, grid_for(c, nCoarse, 256), 256, 0, accum.p, nCoarse, c.divgv);
         items.release(); itemBase.release(); accum.release();
     }
     for (int d = (dc >= 0 ? dc + 1 : 0); d <= D; d++) {
@@ -346,11 +597,11 @@ int stage_divergence(Context& c) {
         const int n = sh ? c.rowLo[d][c.mg.rank + 1] - first : c.cnt[d];
         if (n <= 0) continue;
         if (d == D)
-            PRB_LAUNCH(c, k_divergence_leaf, grid_for(c, n, 256), 256, 0, c.V.p, c.neighs.p, row, c.base[D], first, n, c.divg.p);
+            PRB_LAUNCH(c, k_divergence_leaf, grid_for(c, n, 256), 256, 0, c.V.p, c.neighs.p, row, c.base[D], first, n, c.divgv);
         else if (d == D - 1)
-            PRB_LAUNCH(c, k_divergence_dm1, grid_for(c, n, 256), 256, 0, c.V.p, c.neighs.p, c.child0.p, row, first, n, c.base[D], c.divg.p);
+            PRB_LAUNCH(c, k_divergence_dm1, grid_for(c, n, 256), 256, 0, c.V.p, c.neighs.p, c.child0.p, row, first, n, c.base[D], c.divgv);
         else
-            PRB_LAUNCH(c, k_divergence_flat, grid_for(c, (i64)n * 32, 256), 256, 0, c.V.p, c.offs.p, c.neighs.p, c.didx.p, c.dnum.p, row, first, n, c.base[D], k, c.divg.p);
+            PRB_LAUNCH(c, k_divergence_flat, grid_for(c, (i64)n * 32, 256), 256, 0, c.V.p, c.offs.p, c.neighs.p, c.didx.p, c.dnum.p, row, first, n, c.base[D], k, c.divgv);
     }
     PRB_CUDA(cudaGetLastError());
     return PRB_OK;

@@ -17,6 +17,7 @@ static void release_all(Context& c) {
     c.meshV.release(); c.meshT.release(); c.vval.release();
     c.nMeshV = c.nMeshT = 0;
     c.xv = nullptr;
+    c.divgv = nullptr;
     c.hMeshValid = false;
 }
 
@@ -116,6 +117,7 @@ int prb_set_option(prb_context* h, const char* key, double value) {
     else if (k == "cg_max_iter") h->c.cgMaxIter = (int)value;
     else if (k == "cg_zigzag") h->c.cgZigzag = (int)value;
     else if (k == "refine_bound_check") h->c.refineBoundCheck = (int)value;
+    else if (k == "div_mode") h->c.divMode = (int)value;
     else if (k == "refine") h->c.doRefine = (int)value;
     else if (k == "refine_implicit") h->c.refineImplicit = (int)value;
     else { set_error("unknown option " + k); return PRB_ERR_ARG; }
@@ -308,7 +310,7 @@ int64_t prb_get_array(prb_context* h, const char* name, void* dst, int64_t cap) 
     else if (s == "sg_table") D_(c.sgTab.p, c.sgTab.bytes());
     else if (s == "p2n") D_(c.p2n.p, c.p2n.bytes());
     else if (s == "vectorfield") D_(c.V.p, c.V.bytes());
-    else if (s == "divergence") D_(c.divg.p, c.divg.bytes());
+    else if (s == "divergence") D_(c.divgv, c.divgv ? 4 * (size_t)M : 0);
     else if (s == "x") D_(c.xv, c.xv ? 4 * (size_t)M : 0);
     else if (s == "pointvalue") D_(c.pointValue.p, c.pointValue.bytes());
     else if (s == "vvalue_slots") D_(c.vvalPtr, c.vvalPtr ? 32 * (size_t)M : 0);
@@ -367,7 +369,7 @@ int prb_set_array(prb_context* h, const char* name, const void* src, int64_t byt
     void* dst = nullptr;
     size_t want = 0;
     if (s == "vectorfield") { dst = c.V.p; want = c.V.bytes(); }
-    else if (s == "divergence") { dst = c.divg.p; want = c.divg.bytes(); }
+    else if (s == "divergence") { dst = c.divgv; want = c.divgv ? 4 * (size_t)c.M : 0; }
     else if (s == "x") { dst = c.xv; want = c.xv ? 4 * (size_t)c.M : 0; }
     else if (s == "iso") { if (bytes != 4) return PRB_ERR_ARG; std::memcpy(&c.iso, src, 4); return PRB_OK; }
     else { set_error("unknown array " + s); return PRB_ERR_ARG; }

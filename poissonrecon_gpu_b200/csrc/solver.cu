@@ -693,7 +693,7 @@ int stage_solve(Context& c) {
     P.sgStart[0] = 0;
     P.sgStart[1] = 0;
     for (int d = 2; d <= D + 1; d++) P.sgStart[d] = 1 + (c.base[d - 1] - 1) / 8;
-    P.tab4 = c.sgTab4.p; P.nSg = c.nSg; P.zigzag = c.cgZigzag; P.stencil = c.dStencil.p; P.b = c.divg.p;
+    P.tab4 = c.sgTab4.p; P.nSg = c.nSg; P.zigzag = c.cgZigzag; P.stencil = c.dStencil.p; P.b = c.divgv;
     P.x = c.xv; P.r = r.p + 7; P.p = pBuf + 7; P.pStride = (i64)padN; P.Ap = Ap.p + 7;
     P.world = c.mg.world; P.rank = c.mg.rank; P.shardFrom = mg ? c.shardFrom : D + 1;
     for (int d = 0; d <= D + 1; d++) {
