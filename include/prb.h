@@ -79,6 +79,10 @@ int prb_extract(prb_context* ctx);
 /* All four stages. */
 int prb_run(prb_context* ctx);
 
+/* Multi-GPU: the mesh is DISTRIBUTED.  Every rank marches the depth-D cells of its Morton range and a share of the refinement
+ * passes; prb_get_mesh returns the pieces this rank produced (vertex positions of the pieces back to back, triangles with GLOBAL
+ * vertex ids) and prb_get_array("mesh_layout") says where each piece sits in the whole mesh -- writing all ranks' pieces at those
+ * offsets gives exactly the single-GPU mesh.  prb_stats.n_vertices / n_triangles / the "passes" array describe the whole mesh. */
 /* Triangle mesh of the last prb_extract, in HOST memory owned by the context: vertices are
  * float32 [nv][3] in the normalised unit cube (like the reference's in-core mesh); file
  * coordinates are v*scale + center (prb_stats).  Triangles are int32 [nt][3]. */
@@ -96,7 +100,9 @@ int prb_get_stream(prb_context* ctx, void** stream);
  * and cap_bytes is large enough) and returns its size in bytes, or a negative error.  Names:
  *   points normals sorted_idx sorted_key base count key pidx pnum parent didx dnum children
  *   neighs p2n vectorfield divergence x pointvalue iso center_scale cg_iters lap_stencil
- *   vvalue_slots passes mesh_v mesh_t subdivide child0 sg_table df_table               */
+ *   vvalue_slots passes mesh_v mesh_t subdivide child0 sg_table df_table
+ *   mesh_layout (int64 [pieces][5]: pass, first global vertex, vertices, first global triangle, triangles of every
+ *   piece of the mesh this context holds, in the order they sit in prb_get_mesh's arrays)                     */
 int64_t prb_get_array(prb_context* ctx, const char* name, void* dst, int64_t cap_bytes);
 /* Overwrite an intermediate (teacher forcing in parity tests): vectorfield divergence x iso. */
 int prb_set_array(prb_context* ctx, const char* name, const void* src, int64_t bytes);
@@ -104,6 +110,12 @@ int prb_set_array(prb_context* ctx, const char* name, const void* src, int64_t b
 /* Parity / debug: re-run a single stage ("divergence", "solve", "iso", "extract") on the current
  * intermediates (used with prb_set_array for stage-by-stage comparison against the oracle). */
 int prb_run_stage(prb_context* ctx, const char* name);
+
+/* Unit-test hooks of two building blocks (host pointers in and out): the single-pass exclusive scan used by every compaction
+ * (replaces the thrust::exclusive_scan / copy_if calls of main.cu:399-4502) and the stable LSD radix sort of (key, index) pairs
+ * over the low `key_bits` bits (replaces thrust::sort_by_key, main.cu:598-602): out_idx[i] = input position of the i-th smallest key. */
+int prb_debug_scan(prb_context* ctx, const int32_t* in, int64_t n, int32_t* out, int64_t* total);
+int prb_debug_sort(prb_context* ctx, const uint64_t* keys, int64_t n, int key_bits, uint64_t* out_keys, int32_t* out_idx);
 
 /* Options: "cg_tol" (default 1e-5, CG_CUDA.cuh:347), "cg_max_iter" (10000, CG_CUDA.cuh:263),
  * "refine" (1 = run the refinement passes, main.cu:3799-4564), "refine_implicit" (1; 0 = materialise
@@ -127,6 +139,10 @@ int prb_set_option(prb_context* ctx, const char* key, double value);
  *   prb_mg_plan      host-only helper: the contiguous split of `count` units over `world` ranks
  *                    used for every sharded range (out[world + 1]). */
 int prb_mg_init(prb_context* ctx, int rank, int world, int64_t arena_bytes, void* ipc_handle_out_64_bytes);
+/* Multi-GPU input: rank r passes only ITS slice of the cloud -- the samples [plan[r], plan[r+1]) of prb_mg_plan(n_total, world), host
+ * or device pointers to the first sample of the slice -- and the slices are gathered over NVLink when the octree is built.  (With
+ * prb_set_points every rank passes the whole cloud.)  All ranks must use the same entry point. */
+int prb_set_points_sharded(prb_context* ctx, const float* xyz_slice, const float* normals_slice, int64_t n_total);
 int prb_mg_set_peer(prb_context* ctx, int peer_rank, const void* ipc_handle_64_bytes);
 int prb_mg_barrier(prb_context* ctx);
 int prb_mg_plan(int64_t count, int world, int64_t* out);

@@ -41,6 +41,11 @@ void prbio_free(void* p);
 int prbio_write_mesh(const char* path, const float* vertices, int64_t nv, const int32_t* triangles, int64_t nt,
                      const float center[3], float scale, int binary);
 
+/* Optional (the reference never does this; `poisson_recon --weld`): merges vertices with bit-identical positions -- the seam
+ * vertices every pass duplicates, insertTriangle main.cu:3220-3245 -- keeping first occurrences in order, and re-indexes the
+ * triangles in place.  *nv_out = number of vertices left. */
+int prbio_weld_mesh(float* vertices, int64_t nv, int32_t* triangles, int64_t nt, int64_t* nv_out);
+
 #ifdef __cplusplus
 }
 #endif

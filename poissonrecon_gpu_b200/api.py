@@ -74,6 +74,7 @@ def load_library():
     lib.prb_destroy.restype = None
     lib.prb_last_error.restype = ctypes.c_char_p
     lib.prb_set_points.argtypes = [vp, vp, vp, cll]
+    lib.prb_set_points_sharded.argtypes = [vp, vp, vp, cll]
     for f in ("prb_build_octree", "prb_splat", "prb_solve", "prb_extract", "prb_run"):
         getattr(lib, f).argtypes = [vp]
     lib.prb_get_mesh.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(cll), ctypes.POINTER(vp), ctypes.POINTER(cll)]
@@ -91,14 +92,16 @@ def load_library():
     lib.prb_mg_plan.argtypes = [cll, ci, ctypes.POINTER(cll)]
     lib.prb_host_tables.argtypes = [ci, ctypes.c_char_p, vp, cll]
     lib.prb_host_tables.restype = cll
+    lib.prb_debug_scan.argtypes = [vp, vp, cll, vp, ctypes.POINTER(cll)]
+    lib.prb_debug_sort.argtypes = [vp, vp, cll, ci, vp, vp]
     _lib = lib
     return lib
 
 
-EXPORTS = ["prb_create", "prb_destroy", "prb_last_error", "prb_set_points", "prb_build_octree", "prb_splat", "prb_solve",
+EXPORTS = ["prb_create", "prb_destroy", "prb_last_error", "prb_set_points", "prb_set_points_sharded", "prb_build_octree", "prb_splat", "prb_solve",
            "prb_extract", "prb_run", "prb_get_mesh", "prb_get_mesh_device", "prb_get_stats", "prb_get_array", "prb_set_array",
            "prb_set_option", "prb_run_stage", "prb_get_stream", "prb_host_tables", "prb_mg_init", "prb_mg_set_peer", "prb_mg_barrier",
-           "prb_mg_plan"]
+           "prb_mg_plan", "prb_debug_scan", "prb_debug_sort"]
 
 
 class PoissonRecon:
@@ -136,6 +139,17 @@ class PoissonRecon:
         else:
             px, pn = int(xyz), int(normals)
         self._check(self.lib.prb_set_points(self.h, px, pn, n))
+
+    def set_points_sharded(self, xyz_slice, normals_slice, n_total: int):
+        """Multi-GPU: this rank's slice [n_total*rank/world, n_total*(rank+1)/world) of the cloud (numpy arrays or raw pointers)."""
+        if isinstance(xyz_slice, np.ndarray):
+            xyz_slice = np.ascontiguousarray(xyz_slice, np.float32)
+            normals_slice = np.ascontiguousarray(normals_slice, np.float32)
+            self._keep = (xyz_slice, normals_slice)
+            px, pn = xyz_slice.ctypes.data, normals_slice.ctypes.data
+        else:
+            px, pn = int(xyz_slice), int(normals_slice)
+        self._check(self.lib.prb_set_points_sharded(self.h, px, pn, int(n_total)))
 
     def build_octree(self):
         self._check(self.lib.prb_build_octree(self.h))
@@ -216,11 +230,49 @@ class PoissonRecon:
         t = np.ctypeslib.as_array(ctypes.cast(pt, ctypes.POINTER(ctypes.c_int32)), (nt.value, 3)) if nt.value else np.zeros((0, 3), np.int32)
         return v, t
 
+    def mesh_layout(self):
+        """int64 [pieces, 5]: (pass, first global vertex, vertices, first global triangle, triangles) of the pieces this context holds."""
+        return self.get("mesh_layout", "<i8").reshape(-1, 5)
+
+    def mesh_global(self, group=None):
+        """The whole mesh on every rank of a torch.distributed group (1 GPU: same as mesh()): pieces gathered and written at their global offsets."""
+        v, t = self.mesh()
+        lay = self.mesh_layout()
+        st = self.stats()
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return v, t
+        parts = [None] * dist.get_world_size(group)
+        dist.all_gather_object(parts, (lay, v, t), group=group)
+        V = np.zeros((st["n_vertices"], 3), np.float32)
+        T = np.zeros((st["n_triangles"], 3), np.int32)
+        for lay_r, v_r, t_r in parts:
+            av = at = 0
+            for _, vb, nv, tb, nt in lay_r.tolist():
+                V[vb:vb + nv] = v_r[av:av + nv]
+                T[tb:tb + nt] = t_r[at:at + nt]
+                av += nv; at += nt
+        return V, T
+
     def mesh_device_size(self):
         nv, nt = ctypes.c_int64(), ctypes.c_int64()
         pv, pt = ctypes.c_void_p(), ctypes.c_void_p()
         self._check(self.lib.prb_get_mesh_device(self.h, ctypes.byref(pv), ctypes.byref(nv), ctypes.byref(pt), ctypes.byref(nt)))
         return nv.value, nt.value
+
+    # ---- unit-test hooks
+    def debug_scan(self, a):
+        a = np.ascontiguousarray(a, np.int32)
+        out = np.empty_like(a)
+        tot = ctypes.c_int64()
+        self._check(self.lib.prb_debug_scan(self.h, a.ctypes.data, a.size, out.ctypes.data, ctypes.byref(tot)))
+        return out, tot.value
+
+    def debug_sort(self, keys, key_bits: int):
+        keys = np.ascontiguousarray(keys, np.uint64)
+        ok, oi = np.empty_like(keys), np.empty(keys.size, np.int32)
+        self._check(self.lib.prb_debug_sort(self.h, keys.ctypes.data, keys.size, key_bits, ok.ctypes.data, oi.ctypes.data))
+        return ok, oi
 
     def get(self, name: str, dtype):
         nb = self.lib.prb_get_array(self.h, name.encode(), None, 0)

@@ -118,11 +118,20 @@ struct HBuf {
 // the arena header -- no host round trip, no NCCL call on the data path.
 constexpr int kMaxRanks = 8;
 constexpr size_t kMgHeaderBytes = 16384;     // flags + dot-product slots
+struct MgCgLine {                             // one 128-byte line per (barrier parity, sender): the sender's per-depth partial sums and,
+    double v[14];                             // written last with release semantics, the barrier epoch they belong to
+    unsigned epoch;
+    unsigned pad[3];
+};
 struct MgHeader {
     unsigned flags[kMaxRanks][32];            // flags[r][0]: last epoch rank r has arrived at (one 128-B line per writer)
-    double slots[2][kMaxRanks][32];           // dot-product partials [parity][rank][kind*16 + depth]
+    double slots[2][kMaxRanks][32];           // partial sums of the stages between kernels (iso value, mesh totals) [parity][rank][slot]
+    MgCgLine cg[2][kMaxRanks];                // in-kernel barriers of the CG solve (solver.cu cg_sync)
+    int xchg[2][kMaxRanks][64];               // small integer all-gathers between kernels (mg_exchange_ints), double buffered
     int error;                                // set by a kernel whose peer wait timed out
 };
+static_assert(sizeof(MgCgLine) == 128, "one line per sender");
+static_assert(sizeof(MgHeader) <= kMgHeaderBytes, "arena header too small");
 struct MgDev {                                // passed by value to kernels
     int rank, world;
     MgHeader* hdr;                            // own header
@@ -135,6 +144,8 @@ struct MgState {
     char* peer[kMaxRanks] = {nullptr};        // peer[rank] == arena
     bool peerOpen[kMaxRanks] = {false};
     unsigned epoch = 0;                       // last epoch used (host-tracked, identical on all ranks)
+    unsigned xchgCount = 0;                   // number of mg_exchange_ints calls so far (buffer parity)
+    unsigned cgEpoch = 0;                     // the same for the in-kernel barriers of the CG solve (their own flag words)
     int minShardRows = 65536;                 // depths with fewer rows stay replicated
     bool active() const { return world > 1; }
     void reset_allocs() { used = kMgHeaderBytes; }
@@ -154,12 +165,28 @@ struct MgState {
     }
 };
 int mg_barrier(struct Context& c);            // device-side flag barrier on the context stream (all ranks must call it)
+// all-gather of a buffer that lives at the same arena offset on every rank and whose element range [lo[r], lo[r+1]) was produced by
+// rank r: barrier, pull the other ranks' ranges over NVLink (each rank starts with its successor), barrier
+// all-gather of up to 64 ints per rank through the arena headers: all[r * stride + k] = value k of rank r (all ranks must call it)
+int mg_exchange_ints(struct Context& c, const int* mine, int n, int* all, int stride = -1);
+int mg_allgather(struct Context& c, size_t arenaOffset, size_t elemBytes, const long long* lo /* [world + 1] */);
 
 // One pass (the main depth-D pass or a refinement pass) of mesh output.
 struct PassRecord { int kind, nv, nt; };   // kind: 0 main, 1 coarse (single root), 2 batched per depth
 
+// look-back scan state of a context (scan.cuh)
+struct ScanWork {
+    unsigned long long* desc = nullptr;      // [maxTiles]
+    unsigned* ticket = nullptr;              // [1] + total [1] (as int)
+    size_t maxTiles = 0;
+    unsigned epoch = 0;
+};
 struct Context {
     int device = 0, D = 0;
+    ScanWork scanWork;             // scan.cuh: look-back descriptors + ticket (views of scanDesc / scanTicket)
+    DBuf<unsigned long long> scanDesc;
+    DBuf<unsigned> scanTicket;
+    int* hScanTotal = nullptr;     // pinned host word the scan totals are copied into
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[10];
     int stage = 0;                 // 0 none, 1 points, 2 octree, 3 splat, 4 solve, 5 extract
@@ -176,6 +203,10 @@ struct Context {
     // ---- samples
     i64 N = 0;
     DBuf<float> rawP, rawN;        // file coordinates, [N][3]
+    float *rawPp = nullptr, *rawNp = nullptr;   // where they live: rawP.p / rawN.p, or the peer-mapped arena (prb_set_points_sharded)
+    bool rawSharded = false;       // multi-GPU: only this rank's slice has been uploaded; stage_octree gathers the others over NVLink
+    size_t mgRawPOff = 0, mgRawNOff = 0, mgVOff = 0;
+    float* Vp = nullptr;           // vector field of the current run (V.p, or inside the arena when splat is sharded)
     DBuf<float> P, Nr;             // Morton-sorted, normalised samples / rescaled normals [N][3]
     DBuf<u64> sortedKey;           // Morton key per sorted sample
     DBuf<int> sortedIdx;           // sorted position -> input index
@@ -215,7 +246,10 @@ struct Context {
     HBuf<float> hMeshV;            // pinned host copies (prb_get_mesh)
     HBuf<int> hMeshT;
     bool hMeshValid = false;
-    std::vector<PassRecord> passes;
+    std::vector<PassRecord> passes;            // every pass of the reconstruction (all ranks), in output order
+    struct PieceRecord { long long pass, vBase, nv, tBase, nt; };
+    std::vector<PieceRecord> layout;           // the pieces of the mesh THIS context holds: global vertex / triangle offsets (1 GPU: all passes)
+    i64 nGlobalV = 0, nGlobalT = 0;            // size of the whole mesh (== nMeshV / nMeshT on one GPU)
     std::vector<int> subdivide;    // host copy of the refined leaves (node ids)
     DBuf<float> vval;              // [M][8] corner values (valid at the owner's slot)
     // grow-only workspace of the refinement passes (kept across runs)

@@ -74,12 +74,12 @@ __global__ void __launch_bounds__(128) k_splat_weights(const float* __restrict__
 // slot then adds its terms in the reference's order: neighbour j = 0..26, samples ascending.
 __global__ void __launch_bounds__(128) k_splat(const float* __restrict__ W, const float* __restrict__ Nr,
                                                const int* __restrict__ neighs, const int* __restrict__ pidx, const int* __restrict__ pnum,
-                                               int baseD, int countD, float* __restrict__ V) {
+                                               int baseD, int gFirst, int gEnd, float* __restrict__ V) {
     __shared__ int2 sInfo[4][4][64];
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    const int nGroups = countD >> 3, nSteps = (nGroups + 3) >> 2;
+    const int nGroups = gEnd, nSteps = (gEnd - gFirst + 3) >> 2;       // sibling groups [gFirst, gEnd) of depth D (multi-GPU: this rank's share)
     for (int st = blockIdx.x * 4 + wp; st < nSteps; st += gridDim.x * 4) {
-        const int g0 = 4 * st;
+        const int g0 = gFirst + 4 * st;
         __syncwarp();
 #pragma unroll
         for (int rr = 0; rr < 8; rr++) {
@@ -480,32 +480,89 @@ __global__ void __launch_bounds__(256) k_profile_up(const int* __restrict__ chil
         here[e] = s;
     }
 }
-// b_o for the nodes of ONE depth d <= D-2 from the profiles of their 27 neighbours: one warp per node, the 27 x 3 x k
-// products flattened over the lanes, fixed-order warp reduction
-__global__ void __launch_bounds__(256) k_div_coarse(const int* __restrict__ neighs, const double* __restrict__ prof, const float* __restrict__ row, int base, int count, int lk,
-                                                    float* __restrict__ divg) {
-    const int lane = threadIdx.x & 31, k = 1 << lk;
-    const int total = 81 << lk;
+// b_o for the nodes of ONE depth d <= D-2 from the profiles of their 27 neighbours.
+// k = 2^(D-d) <= 8: one warp per node, lane j = neighbour j: its 3k profile entries are one contiguous run of doubles.
+template <int LK>
+__global__ void __launch_bounds__(256) k_div_coarse_small(const int* __restrict__ neighs, const double* __restrict__ prof, const float* __restrict__ row, int base, int count,
+                                                          float* __restrict__ divg) {
+    constexpr int K = 1 << LK;
+    const int lane = threadIdx.x & 31;
+    double T[3 * K];                                      // the 3k table values this lane's direction digits select, as doubles
+    {
+        const int j = lane < 27 ? lane : 0;
+        const int dj[3] = {j / 9, (j / 3) % 3, j % 3};
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int t = 0; t < K; t++) T[a * K + t] = (double)row[(dj[a] << LK) + t];
+    }
     for (int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; l < count; l += (gridDim.x * blockDim.x) >> 5) {
-        const int* nb = neighs + 27 * (i64)(base + l);
         double acc = 0.0;
-        for (int e = lane; e < total; e += 32) {
-            const int t = e & (k - 1), q = e >> lk, j = q / 3, a = q - 3 * j;
-            const int n = nb[j];
-            if (n < 0) continue;
-            const int dj = a == 0 ? j / 9 : (a == 1 ? (j / 3) % 3 : j % 3);          // d_axis(j) + 1
-            acc += (double)row[(dj << lk) + t] * prof[((size_t)(n - base) * 3 + a) * k + t];
+        if (lane < 27) {
+            const int n = neighs[27 * (i64)(base + l) + lane];
+            if (n >= 0) {
+                const double2* P = reinterpret_cast<const double2*>(prof + (size_t)(n - base) * 3 * K);
+#pragma unroll
+                for (int e = 0; e < 3 * K / 2; e++) { const double2 v = P[e]; acc += T[2 * e] * v.x; acc += T[2 * e + 1] * v.y; }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
         if (lane == 0) divg[base + l] = (float)acc;
     }
 }
+// k >= 16: a group of G threads (a warp, or a whole block for the coarse depths with few nodes and thousands of entries per
+// neighbour) per node; the 81 (neighbour, axis) runs of k entries are flattened over the group, entries fastest (coalesced)
+template <int G>
+__global__ void __launch_bounds__(256) k_div_coarse_wide(const int* __restrict__ neighs, const double* __restrict__ prof, const float* __restrict__ row, int base, int count, int lk,
+                                                         float* __restrict__ divg) {
+    __shared__ double sRed[8];
+    __shared__ int sNb[8][27];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int k = 1 << lk, total = 81 << lk;
+    const int groupsPerBlock = 256 / G, gInBlock = threadIdx.x / G, tInGroup = threadIdx.x % G;
+    for (int l0 = blockIdx.x * groupsPerBlock; l0 < count; l0 += gridDim.x * groupsPerBlock) {
+        const int l = l0 + gInBlock;
+        __syncthreads();
+        if (tInGroup < 27 && l < count) sNb[gInBlock][tInGroup] = neighs[27 * (i64)(base + l) + tInGroup];
+        __syncthreads();
+        double acc = 0.0;
+        if (l < count)
+            for (int e = tInGroup; e < total; e += G) {
+                const int t = e & (k - 1), q = e >> lk, j = q / 3, a = q - 3 * j;
+                const int n = sNb[gInBlock][j];
+                if (n < 0) continue;
+                const int dj = a == 0 ? j / 9 : (a == 1 ? (j / 3) % 3 : j % 3);          // d_axis(j) + 1
+                acc += (double)row[(dj << lk) + t] * prof[((size_t)(n - base) * 3 + a) * k + t];
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (G == 32) {
+            if (lane == 0 && l < count) divg[base + l] = (float)acc;
+        } else {
+            if (lane == 0) sRed[wp] = acc;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double v = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) v += sRed[w];
+                divg[base + l] = (float)v;
+            }
+        }
+    }
+}
 
 int stage_splat(Context& c) {
     const int D = c.D;
     cudaStream_t st = c.stream;
-    PRB_TRY(c.V.alloc(3 * (size_t)c.cnt[D], st));
+    const bool shard = c.mg.active() && D >= c.shardFrom;      // multi-GPU: a rank splats the slots of its Morton range, the field is then gathered
+    if (shard) {
+        c.Vp = c.mg.alloc<float>(3 * (size_t)c.cnt[D], &c.mgVOff);
+        if (!c.Vp) { set_error("multi-GPU arena too small for the vector field (12 bytes per depth-D slot)"); return PRB_ERR_NOMEM; }
+    } else {
+        PRB_TRY(c.V.alloc(3 * (size_t)c.cnt[D], st));
+        c.Vp = c.V.p;
+    }
     PRB_TRY(c.divg.alloc((size_t)c.M + 16, st));       // padded like x: node 1 (every sibling block) on a 32-byte boundary
     c.divgv = c.divg.p + 7;
     float width = (float)(1.0 / (1 << D));
@@ -513,8 +570,14 @@ int stage_splat(Context& c) {
         DBuf<float> W;
         PRB_TRY(W.alloc(9 * (size_t)c.N, st));
         PRB_LAUNCH(c, k_splat_weights, grid_for(c, c.N, 128, 16), 128, 0, c.dMaxDepthFn.p, c.P.p, c.p2n.p, c.offs.p + c.base[D], c.N, width, W.p);
-        PRB_LAUNCH(c, k_splat, grid_for(c, (i64)c.cnt[D], 128, 16), 128, 0, W.p, c.Nr.p, c.neighs.p, c.pidx.p, c.pnum.p, c.base[D], c.cnt[D], c.V.p);
+        const int g0 = shard ? (c.rowLo[D][c.mg.rank] - c.base[D]) / 8 : 0, g1 = shard ? (c.rowLo[D][c.mg.rank + 1] - c.base[D]) / 8 : c.cnt[D] / 8;
+        if (g1 > g0) PRB_LAUNCH(c, k_splat, grid_for(c, (i64)(g1 - g0) * 8, 128, 16), 128, 0, W.p, c.Nr.p, c.neighs.p, c.pidx.p, c.pnum.p, c.base[D], g0, g1, c.Vp);
         W.release();
+    }
+    if (shard) {
+        long long lo[kMaxRanks + 1];
+        for (int r = 0; r <= c.mg.world; r++) lo[r] = c.rowLo[D][r] - c.base[D];
+        PRB_TRY(mg_allgather(c, c.mgVOff, 12, lo));
     }
     PRB_CUDA(cudaEventRecord(c.ev[3], st));
     PRB_TRY(stage_divergence(c));
@@ -542,7 +605,7 @@ static int stage_divergence_blocks(Context& c) {
             PRB_CUDA(cudaFuncSetAttribute(k_div_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const int steps = (last - first + 3) / 4;
             const int grid = std::max(1, std::min(c.smCount, (steps + kDfWarps - 1) / kDfWarps));
-            PRB_LAUNCH(c, k_div_fine, grid, kDfWarps * 32, smem, c.V.p, c.sgTab.p, c.dDfT.p + c.tab.dfOffset[D], c.dDfT.p + c.tab.dfOffset[D - 1], c.base[D], first, last - first,
+            PRB_LAUNCH(c, k_div_fine, grid, kDfWarps * 32, smem, c.Vp, c.sgTab.p, c.dDfT.p + c.tab.dfOffset[D], c.dDfT.p + c.tab.dfOffset[D - 1], c.base[D], first, last - first,
                        leaf0, leaf1, dm0, dm1, c.divgv);
         }
     }
@@ -553,11 +616,17 @@ static int stage_divergence_blocks(Context& c) {
     for (int d = D - 2; d >= 0; --d) { off[d] = total; total += (size_t)c.cnt[d] * 3 * ((size_t)1 << (D - d)); }
     DBuf<double> prof;
     PRB_TRY(prof.alloc(total, st));
-    PRB_LAUNCH(c, k_profile_d2, grid_for(c, (i64)c.cnt[D - 2] * 8, 256), 256, 0, c.V.p, c.child0.p, c.base[D - 2], c.cnt[D - 2], c.base[D], prof.p + off[D - 2]);
+    PRB_LAUNCH(c, k_profile_d2, grid_for(c, (i64)c.cnt[D - 2] * 8, 256), 256, 0, c.Vp, c.child0.p, c.base[D - 2], c.cnt[D - 2], c.base[D], prof.p + off[D - 2]);
     for (int d = D - 3; d >= 0; --d)
         PRB_LAUNCH(c, k_profile_up, grid_for(c, (i64)c.cnt[d] * 3 * ((i64)1 << (D - d)), 256), 256, 0, c.child0.p, c.base[d], c.cnt[d], c.base[d + 1], D - d, prof.p + off[d + 1], prof.p + off[d]);
-    for (int d = D - 2; d >= 0; --d)
-        PRB_LAUNCH(c, k_div_coarse, grid_for(c, (i64)c.cnt[d] * 32, 256), 256, 0, c.neighs.p, prof.p + off[d], c.dDfT.p + c.tab.dfOffset[d], c.base[d], c.cnt[d], D - d, c.divgv);
+    for (int d = D - 2; d >= 0; --d) {
+        const float* row = c.dDfT.p + c.tab.dfOffset[d];
+        const int lk = D - d;
+        if (lk == 2) PRB_LAUNCH(c, k_div_coarse_small<2>, grid_for(c, (i64)c.cnt[d] * 32, 256), 256, 0, c.neighs.p, prof.p + off[d], row, c.base[d], c.cnt[d], c.divgv);
+        else if (lk == 3) PRB_LAUNCH(c, k_div_coarse_small<3>, grid_for(c, (i64)c.cnt[d] * 32, 256), 256, 0, c.neighs.p, prof.p + off[d], row, c.base[d], c.cnt[d], c.divgv);
+        else if (lk == 4) PRB_LAUNCH(c, k_div_coarse_wide<32>, grid_for(c, (i64)c.cnt[d] * 32, 256), 256, 0, c.neighs.p, prof.p + off[d], row, c.base[d], c.cnt[d], lk, c.divgv);
+        else PRB_LAUNCH(c, k_div_coarse_wide<256>, std::max(1, std::min(c.cnt[d], c.smCount * 8)), 256, 0, c.neighs.p, prof.p + off[d], row, c.base[d], c.cnt[d], lk, c.divgv);
+    }
     prof.release();
     PRB_CUDA(cudaGetLastError());
     return PRB_OK;
@@ -583,7 +652,7 @@ int stage_divergence(Context& c) {
         i64 nItems = 0;
         PRB_TRY(exclusive_scan(c, items.p, itemBase.p, nCoarse, &nItems));
         if (nItems > 0)
-            PRB_LAUNCH(c, k_divergence_scatter, (int)nItems, 256, 0, c.V.p, c.offs.p, c.neighs.p, c.didx.p, c.dnum.p, c.dDfT.p, c.dDfOffset.p, itemBase.p,
+            PRB_LAUNCH(c, k_divergence_scatter, (int)nItems, 256, 0, c.Vp, c.offs.p, c.neighs.p, c.didx.p, c.dnum.p, c.dDfT.p, c.dDfOffset.p, itemBase.p,
                        nCoarse, c.base[D], D, accum.p);
         PRB_LAUNCH(c, k_divergence_finish, grid_for(c, nCoarse, 256), 256, 0, accum.p, nCoarse, c.divgv);
         items.release(); itemBase.release(); accum.release();
@@ -597,11 +666,11 @@ int stage_divergence(Context& c) {
         const int n = sh ? c.rowLo[d][c.mg.rank + 1] - first : c.cnt[d];
         if (n <= 0) continue;
         if (d == D)
-            PRB_LAUNCH(c, k_divergence_leaf, grid_for(c, n, 256), 256, 0, c.V.p, c.neighs.p, row, c.base[D], first, n, c.divgv);
+            PRB_LAUNCH(c, k_divergence_leaf, grid_for(c, n, 256), 256, 0, c.Vp, c.neighs.p, row, c.base[D], first, n, c.divgv);
         else if (d == D - 1)
-            PRB_LAUNCH(c, k_divergence_dm1, grid_for(c, n, 256), 256, 0, c.V.p, c.neighs.p, c.child0.p, row, first, n, c.base[D], c.divgv);
+            PRB_LAUNCH(c, k_divergence_dm1, grid_for(c, n, 256), 256, 0, c.Vp, c.neighs.p, c.child0.p, row, first, n, c.base[D], c.divgv);
         else
-            PRB_LAUNCH(c, k_divergence_flat, grid_for(c, (i64)n * 32, 256), 256, 0, c.V.p, c.offs.p, c.neighs.p, c.didx.p, c.dnum.p, row, first, n, c.base[D], k, c.divgv);
+            PRB_LAUNCH(c, k_divergence_flat, grid_for(c, (i64)n * 32, 256), 256, 0, c.Vp, c.offs.p, c.neighs.p, c.didx.p, c.dnum.p, row, first, n, c.base[D], k, c.divgv);
     }
     PRB_CUDA(cudaGetLastError());
     return PRB_OK;

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "mg_device.cuh"
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <mutex>
 #include "mc_case_table.h"
@@ -214,13 +215,36 @@ __device__ __forceinline__ int edge_owner(const Topo& T, int id, int e, int& e2)
     e2 = (o << 2) | ((e & 1) ^ (bm & 1)) | ((((e >> 1) & 1) ^ ((bm >> 1) & 1)) << 1);
     return best;
 }
-// the 8 corner values of a cell in ring order; vals holds 8 floats per id (bit order) at the owner
-__device__ __forceinline__ void cell_corner_values(const Topo& T, int id, const float* __restrict__ vals, int valBase, float v[8]) {
+// Corner values live at the owner: 8 floats per id (bit order).  Multi-GPU: the ids [lo[r], lo[r+1]) were evaluated by rank r and are
+// read from its peer-mapped arena (plain NVLink loads; only cells at a shard boundary ever touch another rank's values).
+struct ValView {
+    const float* p[kMaxRanks];     // p[r][8 * (id - valBase) + slot]; world == 1: everything in p[0]
+    int valBase, world;
+    int lo[kMaxRanks + 1];
+};
+static ValView local_view(const float* vals, int valBase) {
+    ValView W;
+    for (int r = 0; r < kMaxRanks; r++) W.p[r] = vals;
+    W.valBase = valBase; W.world = 1;
+    for (int r = 0; r <= kMaxRanks; r++) W.lo[r] = 0;
+    return W;
+}
+__device__ __forceinline__ int view_rank(const int* lo, int world, int id) {
+    int r = 0;
+    while (r + 1 < world && id >= lo[r + 1]) r++;
+    return r;
+}
+__device__ __forceinline__ float val_at(const ValView& W, int ow, int slot) {
+    const int r = W.world > 1 ? view_rank(W.lo, W.world, ow) : 0;
+    return W.p[r][8 * (i64)(ow - W.valBase) + slot];
+}
+// the 8 corner values of a cell in ring order
+__device__ __forceinline__ void cell_corner_values(const Topo& T, int id, const ValView& W, float v[8]) {
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         int j = ring_to_bits(r), m;
         int ow = corner_owner(T, id, j, m);
-        v[r] = vals[8 * (i64)(ow - valBase) + (j ^ m)];
+        v[r] = val_at(W, ow, j ^ m);
     }
 }
 
@@ -468,12 +492,12 @@ __global__ void __launch_bounds__(kVsWarps * 32) k_vertex_values_stream(Topo T, 
 
 // ------------------------------------------------------------------ classification of depth-D cells
 // per cell: MC case, triangle count, mask of OWNED crossed edges (v1*v2 <= 0, main.cu:2475)
-__global__ void __launch_bounds__(128) k_classify(Topo T, const float* __restrict__ vals, int valBase, unsigned char* __restrict__ cat,
+__global__ void __launch_bounds__(128) k_classify(Topo T, const __grid_constant__ ValView W, unsigned char* __restrict__ cat,
                                                   int* __restrict__ ntri, unsigned short* __restrict__ emask, int* __restrict__ nvtx) {
     for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < T.nCells; l += gridDim.x * blockDim.x) {
         int id = T.cellBase + l;
         float v[8];
-        cell_corner_values(T, id, vals, valBase, v);
+        cell_corner_values(T, id, W, v);
         int c = 0;
 #pragma unroll
         for (int r = 0; r < 8; r++) if (v[r] < 0.f) c |= 1 << r;
@@ -492,7 +516,7 @@ __global__ void __launch_bounds__(128) k_classify(Topo T, const float* __restric
     }
 }
 // interpolated vertices (main.cu:2584-2627), written at vbase[cell] + rank of the edge inside the mask
-__global__ void __launch_bounds__(128) k_emit_vertices(Topo T, const float* __restrict__ vals, int valBase, const ushort4* __restrict__ cellOffs, int D,
+__global__ void __launch_bounds__(128) k_emit_vertices(Topo T, const __grid_constant__ ValView W, const ushort4* __restrict__ cellOffs, int D,
                                                        const unsigned short* __restrict__ emask, const int* __restrict__ vbase, float* __restrict__ outV) {
     const float w = 1.0f / (float)(1 << D);
     for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < T.nCells; l += gridDim.x * blockDim.x) {
@@ -500,7 +524,7 @@ __global__ void __launch_bounds__(128) k_emit_vertices(Topo T, const float* __re
         if (!m) continue;
         int id = T.cellBase + l;
         float v[8];
-        cell_corner_values(T, id, vals, valBase, v);
+        cell_corner_values(T, id, W, v);
         ushort4 o = cellOffs[l];
         int k = 0;
         for (int e = 0; e < 12; e++) {
@@ -520,10 +544,19 @@ __global__ void __launch_bounds__(128) k_emit_vertices(Topo T, const float* __re
         }
     }
 }
-// triangles (main.cu:2699-2757) + marking of faces touched by the surface and of their parent faces
+// triangles (main.cu:2699-2757) + marking of faces touched by the surface and of their parent faces.  A vertex id is
+// (first vertex of the owner cell's rank) + (the owner's offset inside that rank) + (rank of the edge inside the owner's mask);
+// multi-GPU: the owner of an edge on a shard boundary belongs to the previous rank, whose offset / mask arrays are read in place.
+struct TriView {
+    const int* vbase[kMaxRanks];             // [id - idxBase] per rank
+    const unsigned short* emask[kMaxRanks];
+    int vtxBase[kMaxRanks];                  // first vertex id of every rank's cells
+    int idxBase, world;
+    int lo[kMaxRanks + 1];
+};
 __global__ void __launch_bounds__(128) k_emit_triangles(Topo T, const unsigned char* __restrict__ cat, const int* __restrict__ ntri, const int* __restrict__ tbase,
-                                                        const unsigned short* __restrict__ emask, const int* __restrict__ vbase, int* __restrict__ outT,
-                                                        int markFaces, int D, const int* __restrict__ parent, const ushort4* __restrict__ offs,
+                                                        const __grid_constant__ TriView V, int* __restrict__ outT,
+                                                        int markFaces, int nUpper, const int* __restrict__ parent, const ushort4* __restrict__ offs,
                                                         unsigned* __restrict__ fmark) {
     for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < T.nCells; l += gridDim.x * blockDim.x) {
         int nt = ntri[l];
@@ -534,8 +567,9 @@ __global__ void __launch_bounds__(128) k_emit_triangles(Topo T, const unsigned c
             int e = cMcTri[c][j], e2;
             used |= 1u << e;
             int ow = edge_owner(T, id, e, e2);
-            int ol = ow - T.cellBase;
-            outT[3 * (i64)tbase[l] + j] = vbase[ol] + __popc((unsigned)emask[ol] & ((1u << e2) - 1u));
+            const int r = V.world > 1 ? view_rank(V.lo, V.world, ow) : 0;
+            const int ol = ow - V.idxBase;
+            outT[3 * (i64)tbase[l] + j] = V.vtxBase[r] + V.vbase[r][ol] + __popc((unsigned)V.emask[r][ol] & ((1u << e2) - 1u));
         }
         if (!markFaces) continue;
         for (int f = 0; f < 6; f++) {
@@ -544,15 +578,15 @@ __global__ void __launch_bounds__(128) k_emit_triangles(Topo T, const unsigned c
             // face (node, f) and the chain of parent faces (main.cu:2738-2755).  A face is shared
             // by the two cells across it; its hasParentFace flag was set by its OWNER (min index)
             // with the reference's parentFaceKind table (MarchingCubes.cuh:708-717: child code
-            // read as x=bit0, literal row 7).
+            // read as x=bit0, literal row 7).  Only nodes above depth D are ever tested (k_find_subdivide).
             int node = id;
             int axis = f >> 1, dd[3] = {0, 0, 0};
             dd[axis] = (f & 1) ? 1 : -1;
             int jn = 9 * (dd[0] + 1) + 3 * (dd[1] + 1) + (dd[2] + 1);
             while (true) {
                 int across = T.nbr[27 * (i64)node + jn];
-                atomicOr(&fmark[node], 1u << f);
-                if (across >= 0) atomicOr(&fmark[across], 1u << (f ^ 1));
+                if (node < nUpper) atomicOr(&fmark[node], 1u << f);
+                if (across >= 0 && across < nUpper) atomicOr(&fmark[across], 1u << (f ^ 1));
                 int owner = (across >= 0 && across < node) ? across : node;
                 int fo = (owner == node) ? f : (f ^ 1);
                 int pa = parent[owner];
@@ -569,18 +603,21 @@ __global__ void __launch_bounds__(128) k_emit_triangles(Topo T, const unsigned c
     }
 }
 // empty leaves below depth D that must be refined (main.cu:2957-2992)
-__global__ void __launch_bounds__(128) k_find_subdivide(Topo T, int nNodes, const int* __restrict__ child0, const float* __restrict__ vval,
-                                                        const unsigned* __restrict__ fmark, int* __restrict__ flag) {
+struct MarkView { const unsigned* p[kMaxRanks]; int world; };      // face marks of every rank's own cells (multi-GPU: OR of the peers' arrays)
+__global__ void __launch_bounds__(128) k_find_subdivide(Topo T, int nNodes, const int* __restrict__ child0, const __grid_constant__ ValView W,
+                                                        const __grid_constant__ MarkView F, int* __restrict__ flag) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nNodes; i += gridDim.x * blockDim.x) {
         int f = 0;
         if (i > 0 && child0[i] < 0) {
             float v[8];
-            cell_corner_values(T, i, vval, 0, v);
+            cell_corner_values(T, i, W, v);
             int sign = (v[0] < 0.f) ? -1 : 1;
             int ht = 0;
 #pragma unroll
             for (int r = 1; r < 8; r++) if ((float)sign * v[r] < 0.f) ht = 1;
-            f = (ht || fmark[i] != 0u) ? 1 : 0;
+            unsigned fm = 0u;
+            for (int r = 0; r < F.world; r++) fm |= F.p[r][i];
+            f = (ht || fm != 0u) ? 1 : 0;
         }
         flag[i] = f;
     }
@@ -1363,32 +1400,67 @@ struct PassOut {
     int nv = 0, nt = 0;
 };
 
+// multi-GPU main pass: every rank marches the depth-D cells of its Morton range
+struct McShard {
+    ValView W;                               // corner values of depth D, per owner rank
+    int* vbaseFull = nullptr;                // [cnt[D]] in the arena (same offset on every rank): vertex offset of a cell inside its rank's part
+    unsigned short* emaskFull = nullptr;     // [cnt[D]]
+    size_t vbaseOff = 0, emaskOff = 0;
+    int rankV[kMaxRanks] = {0}, rankT[kMaxRanks] = {0};     // vertices / triangles of every rank's part (out)
+};
+
 // classification + emission shared by the main pass and the refinement passes
-static int run_mc_on_cells(Context& c, const Topo& T, const float* vals, int valBase, const ushort4* cellOffs, bool markFaces, unsigned* fmark, PassOut& out) {
+static int run_mc_on_cells(Context& c, const Topo& T, const ValView& W, const ushort4* cellOffs, bool markFaces, unsigned* fmark, PassOut& out, McShard* sh = nullptr) {
     cudaStream_t st = c.stream;
-    const int n = T.nCells;
+    const int n = T.nCells, D = c.D;
     DBuf<unsigned char> cat;
-    DBuf<unsigned short> emask;
-    DBuf<int> ntri, nvtx, tbase, vbase;
+    DBuf<unsigned short> emaskL;
+    DBuf<int> ntri, nvtx, tbase, vbaseL;
     PRB_TRY(cat.alloc((size_t)n, st));
-    PRB_TRY(emask.alloc((size_t)n, st));
     PRB_TRY(ntri.alloc((size_t)n, st));
     PRB_TRY(nvtx.alloc((size_t)n, st));
     PRB_TRY(tbase.alloc((size_t)n, st));
-    PRB_TRY(vbase.alloc((size_t)n, st));
-    PRB_LAUNCH(c, k_classify, grid_for(c, n, 128, 16), 128, 0, T, vals, valBase, cat.p, ntri.p, emask.p, nvtx.p);
+    unsigned short* emask;
+    int* vbase;
+    if (sh) {                                // this rank's window of the arena arrays
+        emask = sh->emaskFull + (T.cellBase - c.base[D]);
+        vbase = sh->vbaseFull + (T.cellBase - c.base[D]);
+    } else {
+        PRB_TRY(emaskL.alloc((size_t)n, st));
+        PRB_TRY(vbaseL.alloc((size_t)n, st));
+        emask = emaskL.p; vbase = vbaseL.p;
+    }
+    if (n) PRB_LAUNCH(c, k_classify, grid_for(c, n, 128, 16), 128, 0, T, W, cat.p, ntri.p, emask, nvtx.p);
     i64 totV = 0, totT = 0;
-    PRB_TRY(exclusive_scan(c, nvtx.p, vbase.p, n, &totV));
+    PRB_TRY(exclusive_scan(c, nvtx.p, vbase, n, &totV));
     PRB_TRY(exclusive_scan(c, ntri.p, tbase.p, n, &totT));
     out.nv = (int)totV;
     out.nt = (int)totT;
+    TriView V;
+    for (int r = 0; r < kMaxRanks; r++) { V.vbase[r] = vbase; V.emask[r] = emask; V.vtxBase[r] = 0; }
+    for (int r = 0; r <= kMaxRanks; r++) V.lo[r] = 0;
+    V.idxBase = T.cellBase; V.world = 1;
+    if (sh) {
+        // the other ranks' counts (and, with the barrier inside, their finished offset / mask arrays)
+        int mine[2] = {out.nv, out.nt}, all[kMaxRanks][2];
+        PRB_TRY(mg_exchange_ints(c, mine, 2, &all[0][0]));
+        int accV = 0;
+        for (int r = 0; r < c.mg.world; r++) {
+            sh->rankV[r] = all[r][0]; sh->rankT[r] = all[r][1];
+            V.vbase[r] = (const int*)(c.mg.peer[r] + sh->vbaseOff);
+            V.emask[r] = (const unsigned short*)(c.mg.peer[r] + sh->emaskOff);
+            V.vtxBase[r] = accV;
+            accV += all[r][0];
+        }
+        V.idxBase = c.base[D]; V.world = c.mg.world;
+        for (int r = 0; r <= c.mg.world; r++) V.lo[r] = c.rowLo[D][r];
+    }
     PRB_TRY(out.v.alloc(3 * (size_t)totV, st));
     PRB_TRY(out.t.alloc(3 * (size_t)totT, st));
-    if (totV) PRB_LAUNCH(c, k_emit_vertices, grid_for(c, n, 128, 16), 128, 0, T, vals, valBase, cellOffs, c.D, emask.p, vbase.p, out.v.p);
-    if (totT || markFaces)
-        PRB_LAUNCH(c, k_emit_triangles, grid_for(c, n, 128, 16), 128, 0, T, cat.p, ntri.p, tbase.p, emask.p, vbase.p, out.t.p, markFaces ? 1 : 0, c.D,
+    if (totV) PRB_LAUNCH(c, k_emit_vertices, grid_for(c, n, 128, 16), 128, 0, T, W, cellOffs, c.D, emask, vbase, out.v.p);
+    if (n && (totT || markFaces))
+        PRB_LAUNCH(c, k_emit_triangles, grid_for(c, n, 128, 16), 128, 0, T, cat.p, ntri.p, tbase.p, V, out.t.p, markFaces ? 1 : 0, c.base[D],
                    c.parent.p, c.offs.p, fmark);
-    cat.release(); emask.release(); ntri.release(); nvtx.release(); tbase.release(); vbase.release();
     return PRB_OK;
 }
 
@@ -1547,7 +1619,7 @@ static int refine_pass(Context& c, const int* dRoots, int nr, int rd, bool singl
     PRB_LAUNCH(c, k_vvertex_values, grid_for(c, nD, 128, 16), 128, 0, V, T, vneigh.p, vmask.p, voffs.p, c.neighs.p, c.parent.p, c.offs.p, c.xv, (const float4*)c.dBvGrid.p, (const float4*)c.dBvCell.p, c.dBaseFn.p, c.iso, sval.p);
     outs.emplace_back();
     PassOut& po = outs.back();
-    PRB_TRY(run_mc_on_cells(c, T, sval.p, T.cellBase, voffs.p, false, nullptr, po));
+    PRB_TRY(run_mc_on_cells(c, T, local_view(sval.p, T.cellBase), voffs.p, false, nullptr, po));
     if (single && po.nv == 0) {      // main.cu:4095-4103: nothing is inserted for a coarse root without crossings
         po.v.release(); po.t.release();
         outs.pop_back();
@@ -1581,16 +1653,27 @@ static int ensure_bv_tables(Context& c) {
     return PRB_OK;
 }
 
+// cost model of a refinement pass (multi-GPU: whole passes are dealt out to the ranks, largest first)
+static double pass_weight(int D, int rd, int nr) {
+    const int lv = D - rd;
+    if (lv >= 3) return (double)nr * (std::pow(8.0, lv) / 512.0 + 6.0 * std::pow(4.0, lv));     // brick certificates + the evaluated shell
+    return (double)nr * std::pow(8.0, lv) * 40.0;                                                  // materialised subtrees: every virtual cell is evaluated
+}
+
 int stage_extract(Context& c) {
     cudaStream_t st = c.stream;
     const int D = c.D, M = c.M;
     PRB_TRY(upload_mc_tables(c.device));
     c.passes.clear();
+    c.layout.clear();
     c.subdivide.clear();
     c.hMeshValid = false;
     Topo R;
     R.nbr = c.neighs.p; R.rowBase = 0; R.minId = 0; R.cellBase = c.base[D]; R.nCells = c.cnt[D];
     const bool mg = c.mg.active();
+    const int W = c.mg.world, me = c.mg.rank;
+    const bool shard = mg && D >= c.shardFrom;            // the depth-D cells (and every depth >= shardFrom) are split by Morton range
+    const int nUpper = c.base[D];
     if (mg) {
         if (!c.mgVval) c.mgVval = c.mg.alloc<float>(8 * (size_t)M, &c.mgVvalOff);
         if (!c.mgVval) { set_error("multi-GPU arena too small for the corner values (32 bytes per node)"); return PRB_ERR_NOMEM; }
@@ -1599,45 +1682,79 @@ int stage_extract(Context& c) {
         PRB_TRY(c.vval.alloc(8 * (size_t)M, st));
         c.vvalPtr = c.vval.p;
     }
+    // ---- corner values.  Multi-GPU: a rank evaluates its node range of every sharded depth (and all of the small replicated
+    // depths); the values of the depths above D are then gathered (they feed k_find_subdivide on every rank), those of depth D stay
+    // where they are: only cells on a shard boundary read a neighbour rank's values, in place over NVLink
     {
-        // multi-GPU: the sibling groups are split evenly; every rank then pulls the other ranks' values over NVLink
-        const i64 nGroups = (M - 1) / 8;
-        const int W = c.mg.world, me = c.mg.rank;
-        const int g0 = mg ? (int)((nGroups * me) / W) : 0, g1 = mg ? (int)((nGroups * (me + 1)) / W) : (int)nGroups;
-        if (g1 > g0) {
-            PRB_TRY(ensure_bv_tables(c));
-            BvTables B;
-            B.anc = (const float4*)c.dBvAnc.p; B.own = (const float4*)c.dBvOwn.p; B.cellD = (const float4*)c.dBvCell.p; B.gridLo = (const float4*)c.dBvGrid.p;
-            for (int d = 0; d <= kMaxDepth; d++) { B.ancOff[d] = c.bvAncOff[d]; B.ownOff[d] = c.bvOwnOff[d]; }
+        PRB_TRY(ensure_bv_tables(c));
+        BvTables B;
+        B.anc = (const float4*)c.dBvAnc.p; B.own = (const float4*)c.dBvOwn.p; B.cellD = (const float4*)c.dBvCell.p; B.gridLo = (const float4*)c.dBvGrid.p;
+        for (int d = 0; d <= kMaxDepth; d++) { B.ancOff[d] = c.bvAncOff[d]; B.ownOff[d] = c.bvOwnOff[d]; }
+        auto launch = [&](int g0, int g1) {
+            if (g1 <= g0) return;
             const i64 nChunks = ((i64)(g1 - g0) + kVsChunk - 1) / kVsChunk;
             PRB_LAUNCH(c, k_vertex_values_stream, grid_for(c, nChunks * 32, kVsWarps * 32, 8), kVsWarps * 32, 0, R, g0, g1 - g0, D, c.parent.p, c.child0.p, c.offs.p,
                        c.xv, c.dBaseFn.p, B, c.iso, c.vvalPtr);
-        }
-        if (mg) {
+        };
+        if (!shard) {
+            launch(0, (M - 1) / 8);
+        } else {
+            launch(0, (c.base[c.shardFrom] - 1) / 8);
+            for (int d = c.shardFrom; d <= D; d++) launch((c.rowLo[d][me] - 1) / 8, (c.rowLo[d][me + 1] - 1) / 8);
             PRB_TRY(mg_barrier(c));
             for (int qi = 1; qi < W; qi++) {          // start with the next rank: the peers are not all pulled from in the same order
                 const int q = (me + qi) % W;
-                const i64 a = (nGroups * q) / W, b = (nGroups * (q + 1)) / W;
                 const float* src = (const float*)(c.mg.peer[q] + c.mgVvalOff);
-                if (b > a) PRB_CUDA(cudaMemcpyAsync(c.vvalPtr + 8 * (1 + 8 * a), src + 8 * (1 + 8 * a), sizeof(float) * 64 * (size_t)(b - a), cudaMemcpyDeviceToDevice, st));
+                for (int d = c.shardFrom; d < D; d++) {
+                    const size_t a = (size_t)c.rowLo[d][q], b = (size_t)c.rowLo[d][q + 1];
+                    if (b > a) PRB_CUDA(cudaMemcpyAsync(c.vvalPtr + 8 * a, src + 8 * a, 32 * (b - a), cudaMemcpyDeviceToDevice, st));
+                }
             }
             PRB_TRY(mg_barrier(c));
         }
     }
-    DBuf<unsigned> fmark;
-    PRB_TRY(fmark.alloc((size_t)M, st));
-    PRB_CUDA(cudaMemsetAsync(fmark.p, 0, sizeof(unsigned) * (size_t)M, st));
+    // ---- main pass
+    DBuf<unsigned> fmarkL;
+    unsigned* fmark = nullptr;
+    size_t fmarkOff = 0;
+    if (shard) {
+        fmark = c.mg.alloc<unsigned>((size_t)nUpper, &fmarkOff);
+        if (!fmark) { set_error("multi-GPU arena too small for the face marks"); return PRB_ERR_NOMEM; }
+    } else {
+        PRB_TRY(fmarkL.alloc((size_t)nUpper, st));
+        fmark = fmarkL.p;
+    }
+    PRB_CUDA(cudaMemsetAsync(fmark, 0, sizeof(unsigned) * (size_t)nUpper, st));
     std::vector<PassOut> outs;
     outs.reserve(64);
     outs.emplace_back();
-    PRB_TRY(run_mc_on_cells(c, R, c.vvalPtr, 0, c.offs.p + c.base[D], true, fmark.p, outs.back()));
-    c.passes.push_back({0, outs.back().nv, outs.back().nt});
-    // ---- leaves to refine
-    const int nUpper = c.base[D];
+    McShard sh;
+    if (shard) {
+        sh.vbaseFull = c.mg.alloc<int>((size_t)c.cnt[D], &sh.vbaseOff);
+        sh.emaskFull = c.mg.alloc<unsigned short>((size_t)c.cnt[D], &sh.emaskOff);
+        if (!sh.vbaseFull || !sh.emaskFull) { set_error("multi-GPU arena too small for the marching-cubes offsets (6 bytes per depth-D slot)"); return PRB_ERR_NOMEM; }
+        for (int r = 0; r < kMaxRanks; r++) sh.W.p[r] = r < W ? (const float*)(c.mg.peer[r] + c.mgVvalOff) : nullptr;
+        sh.W.valBase = 0; sh.W.world = W;
+        for (int r = 0; r <= kMaxRanks; r++) sh.W.lo[r] = r <= W ? c.rowLo[D][r] : 0;
+        Topo Rm = R;
+        Rm.cellBase = c.rowLo[D][me]; Rm.nCells = c.rowLo[D][me + 1] - c.rowLo[D][me];
+        PRB_TRY(run_mc_on_cells(c, Rm, sh.W, c.offs.p + Rm.cellBase, true, fmark, outs.back(), &sh));
+        PRB_TRY(mg_barrier(c));               // every rank's face marks are complete
+    } else {
+        PRB_TRY(run_mc_on_cells(c, R, local_view(c.vvalPtr, 0), c.offs.p + c.base[D], true, fmark, outs.back()));
+        sh.rankV[0] = outs.back().nv; sh.rankT[0] = outs.back().nt;
+    }
+    const int nMainParts = shard ? W : 1;
+    // ---- leaves to refine (multi-GPU: the same list on every rank, from the OR of all ranks' face marks)
     DBuf<int> flag, excl, subIds;
     PRB_TRY(flag.alloc((size_t)nUpper, st));
     PRB_TRY(excl.alloc((size_t)nUpper, st));
-    PRB_LAUNCH(c, k_find_subdivide, grid_for(c, nUpper, 128, 16), 128, 0, R, nUpper, c.child0.p, c.vvalPtr, fmark.p, flag.p);
+    {
+        MarkView F;
+        F.world = shard ? W : 1;
+        for (int r = 0; r < kMaxRanks; r++) F.p[r] = (shard && r < W) ? (const unsigned*)(c.mg.peer[r] + fmarkOff) : fmark;
+        PRB_LAUNCH(c, k_find_subdivide, grid_for(c, nUpper, 128, 16), 128, 0, R, nUpper, c.child0.p, local_view(c.vvalPtr, 0), F, flag.p);
+    }
     i64 nSub = 0;
     PRB_TRY(exclusive_scan(c, flag.p, excl.p, nUpper, &nSub));
     PRB_TRY(subIds.alloc((size_t)nSub, st));
@@ -1647,46 +1764,114 @@ int stage_extract(Context& c) {
         PRB_CUDA(cudaMemcpyAsync(c.subdivide.data(), subIds.p, sizeof(int) * (size_t)nSub, cudaMemcpyDeviceToHost, st));
         PRB_CUDA(cudaStreamSynchronize(st));
     }
-    flag.release(); excl.release(); fmark.release();
+    flag.release(); excl.release();
+    // ---- refinement passes in the reference's order: single roots of depth 1, 2 (main.cu:3887-4202), then one batch per depth
+    // (main.cu:4211-4561).  Passes are independent of each other (vertices are shared inside a pass only), so with several GPUs whole
+    // passes are dealt out: largest estimated cost first, to the least loaded rank
+    struct PassPlan { int kind, depth, first, count, owner, out; };
+    std::vector<PassPlan> plan;
     if (c.doRefine) {
+        std::vector<int> firstOfDepth(D + 2, (int)nSub);      // node ids ascend with depth, so the list is grouped by depth already
+        size_t q = 0;
+        for (int d = 0; d <= D; d++) {
+            while (q < c.subdivide.size() && c.subdivide[q] < c.base[d]) q++;
+            firstOfDepth[d] = (int)q;
+        }
+        firstOfDepth[D + 1] = (int)nSub;
+        const int finerDepth = 3;    // main.cu:3886
+        for (int d = 1; d < finerDepth && d < D; d++)
+            for (int k = firstOfDepth[d]; k < firstOfDepth[d + 1]; k++) plan.push_back({1, d, k, 1, 0, -1});
+        for (int d = finerDepth; d < D; d++) plan.push_back({2, d, firstOfDepth[d], firstOfDepth[d + 1] - firstOfDepth[d], 0, -1});
+        if (mg) {
+            std::vector<int> order(plan.size());
+            for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pass_weight(D, plan[a].depth, plan[a].count) > pass_weight(D, plan[b].depth, plan[b].count); });
+            double load[kMaxRanks] = {0};
+            // the main pass is not free either: start from every rank's share of it
+            for (int r = 0; r < W; r++) load[r] = 0.0;
+            for (int i : order) {
+                int best = 0;
+                for (int r = 1; r < W; r++) if (load[r] < load[best]) best = r;
+                plan[i].owner = best;
+                load[best] += pass_weight(D, plan[i].depth, plan[i].count);
+            }
+        }
         DBuf<int> rootMap;
         PRB_TRY(rootMap.alloc((size_t)M, st));
         PRB_CUDA(cudaMemsetAsync(rootMap.p, 0xff, sizeof(int) * (size_t)M, st));
-        // node ids ascend with depth, so the list is grouped by depth already
-        std::vector<int> firstOfDepth(D + 2, (int)nSub);
-        {
-            size_t q = 0;
-            for (int d = 0; d <= D; d++) {
-                while (q < c.subdivide.size() && c.subdivide[q] < c.base[d]) q++;
-                firstOfDepth[d] = (int)q;
-            }
-            firstOfDepth[D + 1] = (int)nSub;
+        for (auto& pp : plan) {
+            if (mg && pp.owner != me) continue;
+            const size_t before = outs.size();
+            const size_t passesBefore = c.passes.size();
+            PRB_TRY(refine_pass(c, subIds.p + pp.first, pp.count, pp.depth, pp.kind == 1, rootMap, outs));
+            c.passes.resize(passesBefore);              // (the global list is rebuilt below)
+            pp.out = outs.size() > before ? (int)outs.size() - 1 : -1;
         }
-        const int finerDepth = 3;    // main.cu:3886
-        for (int d = 1; d < finerDepth && d < D; d++)                      // coarse roots: one pass each (main.cu:3887-4202)
-            for (int q = firstOfDepth[d]; q < firstOfDepth[d + 1]; q++) PRB_TRY(refine_pass(c, subIds.p + q, 1, d, true, rootMap, outs));
-        for (int d = finerDepth; d < D; d++)                               // batched per depth (main.cu:4211-4561)
-            PRB_TRY(refine_pass(c, subIds.p + firstOfDepth[d], firstOfDepth[d + 1] - firstOfDepth[d], d, false, rootMap, outs));
         rootMap.release();
     }
     subIds.release();
-    // ---- concatenate passes (insertTriangle, main.cu:3220-3245: indices offset by the vertices so far)
+    // ---- counts of every pass on every rank -> global pass list, vertex / triangle bases of the local pieces
+    const int nPlan = (int)plan.size();
+    std::vector<int> pnv(nPlan, 0), pnt(nPlan, 0);
+    for (int i = 0; i < nPlan; i++)
+        if (plan[i].out >= 0) { pnv[i] = outs[plan[i].out].nv; pnt[i] = outs[plan[i].out].nt; }
+    if (mg) {
+        for (int i0 = 0; i0 < nPlan; i0 += 32) {
+            const int n = std::min(32, nPlan - i0);
+            int mine[64], all[kMaxRanks][64];
+            for (int k = 0; k < n; k++) { mine[2 * k] = pnv[i0 + k]; mine[2 * k + 1] = pnt[i0 + k]; }
+            PRB_TRY(mg_exchange_ints(c, mine, 2 * n, &all[0][0], 64));
+            for (int k = 0; k < n; k++) { pnv[i0 + k] = all[plan[i0 + k].owner][2 * k]; pnt[i0 + k] = all[plan[i0 + k].owner][2 * k + 1]; }
+        }
+        if (nPlan == 0) PRB_TRY(mg_barrier(c));      // nobody leaves while a peer may still read this rank's arena
+    }
+    i64 gv = 0, gt = 0;
+    struct Piece { int out; i64 vBase, tBase; int nv, nt, pass; };
+    std::vector<Piece> mine;
+    {
+        int mainV = 0, mainT = 0;
+        for (int r = 0; r < nMainParts; r++) {
+            if (r == (shard ? me : 0)) mine.push_back({0, gv, gt, outs[0].nv, outs[0].nt, 0});
+            gv += sh.rankV[r]; gt += sh.rankT[r];
+            mainV += sh.rankV[r]; mainT += sh.rankT[r];
+        }
+        c.passes.push_back({0, mainV, mainT});
+    }
+    for (int i = 0; i < nPlan; i++) {
+        if (plan[i].kind == 1 && pnv[i] == 0) continue;      // main.cu:4095-4103: nothing is inserted for a coarse root without crossings
+        if (plan[i].out >= 0) mine.push_back({plan[i].out, gv, gt, pnv[i], pnt[i], (int)c.passes.size()});
+        c.passes.push_back({plan[i].kind, pnv[i], pnt[i]});
+        gv += pnv[i]; gt += pnt[i];
+    }
+    if (gv > 0x7fffffffll / 3 || gt > 0x7fffffffll / 3) { set_error("mesh too large for 32-bit indices"); return PRB_ERR_NOMEM; }
+    // ---- this rank's pieces, concatenated (insertTriangle, main.cu:3220-3245: indices offset by the vertices so far)
     i64 tv = 0, tt = 0;
-    for (auto& o : outs) { tv += o.nv; tt += o.nt; }
+    for (auto& pc : mine) { tv += pc.nv; tt += pc.nt; }
     PRB_TRY(c.meshV.alloc(3 * (size_t)tv, st));
     PRB_TRY(c.meshT.alloc(3 * (size_t)tt, st));
     i64 av = 0, at = 0;
-    for (auto& o : outs) {
-        if (o.nv) PRB_CUDA(cudaMemcpyAsync(c.meshV.p + 3 * av, o.v.p, 12 * (size_t)o.nv, cudaMemcpyDeviceToDevice, st));
-        if (o.nt) {
-            PRB_CUDA(cudaMemcpyAsync(c.meshT.p + 3 * at, o.t.p, 12 * (size_t)o.nt, cudaMemcpyDeviceToDevice, st));
-            if (av) PRB_LAUNCH(c, k_offset_triangles, grid_for(c, 3 * (i64)o.nt, 256), 256, 0, c.meshT.p + 3 * at, 3 * (i64)o.nt, (int)av);
+    for (auto& pc : mine) {
+        PassOut& o = outs[pc.out];
+        if (pc.nv) PRB_CUDA(cudaMemcpyAsync(c.meshV.p + 3 * av, o.v.p, 12 * (size_t)pc.nv, cudaMemcpyDeviceToDevice, st));
+        if (pc.nt) {
+            PRB_CUDA(cudaMemcpyAsync(c.meshT.p + 3 * at, o.t.p, 12 * (size_t)pc.nt, cudaMemcpyDeviceToDevice, st));
+            // (the triangles of the main pass already carry global vertex ids)
+            if (pc.pass != 0 && pc.vBase) PRB_LAUNCH(c, k_offset_triangles, grid_for(c, 3 * (i64)pc.nt, 256), 256, 0, c.meshT.p + 3 * at, 3 * (i64)pc.nt, (int)pc.vBase);
         }
-        av += o.nv; at += o.nt;
-        o.v.release(); o.t.release();
+        c.layout.push_back({(i64)pc.pass, pc.vBase, (i64)pc.nv, pc.tBase, (i64)pc.nt});
+        av += pc.nv; at += pc.nt;
     }
+    for (auto& o : outs) { o.v.release(); o.t.release(); }
     c.nMeshV = tv;
     c.nMeshT = tt;
+    c.nGlobalV = gv;
+    c.nGlobalT = gt;
+    if (mg) {
+        int err = 0;
+        PRB_CUDA(cudaMemcpyAsync(&err, &((MgHeader*)c.mg.arena)->error, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PRB_CUDA(cudaStreamSynchronize(st));
+        if (err) { set_error("multi-GPU extraction: timed out waiting for a peer"); return PRB_ERR_CUDA; }
+    }
     PRB_CUDA(cudaGetLastError());
     return PRB_OK;
 }

@@ -18,6 +18,42 @@ int mg_barrier(Context& c) {
     return PRB_OK;
 }
 
+struct XchgVals { int v[64]; };
+__global__ void k_mg_publish_ints(MgDev mg, int parity, XchgVals vals, int n) {
+    const int t = threadIdx.x;
+    if (t < n)
+        for (int r = 0; r < mg.world; r++) mg.peerHdr[r]->xchg[parity][mg.rank][t] = vals.v[t];
+}
+int mg_exchange_ints(Context& c, const int* mine, int n, int* all, int stride) {
+    if (n < 0 || n > 64) { set_error("mg_exchange_ints: at most 64 values"); return PRB_ERR_ARG; }
+    if (stride < 0) stride = n;
+    if (!c.mg.active()) { for (int k = 0; k < n; k++) all[k] = mine[k]; return PRB_OK; }
+    XchgVals v;
+    for (int k = 0; k < 64; k++) v.v[k] = k < n ? mine[k] : 0;
+    const int parity = (int)(c.mg.xchgCount++ & 1u);
+    PRB_LAUNCH(c, k_mg_publish_ints, 1, 64, 0, c.mg.dev(), parity, v, n);
+    PRB_TRY(mg_barrier(c));
+    int host[kMaxRanks][64];
+    PRB_CUDA(cudaMemcpyAsync(host, &((MgHeader*)c.mg.arena)->xchg[parity][0][0], sizeof(host), cudaMemcpyDeviceToHost, c.stream));
+    PRB_CUDA(cudaStreamSynchronize(c.stream));
+    for (int r = 0; r < c.mg.world; r++)
+        for (int k = 0; k < n; k++) all[r * stride + k] = host[r][k];
+    return PRB_OK;
+}
+
+int mg_allgather(Context& c, size_t arenaOffset, size_t elemBytes, const long long* lo) {
+    if (!c.mg.active()) return PRB_OK;
+    const int W = c.mg.world, me = c.mg.rank;
+    PRB_TRY(mg_barrier(c));
+    for (int qi = 1; qi < W; qi++) {
+        const int q = (me + qi) % W;
+        const size_t a = (size_t)lo[q] * elemBytes, b = (size_t)lo[q + 1] * elemBytes;
+        if (b > a) PRB_CUDA(cudaMemcpyAsync(c.mg.arena + arenaOffset + a, c.mg.peer[q] + arenaOffset + a, b - a, cudaMemcpyDeviceToDevice, c.stream));
+    }
+    PRB_TRY(mg_barrier(c));
+    return PRB_OK;
+}
+
 }  // namespace prb
 
 using namespace prb;

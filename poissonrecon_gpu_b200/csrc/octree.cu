@@ -9,10 +9,29 @@
 // Results follow the reference's INTENDED semantics (the reference's own pidx
 // is racy, see tests/golden/ref_sphere100k_d8_report.json "ref_run_to_run").
 #include "common.cuh"
-#include <cub/device/device_radix_sort.cuh>
 #include "scan.cuh"
 
 namespace prb {
+
+int scan_work_ensure(Context& c, size_t tiles) {
+    ScanWork& w = c.scanWork;
+    if (!c.hScanTotal) PRB_CUDA(cudaMallocHost((void**)&c.hScanTotal, 64));
+    if (!w.ticket) {
+        PRB_TRY(c.scanTicket.alloc(16, c.stream));
+        PRB_CUDA(cudaMemsetAsync(c.scanTicket.p, 0, 16 * sizeof(unsigned), c.stream));
+        w.ticket = c.scanTicket.p;
+    }
+    if (tiles > w.maxTiles) {
+        // (stream order: every earlier scan on this stream is complete before the new block is used)
+        const size_t want = tiles + tiles / 2 + 1024;
+        PRB_TRY(c.scanDesc.alloc(want, c.stream));
+        PRB_CUDA(cudaMemsetAsync(c.scanDesc.p, 0, want * sizeof(unsigned long long), c.stream));
+        w.desc = c.scanDesc.p;
+        w.maxTiles = want;
+        w.epoch = 0;                           // fresh zeroed descriptors: status 0 / 1 never match an epoch >= 1
+    }
+    return PRB_OK;
+}
 
 // exclusive scan of an int array (kernels in scan.cuh)
 int exclusive_scan(Context& c, const int* in, int* out, i64 n, i64* total_host) {
@@ -57,12 +76,22 @@ __global__ void k_bbox_final(const float* __restrict__ part, int nb, float* __re
 
 // A0 + A1: normalise (main.cu:552-571) and Morton-encode (main.cu:132-164).  Host float
 // semantics of the reference are kept: no FMA contraction in the normal length, IEEE division.
-__global__ void __launch_bounds__(256) k_normalise_encode(const float* __restrict__ xyz, const float* __restrict__ nrm, i64 n,
-                                                          float cx, float cy, float cz, float scale, int D,
-                                                          float* __restrict__ P0, float* __restrict__ N0, u64* __restrict__ keys, int* __restrict__ idx) {
+// One block per SORT TILE (sort.cu): the digit histogram of the first radix pass is taken on the way.
+constexpr int kEncThreads = 256, kEncItems = 16;          // = kSortThreads, kSortItems (sort.cu)
+__global__ void __launch_bounds__(kEncThreads) k_normalise_encode_count(const float* __restrict__ xyz, const float* __restrict__ nrm, i64 n,
+                                                                        float cx, float cy, float cz, float scale, int D, int bits, int nTiles,
+                                                                        float* __restrict__ P0, float* __restrict__ N0, u64* __restrict__ keys, int* __restrict__ idx,
+                                                                        int* __restrict__ counts) {
+    extern __shared__ int sHist[];
+    const int radix = 1 << bits;
+    for (int d = threadIdx.x; d < radix; d += kEncThreads) sHist[d] = 0;
+    __syncthreads();
     const float ctr[3] = {cx, cy, cz};
     const float nscale = (float)(2 << D);
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+    const i64 t0 = (i64)blockIdx.x * (kEncThreads * kEncItems);
+    for (int it = 0; it < kEncItems; it++) {
+        const i64 i = t0 + it * kEncThreads + threadIdx.x;
+        if (i >= n) break;
         float p[3], q[3];
 #pragma unroll
         for (int a = 0; a < 3; a++) {
@@ -89,16 +118,16 @@ __global__ void __launch_bounds__(256) k_normalise_encode(const float* __restric
         for (int a = 0; a < 3; a++) { P0[3 * i + a] = p[a]; N0[3 * i + a] = __fmul_rn(q[a], len); }
         keys[i] = k;
         idx[i] = (int)i;
+        atomicAdd(&sHist[(int)(k & (u64)(radix - 1))], 1);
     }
+    __syncthreads();
+    for (int d = threadIdx.x; d < radix; d += kEncThreads) counts[(size_t)d * nTiles + blockIdx.x] = sHist[d];
 }
-__global__ void __launch_bounds__(256) k_gather_samples(const int* __restrict__ idx, const float* __restrict__ P0, const float* __restrict__ N0, i64 n,
-                                                        float* __restrict__ P, float* __restrict__ Nr) {
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
-        i64 s = idx[i];
-#pragma unroll
-        for (int a = 0; a < 3; a++) { P[3 * i + a] = P0[3 * s + a]; Nr[3 * i + a] = N0[3 * s + a]; }
-    }
-}
+int sort_tiles(i64 n);
+int sort_passes(int keyBits);
+int sort_digit_bits(int keyBits);
+int radix_sort_gather(Context& c, u64* keys0, int* idx0, u64* keysTmp, int* idxTmp, int* counts, i64 n, int keyBits, const float* P0, const float* N0,
+                      u64* keysOut, int* idxOut, float* P, float* Nr);
 // run heads: first element of every run of equal (key >> shift)
 __global__ void __launch_bounds__(256) k_head_flags(const u64* __restrict__ key, i64 n, int shift, int* __restrict__ flag) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
@@ -318,13 +347,31 @@ int stage_octree(Context& c) {
     const i64 N = c.N;
     cudaStream_t st = c.stream;
     if (N <= 0 || N > 0x7fffffff / 4) { set_error("point count out of range"); return PRB_ERR_ARG; }
+    if (c.rawSharded) {
+        // multi-GPU: every rank uploaded its slice into its arena; gather the others (24 bytes per sample over NVLink)
+        long long lo[kMaxRanks + 1];
+        for (int r = 0; r <= c.mg.world; r++) lo[r] = (N * r) / c.mg.world;
+        for (int q = 0; q < c.mg.world; q++)
+            if (!c.mg.peer[q]) { set_error("multi-GPU: peer arenas not exchanged (prb_mg_set_peer)"); return PRB_ERR_STATE; }
+        PRB_TRY(mg_barrier(c));
+        for (int qi = 1; qi < c.mg.world; qi++) {
+            const int q = (c.mg.rank + qi) % c.mg.world;
+            const size_t a = 12 * (size_t)lo[q], b = 12 * (size_t)lo[q + 1];
+            if (b > a) {
+                PRB_CUDA(cudaMemcpyAsync((char*)c.rawPp + a, c.mg.peer[q] + c.mgRawPOff + a, b - a, cudaMemcpyDeviceToDevice, st));
+                PRB_CUDA(cudaMemcpyAsync((char*)c.rawNp + a, c.mg.peer[q] + c.mgRawNOff + a, b - a, cudaMemcpyDeviceToDevice, st));
+            }
+        }
+        PRB_TRY(mg_barrier(c));
+        c.rawSharded = false;
+    }
     // ---- A0 bounding box -> scale / centre (host float arithmetic of main.cu:539-545)
     {
         int nb = grid_for(c, N, 256, 4);
         DBuf<float> part, box;
         PRB_TRY(part.alloc((size_t)nb * 6, st));
         PRB_TRY(box.alloc(6, st));
-        PRB_LAUNCH(c, k_bbox_partial, nb, 256, 0, c.rawP.p, N, part.p);
+        PRB_LAUNCH(c, k_bbox_partial, nb, 256, 0, c.rawPp, N, part.p);
         PRB_LAUNCH(c, k_bbox_final, 1, 32, 0, part.p, nb, box.p);
         float h[6];
         PRB_CUDA(cudaMemcpyAsync(h, box.p, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -353,18 +400,20 @@ int stage_octree(Context& c) {
     PRB_TRY(c.sortedIdx.alloc((size_t)N, st));
     PRB_TRY(c.P.alloc(3 * (size_t)N, st));
     PRB_TRY(c.Nr.alloc(3 * (size_t)N, st));
-    PRB_LAUNCH(c, k_normalise_encode, grid_for(c, N, 256), 256, 0, c.rawP.p, c.rawN.p, N, c.center[0], c.center[1], c.center[2], c.scale, D,
-               P0.p, N0.p, keys0.p, idx0.p);
     {
-        size_t tmpBytes = 0;
-        PRB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys0.p, c.sortedKey.p, idx0.p, c.sortedIdx.p, (int)N, 0, 3 * D, st));
-        DBuf<char> tmp;
-        PRB_TRY(tmp.alloc(tmpBytes, st));
-        PRB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, keys0.p, c.sortedKey.p, idx0.p, c.sortedIdx.p, (int)N, 0, 3 * D, st));
-        c.launches += 2 + (3 * D + 7) / 8;   // onesweep: histogram + scan + one pass per digit
-        tmp.release();
+        // A2: stable LSD radix sort over the 3 D key bits with the sample index as payload (sort.cu); the first digit histogram comes
+        // out of the key generation, the sample gather rides on the last scatter pass
+        const int bits = sort_digit_bits(3 * D), nTiles = sort_tiles(N);
+        DBuf<u64> keysTmp;
+        DBuf<int> idxTmp, counts;
+        const bool needTmp = sort_passes(3 * D) > 1;
+        PRB_TRY(keysTmp.alloc(needTmp ? (size_t)N : 0, st));
+        PRB_TRY(idxTmp.alloc(needTmp ? (size_t)N : 0, st));
+        PRB_TRY(counts.alloc(((size_t)1 << bits) * (size_t)nTiles, st));
+        PRB_LAUNCH(c, k_normalise_encode_count, nTiles, kEncThreads, sizeof(int) << bits, c.rawPp, c.rawNp, N, c.center[0], c.center[1], c.center[2], c.scale, D, bits, nTiles,
+                   P0.p, N0.p, keys0.p, idx0.p, counts.p);
+        PRB_TRY(radix_sort_gather(c, keys0.p, idx0.p, keysTmp.p, idxTmp.p, counts.p, N, 3 * D, P0.p, N0.p, c.sortedKey.p, c.sortedIdx.p, c.P.p, c.Nr.p));
     }
-    PRB_LAUNCH(c, k_gather_samples, grid_for(c, N, 256), 256, 0, c.sortedIdx.p, P0.p, N0.p, N, c.P.p, c.Nr.p);
     P0.release(); N0.release(); keys0.release(); idx0.release();
     // ---- A3 unique leaves
     DBuf<int> flagN, exclN;

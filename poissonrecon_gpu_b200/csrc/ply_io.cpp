@@ -310,6 +310,42 @@ int prbio_read_points(const char* path, float** xyz, float** normals, int64_t* n
     return 0;
 }
 
+// Optional cross-pass weld: vertices with bit-identical positions become one (first occurrence kept, order preserved), triangles are
+// re-indexed in place.  The reference never welds: every pass appends its own copy of the vertices on a seam (main.cu:3220-3245).
+int prbio_weld_mesh(float* v, int64_t nv, int32_t* t, int64_t nt, int64_t* nv_out) {
+    if (nv < 0 || nt < 0 || (nv > 0 && !v) || (nt > 0 && !t) || !nv_out) return fail(kErrArg, "prbio_weld_mesh: bad argument");
+    struct Key { uint32_t a, b, c; };
+    auto key_of = [&](int64_t i) { Key k; std::memcpy(&k, v + 3 * i, 12); if (k.a == 0x80000000u) k.a = 0; if (k.b == 0x80000000u) k.b = 0; if (k.c == 0x80000000u) k.c = 0; return k; };
+    // open addressing over a power-of-two table of vertex ids
+    size_t cap = 16;
+    while (cap < 2 * (size_t)nv + 1) cap <<= 1;
+    std::vector<int32_t> slot(cap, -1), remap((size_t)nv);
+    int64_t out = 0;
+    for (int64_t i = 0; i < nv; i++) {
+        const Key k = key_of(i);
+        size_t h = ((size_t)k.a * 0x9E3779B97F4A7C15ull) ^ ((size_t)k.b * 0xC2B2AE3D27D4EB4Full) ^ ((size_t)k.c * 0x165667B19E3779F9ull);
+        h &= cap - 1;
+        for (;;) {
+            const int32_t j = slot[h];
+            if (j < 0) {
+                slot[h] = (int32_t)out;
+                if (out != i) std::memcpy(v + 3 * out, v + 3 * i, 12);
+                remap[(size_t)i] = (int32_t)out++;
+                break;
+            }
+            const Key kj = key_of(j);
+            if (kj.a == k.a && kj.b == k.b && kj.c == k.c) { remap[(size_t)i] = j; break; }
+            h = (h + 1) & (cap - 1);
+        }
+    }
+    for (int64_t q = 0; q < 3 * nt; q++) {
+        if (t[q] < 0 || t[q] >= nv) return fail(kErrArg, "prbio_weld_mesh: triangle index out of range");
+        t[q] = remap[(size_t)t[q]];
+    }
+    *nv_out = out;
+    return 0;
+}
+
 int prbio_write_mesh(const char* path, const float* v, int64_t nv, const int32_t* t, int64_t nt, const float center[3], float scale, int binary) {
     if (!path || nv < 0 || nt < 0 || (nv > 0 && !v) || (nt > 0 && !t) || !center) return fail(kErrArg, "prbio_write_mesh: bad argument");
     std::string name(path);

@@ -16,6 +16,7 @@ static void release_all(Context& c) {
     c.V.release(); c.divg.release(); c.x.release(); c.pointValue.release();
     c.meshV.release(); c.meshT.release(); c.vval.release();
     c.nMeshV = c.nMeshT = 0;
+    c.nGlobalV = c.nGlobalT = 0;
     c.xv = nullptr;
     c.divgv = nullptr;
     c.hMeshValid = false;
@@ -99,6 +100,9 @@ void prb_destroy(prb_context* h) {
     release_all(c);
     c.wsVal7.release(); c.wsLow.release(); c.wsCat.release(); c.wsNtri.release(); c.wsEmask.release(); c.wsVpre.release(); c.wsVbase.release(); c.wsTbase.release();
     c.dBvAnc.release(); c.dBvOwn.release(); c.dBvCell.release(); c.dBvGrid.release(); c.dMaxDepthFn.release(); c.dBaseFn.release(); c.dDfT.release(); c.dDfOffset.release(); c.dStencil.release();
+    c.scanDesc.release(); c.scanTicket.release();
+    if (c.hScanTotal) cudaFreeHost(c.hScanTotal);
+    c.hScanTotal = nullptr;
     cudaStreamSynchronize(c.stream);
     arena_unregister(c.stream);
     for (int r = 0; r < kMaxRanks; r++)
@@ -124,22 +128,53 @@ int prb_set_option(prb_context* h, const char* key, double value) {
     return PRB_OK;
 }
 
-int prb_set_points(prb_context* h, const float* xyz, const float* normals, int64_t n) {
-    if (!h || !xyz || !normals || n <= 0) { set_error("prb_set_points: bad argument"); return PRB_ERR_ARG; }
-    Context& c = h->c;
-    PRB_DEVICE(c);
+static int begin_run(Context& c, int64_t n) {
     release_all(c);
     c.mg.reset_allocs();
     c.mgP = c.mgX = c.mgVval = nullptr;
     c.vvalPtr = nullptr;
+    c.rawPp = c.rawNp = c.Vp = nullptr;
+    c.rawSharded = false;
     c.N = n;
     c.launches = 0;
+    return PRB_OK;
+}
+
+int prb_set_points(prb_context* h, const float* xyz, const float* normals, int64_t n) {
+    if (!h || !xyz || !normals || n <= 0) { set_error("prb_set_points: bad argument"); return PRB_ERR_ARG; }
+    Context& c = h->c;
+    PRB_DEVICE(c);
+    PRB_TRY(begin_run(c, n));
     PRB_CUDA(cudaEventRecord(c.ev[0], c.stream));
     PRB_TRY(c.rawP.alloc(3 * (size_t)n, c.stream));
     PRB_TRY(c.rawN.alloc(3 * (size_t)n, c.stream));
-    PRB_CUDA(cudaMemcpyAsync(c.rawP.p, xyz, 12 * (size_t)n, cudaMemcpyDefault, c.stream));
-    PRB_CUDA(cudaMemcpyAsync(c.rawN.p, normals, 12 * (size_t)n, cudaMemcpyDefault, c.stream));
+    c.rawPp = c.rawP.p; c.rawNp = c.rawN.p;
+    PRB_CUDA(cudaMemcpyAsync(c.rawPp, xyz, 12 * (size_t)n, cudaMemcpyDefault, c.stream));
+    PRB_CUDA(cudaMemcpyAsync(c.rawNp, normals, 12 * (size_t)n, cudaMemcpyDefault, c.stream));
     PRB_CUDA(cudaEventRecord(c.ev[1], c.stream));
+    c.stage = 1;
+    return PRB_OK;
+}
+
+// Multi-GPU: rank r passes only ITS slice of the cloud, the samples [plan[r], plan[r+1]) of prb_mg_plan(n_total, world); the slices
+// are gathered over NVLink at the start of prb_build_octree (every rank builds the same octree from the same n_total samples).
+int prb_set_points_sharded(prb_context* h, const float* xyz_slice, const float* normals_slice, int64_t n_total) {
+    if (!h || !xyz_slice || !normals_slice || n_total <= 0) { set_error("prb_set_points_sharded: bad argument"); return PRB_ERR_ARG; }
+    Context& c = h->c;
+    if (!c.mg.active()) return prb_set_points(h, xyz_slice, normals_slice, n_total);
+    PRB_DEVICE(c);
+    PRB_TRY(begin_run(c, n_total));
+    PRB_CUDA(cudaEventRecord(c.ev[0], c.stream));
+    c.rawPp = c.mg.alloc<float>(3 * (size_t)n_total, &c.mgRawPOff);
+    c.rawNp = c.mg.alloc<float>(3 * (size_t)n_total, &c.mgRawNOff);
+    if (!c.rawPp || !c.rawNp) { set_error("multi-GPU arena too small for the samples (24 bytes per sample; prb_mg_init arena_bytes)"); return PRB_ERR_NOMEM; }
+    const int64_t a = (n_total * c.mg.rank) / c.mg.world, b = (n_total * (c.mg.rank + 1)) / c.mg.world;
+    if (b > a) {
+        PRB_CUDA(cudaMemcpyAsync(c.rawPp + 3 * a, xyz_slice, 12 * (size_t)(b - a), cudaMemcpyDefault, c.stream));
+        PRB_CUDA(cudaMemcpyAsync(c.rawNp + 3 * a, normals_slice, 12 * (size_t)(b - a), cudaMemcpyDefault, c.stream));
+    }
+    PRB_CUDA(cudaEventRecord(c.ev[1], c.stream));
+    c.rawSharded = true;
     c.stage = 1;
     return PRB_OK;
 }
@@ -263,8 +298,8 @@ int prb_get_stats(prb_context* h, prb_stats* out) {
     for (int d = 0; d < 16; d++) { s.nodes_per_depth[d] = d <= c.D ? c.cnt[d] : 0; s.cg_iters[d] = d <= c.D ? c.cgIters[d] : 0; }
     s.n_subdivide = (int)c.subdivide.size();
     s.n_passes = (int)c.passes.size();
-    s.n_vertices = c.nMeshV;
-    s.n_triangles = c.nMeshT;
+    s.n_vertices = c.nGlobalV;       // the whole mesh (multi-GPU: this context holds the pieces listed by "mesh_layout")
+    s.n_triangles = c.nGlobalT;
     s.iso_value = c.iso;
     for (int a = 0; a < 3; a++) s.center[a] = c.center[a];
     s.scale = c.scale;
@@ -309,7 +344,7 @@ int64_t prb_get_array(prb_context* h, const char* name, void* dst, int64_t cap) 
     else if (s == "neighs") D_(c.neighs.p, c.neighs.bytes());
     else if (s == "sg_table") D_(c.sgTab.p, c.sgTab.bytes());
     else if (s == "p2n") D_(c.p2n.p, c.p2n.bytes());
-    else if (s == "vectorfield") D_(c.V.p, c.V.bytes());
+    else if (s == "vectorfield") D_(c.Vp, c.Vp ? 12 * (size_t)c.cnt[D] : 0);
     else if (s == "divergence") D_(c.divgv, c.divgv ? 4 * (size_t)M : 0);
     else if (s == "x") D_(c.xv, c.xv ? 4 * (size_t)M : 0);
     else if (s == "pointvalue") D_(c.pointValue.p, c.pointValue.bytes());
@@ -323,6 +358,7 @@ int64_t prb_get_array(prb_context* h, const char* name, void* dst, int64_t cap) 
     else if (s == "df_table") H_(c.tab.dfT.data(), c.tab.dfT.size() * 4);
     else if (s == "passes") { std::vector<int> v; for (auto& p : c.passes) { v.push_back(p.kind); v.push_back(p.nv); v.push_back(p.nt); } H_(v.data(), v.size() * 4); }
     else if (s == "subdivide") H_(c.subdivide.data(), c.subdivide.size() * 4);
+    else if (s == "mesh_layout") H_(c.layout.data(), c.layout.size() * sizeof(Context::PieceRecord));
     else if (s == "children") {
         // expanded [M][8] view of child0 for comparison with the reference layout
         std::vector<int> c0(M);
@@ -368,7 +404,7 @@ int prb_set_array(prb_context* h, const char* name, const void* src, int64_t byt
     std::string s(name);
     void* dst = nullptr;
     size_t want = 0;
-    if (s == "vectorfield") { dst = c.V.p; want = c.V.bytes(); }
+    if (s == "vectorfield") { dst = c.Vp; want = c.Vp ? 12 * (size_t)c.cnt[c.D] : 0; }
     else if (s == "divergence") { dst = c.divgv; want = c.divgv ? 4 * (size_t)c.M : 0; }
     else if (s == "x") { dst = c.xv; want = c.xv ? 4 * (size_t)c.M : 0; }
     else if (s == "iso") { if (bytes != 4) return PRB_ERR_ARG; std::memcpy(&c.iso, src, 4); return PRB_OK; }

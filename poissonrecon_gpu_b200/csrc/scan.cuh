@@ -6,6 +6,9 @@
 
 namespace prb {
 
+int scan_work_ensure(Context& c, size_t tiles);     // octree.cu: descriptors + ticket of the context (grow-only)
+
+
 constexpr int kScanBlock = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanBlock * kScanItems;
@@ -91,24 +94,87 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_apply(Op in, int* __restric
     }
 }
 
+// ---- single-pass chained scan with decoupled look-back.  Tiles take their index from a ticket counter (a tile only ever waits
+// for tiles that have started), publish their aggregate, then walk back over their predecessors -- 32 at a time, one per lane of
+// warp 0 -- until one with an inclusive prefix is met.  A descriptor is one 64-bit word (status << 32 | value), written and read
+// atomically; status = 2 * epoch + {0: aggregate, 1: inclusive prefix}: the per-call epoch makes clearing the descriptors
+// between calls unnecessary, and the last tile rewinds the ticket counter.
+__device__ __forceinline__ unsigned long long scan_ld(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void scan_st(unsigned long long* p, unsigned long long v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory"); }
+template <class Op>
+__global__ void __launch_bounds__(kScanBlock) k_scan_lookback(Op in, int* out /* may alias the input */, i64 n, int nTiles, unsigned long long* __restrict__ desc, unsigned* __restrict__ ticket,
+                                                              unsigned epoch, int* __restrict__ total) {
+    __shared__ int sm[33];
+    __shared__ int sTile, sPrefix;
+    if (threadIdx.x == 0) sTile = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int tile = sTile;
+    // thread t owns the kScanItems consecutive elements [t0 + t * kScanItems, ...): a warp covers one contiguous run
+    const i64 i0 = (i64)tile * kScanTile + (i64)threadIdx.x * kScanItems;
+    int v[kScanItems], sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) { v[k] = (i0 + k < n) ? in(i0 + k) : 0; sum += v[k]; }
+    int agg;
+    const int excl = block_exclusive_scan(sum, &agg, sm);
+    const unsigned stA = 2u * epoch, stP = 2u * epoch + 1u;
+    if (threadIdx.x < 32) {
+        int prefix = 0;
+        if (tile == 0) {
+            if (threadIdx.x == 0) scan_st(desc, ((unsigned long long)stP << 32) | (unsigned)agg);
+        } else {
+            if (threadIdx.x == 0) scan_st(desc + tile, ((unsigned long long)stA << 32) | (unsigned)agg);
+            for (int j = tile - 1;; j -= 32) {
+                const int mine = j - (int)threadIdx.x;
+                unsigned st = stP;
+                int val = 0;
+                if (mine >= 0) {
+                    unsigned long long d;
+                    do { d = scan_ld(desc + mine); st = (unsigned)(d >> 32); } while (st != stA && st != stP);
+                    val = (int)(unsigned)(d & 0xffffffffu);
+                }
+                const unsigned incl = __ballot_sync(0xffffffffu, st == stP);      // (lanes past tile 0 count as inclusive with value 0)
+                const int first = incl ? __ffs(incl) - 1 : 31;                      // nearest predecessor with an inclusive prefix (none: the whole window counts)
+                int part = ((int)threadIdx.x <= first) ? val : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                prefix += part;
+                if (incl) break;
+            }
+            if (threadIdx.x == 0) scan_st(desc + tile, ((unsigned long long)stP << 32) | (unsigned)(prefix + agg));
+        }
+        if (threadIdx.x == 0) {
+            sPrefix = prefix;
+            if (tile == nTiles - 1) { *total = prefix + agg; *ticket = 0u; }      // every ticket has been drawn: rewind for the next call
+        }
+    }
+    __syncthreads();
+    int run = sPrefix + excl;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        if (i0 + k < n) out[i0 + k] = run;
+        run += v[k];
+    }
+}
+
 // exclusive scan of in(0..n) into out on the context stream; the grand total is returned through
 // *total_host (synchronises the stream) when total_host != nullptr.
 template <class Op>
 int exclusive_scan_op(Context& c, Op in, int* out, i64 n, i64* total_host) {
     if (n <= 0) { if (total_host) *total_host = 0; return PRB_OK; }
     int nb = div_up(n, kScanTile);
-    DBuf<int> sums;
-    PRB_TRY(sums.alloc((size_t)nb + 1, c.stream));
-    PRB_LAUNCH(c, k_scan_tile_sums<Op>, nb, kScanBlock, 0, in, sums.p, n);
-    PRB_LAUNCH(c, k_scan_sums, 1, 1024, 0, sums.p, nb, sums.p + nb);
-    PRB_LAUNCH(c, k_scan_apply<Op>, nb, kScanBlock, 0, in, out, sums.p, n);
+    PRB_TRY(scan_work_ensure(c, (size_t)nb));
+    ScanWork& w = c.scanWork;
+    w.epoch++;
+    PRB_LAUNCH(c, k_scan_lookback<Op>, nb, kScanBlock, 0, in, out, n, nb, w.desc, w.ticket, w.epoch, (int*)(w.ticket + 1));
     if (total_host) {
-        int t = 0;
-        PRB_CUDA(cudaMemcpyAsync(&t, sums.p + nb, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        PRB_CUDA(cudaMemcpyAsync(c.hScanTotal, w.ticket + 1, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
         PRB_CUDA(cudaStreamSynchronize(c.stream));
-        *total_host = t;
+        *total_host = *c.hScanTotal;
     }
-    sums.release();
     return PRB_OK;
 }
 

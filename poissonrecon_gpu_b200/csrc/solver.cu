@@ -138,31 +138,68 @@ struct CgParams {
     const float* peerP[kMaxRanks];
     MgDev mg;
     unsigned epoch0;
+    unsigned* barCount;            // arrival counter / release flag of cg_sync (zeroed before the launch)
+    unsigned* barRelease;
 };
 
-// grid-wide (world == 1) or box-wide barrier.  kind: -1 none, 0/1 = publish this rank's per-depth
-// partial sums `local[1..D]` to every rank's slot table before signalling.
-template <bool MG>
-__device__ __forceinline__ void cg_sync(cg::grid_group& grid, const CgParams& P, unsigned& epoch, int parity, int kind, const double* local) {
-    grid.sync();
-    if (!MG) return;
-    epoch++;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (kind >= 0)
-            for (int r = 0; r < P.world; r++)
-                for (int d = 1; d <= P.D; d++) P.mg.peerHdr[r]->slots[parity][P.rank][kind * 16 + d] = local[d];
-        mg_signal_wait(P.mg, epoch);
-    }
-    grid.sync();
+// Grid-wide (world == 1) or box-wide barrier between the phases of an iteration.  Every CTA arrives on a counter; the LAST one
+// to arrive does the cross-GPU part -- warp 0, lane r <-> rank r: the lane writes this rank's per-depth partial sums (kind >= 0:
+// `local[1..D]`, complete because every CTA has arrived) and then, with release semantics, the barrier epoch into ITS line of
+// rank r's header, and polls the line rank r writes into this rank's header; all peers in parallel, one NVLink round trip -- and
+// then releases the other CTAs through a flag.  One counter round trip instead of two cooperative grid syncs around a
+// single-thread exchange.  Lines alternate with the epoch parity: a rank can run at most one barrier ahead of the slowest one.
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
-// total of a per-depth dot product after cg_sync
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
 template <bool MG>
-__device__ __forceinline__ double cg_total(const CgParams& P, int parity, int kind, int d, const double* local) {
-    if (!MG) return local[d];
-    const volatile double* s = &P.mg.hdr->slots[parity][0][kind * 16 + d];
-    if (d < P.shardFrom) return s[0];
+__device__ __forceinline__ void cg_sync(const CgParams& P, unsigned& epoch, unsigned& gen, int kind, const double* local) {
+    __syncthreads();
+    gen++;
+    if (MG) epoch++;
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int last = 0;
+        if (lane == 0) {
+            __threadfence();
+            last = atomicAdd(P.barCount, 1u) == gen * gridDim.x - 1u;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            if (MG) {
+                __threadfence();
+                if (lane < P.world && !P.mg.hdr->error) {
+                    MgCgLine* out = &P.mg.peerHdr[lane]->cg[epoch & 1u][P.rank];
+                    if (kind >= 0)
+                        for (int d = 1; d <= P.D; d++) out->v[d] = __ldcg(local + d);
+                    __threadfence_system();
+                    mg_store_release_sys(&out->epoch, epoch);
+                    const unsigned* in = &P.mg.hdr->cg[epoch & 1u][lane].epoch;
+                    const long long t0 = clock64();
+                    while ((int)(mg_load_acquire_sys(in) - epoch) < 0)
+                        if (clock64() - t0 > kMgSpinCycles) { P.mg.hdr->error = 1; break; }
+                }
+                __syncwarp();
+                __threadfence_system();
+            }
+            if (lane == 0) st_release_gpu(P.barRelease, gen);
+        } else if (lane == 0) {
+            while ((int)(ld_acquire_gpu(P.barRelease) - gen) < 0) {}
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+}
+// total of a per-depth dot product after cg_sync (`epoch`: the barrier that carried it)
+template <bool MG>
+__device__ __forceinline__ double cg_total(const CgParams& P, unsigned epoch, int d, const double* local) {
+    if (!MG) return __ldcg(local + d);
+    const volatile MgCgLine* L = &P.mg.hdr->cg[epoch & 1u][0];
+    if (d < P.shardFrom) return L[0].v[d];
     double t = 0.0;
-    for (int r = 0; r < P.world; r++) t += s[r * 32];
+    for (int r = 0; r < P.world; r++) t += L[r].v[d];
     return t;
 }
 
@@ -244,7 +281,6 @@ extern __shared__ __align__(16) float sDyn[];   // [kCgWarps][2][kWarpBufFloats]
 
 template <bool MG>
 __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_constant__ CgParams P) {
-    cg::grid_group grid = cg::this_grid();
     __shared__ __align__(16) float sSt[kMaxDepth + 1][4];
     __shared__ double sAcc[kMaxDepth + 1];
     __shared__ float sR1[kMaxDepth + 1], sAlpha[kMaxDepth + 1], sBeta[kMaxDepth + 1];
@@ -301,10 +337,10 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
         __syncthreads();
         if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&P.dots[64 + tid], sAcc[tid]);   // dedicated init buffer
     }
-    unsigned epoch = P.epoch0;
-    cg_sync<MG>(grid, P, epoch, 0, 0, P.dots + 64);
+    unsigned epoch = P.epoch0, gen = 0;
+    cg_sync<MG>(P, epoch, gen, 0, P.dots + 64);
     if (tid >= 1 && tid <= D) {
-        float r1 = (float)cg_total<MG>(P, 0, 0, tid, P.dots + 64);
+        float r1 = (float)cg_total<MG>(P, epoch, tid, P.dots + 64);
         sR1[tid] = r1; sIter[tid] = 1; sBeta[tid] = 0.f; sAlpha[tid] = 0.f; sPend[tid] = 0;
         sActive[tid] = (r1 > P.tol2 && 1 <= P.maxIter) ? 1 : 0;
     }
@@ -388,7 +424,7 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
                          o.w = __fadd_rn(rv.w, __fmul_rn(be, pv.w));
                          *reinterpret_cast<float4*>(pNew + i) = o;
                      });
-        cg_sync<MG>(grid, P, epoch, cur, -1, nullptr);
+        cg_sync<MG>(P, epoch, gen, -1, nullptr);
         // ---------------- phase A: Ap = A p ; p.Ap over the flat step list of all active depths
         {
             const int total = sStep[D + 1];
@@ -578,12 +614,12 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
         }
         __syncthreads();
         if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&dPAp[tid], sAcc[tid]);
-        cg_sync<MG>(grid, P, epoch, cur, 0, dPAp);
+        cg_sync<MG>(P, epoch, gen, 0, dPAp);
         // both accumulators of the NEXT iteration are zeroed here: every block has passed this
         // iteration's syncs, hence finished reading them after the previous iteration's syncs
         if (blockIdx.x == 0 && tid < 32) P.dots[nxt * 32 + tid] = 0.0;
         if (tid <= D) sAcc[tid] = 0.0;
-        if (tid >= 1 && tid <= D && sActive[tid]) sAlpha[tid] = (float)((double)sR1[tid] / cg_total<MG>(P, cur, 0, tid, dPAp));
+        if (tid >= 1 && tid <= D && sActive[tid]) sAlpha[tid] = (float)((double)sR1[tid] / cg_total<MG>(P, epoch, tid, dPAp));
         __syncthreads();
         // ---------------- phase B: r -= alpha Ap ; r.r   (x += alpha p is applied under the next SpMV, or by the sweep after the loop)
         const bool revB = P.zigzag && (phase++ & 1) != 0;
@@ -611,9 +647,9 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
         }
         __syncthreads();
         if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&dRRn[tid], sAcc[tid]);
-        cg_sync<MG>(grid, P, epoch, cur, 1, dRRn);
+        cg_sync<MG>(P, epoch, gen, 1, dRRn);
         if (tid >= 1 && tid <= D && sActive[tid]) {
-            float r0 = sR1[tid], r1 = (float)cg_total<MG>(P, cur, 1, tid, dRRn);
+            float r0 = sR1[tid], r1 = (float)cg_total<MG>(P, epoch, tid, dRRn);
             sR1[tid] = r1;
             int k = sIter[tid] + 1;
             sIter[tid] = k;
@@ -682,10 +718,10 @@ int stage_solve(Context& c) {
     DBuf<int> itersOut;
     PRB_TRY(r.alloc(padN, st));
     PRB_TRY(Ap.alloc(padN, st));
-    PRB_TRY(dots.alloc(96, st));
+    PRB_TRY(dots.alloc(96 + 32, st));                   // + the arrival counter and the release flag of cg_sync, one 128-byte line each
     PRB_TRY(itersOut.alloc(16, st));
     PRB_TRY(resOut.alloc(16, st));
-    PRB_CUDA(cudaMemsetAsync(dots.p, 0, 96 * sizeof(double), st));
+    PRB_CUDA(cudaMemsetAsync(dots.p, 0, (96 + 32) * sizeof(double), st));
     PRB_CUDA(cudaMemsetAsync(itersOut.p, 0, 16 * sizeof(int), st));
     CgParams P;
     P.D = D;
@@ -706,9 +742,10 @@ int stage_solve(Context& c) {
     }
     for (int q = 0; q < kMaxRanks; q++) P.peerP[q] = (mg && q < c.mg.world) ? (const float*)(c.mg.peer[q] + c.mgPOff) + 7 : nullptr;
     P.mg = c.mg.dev();
-    P.epoch0 = c.mg.epoch;
     if (mg) PRB_TRY(mg_barrier(c));        // every rank's previous use of the arena buffers is over before anyone writes p / x again
-    P.epoch0 = c.mg.epoch;
+    P.epoch0 = c.mg.cgEpoch;
+    P.barCount = reinterpret_cast<unsigned*>(dots.p + 96);
+    P.barRelease = P.barCount + 32;       // (its own 128-byte line)
     P.dots = dots.p; P.itersOut = itersOut.p; P.resOut = resOut.p;
     float tol = (float)c.cgTol;
     P.tol2 = tol * tol;
@@ -735,7 +772,7 @@ int stage_solve(Context& c) {
     c.cgRowIters = 0;
     for (int d = 0; d <= D; d++) { c.cgIters[d] = hIters[d]; c.cgRowIters += (i64)(P.row1[d] - P.row0[d]) * hIters[d]; }
     if (mg) {
-        c.mg.epoch = (unsigned)hIters[15];
+        c.mg.cgEpoch = (unsigned)hIters[15];
         // collect the other ranks' parts of the solution (pull over NVLink), then let nobody run ahead
         PRB_TRY(mg_barrier(c));
         for (int qi = 1; qi < c.mg.world; qi++) {     // start with the next rank: the peers are not all pulled from in the same order

@@ -60,8 +60,22 @@ def make_case(name):
     if name == "sphere2k_d3":
         p, n = synth.sphere(2_000, seed=6)
         return p, n, 3
+    # ---- depth 10 / 11 clouds whose refinement passes the CPU oracle can still materialise (tens of millions of virtual cells):
+    # roots 5 to 8 levels above maxDepth (the certified super-brick path, single-root coarse passes) and 64-bit keys at depth 11
+    if name == "tiny_sphere60k_d10":   # dense small object + two far samples fixing the cube: one depth-2 root (8^8 virtual cells), none of the big passes emits
+        s, _ = synth.sphere(60_000, seed=11)
+        p = np.concatenate([s * np.float32(0.03) + np.array([0.31, 0.27, 0.36], np.float32), np.array([[0, 0, 0], [1, 1, 1]], np.float32)]).astype(np.float32)
+        n = np.concatenate([s, np.array([[0, 0, -1], [0, 0, 1]], np.float32)]).astype(np.float32)
+        return p, n, 10
+    if name == "sparse80_d10":         # 80 samples: roots at depths 3..9, every batched pass emits triangles
+        p, n = synth.sphere(80, seed=13)
+        return p, n, 10
+    if name == "sparse300_d11":        # depth 11 (33-bit keys): roots at depths 3..10, the depth-3 pass has 8^8 virtual cells and emits
+        p, n = synth.sphere(300, seed=12)
+        return p, n, 11
     raise KeyError(name)
 
 
 SMALL_CASES = ["sphere3k_d5", "sphere20k_d6", "torus60k_d7", "scan80k_d7", "multi120k_d7", "sphere8k_d8"]
 EDGE_CASES = ["one_point_d5", "two_points_d4", "duplicates_d6", "lattice_d5", "zero_normals_d5", "cluster_plus_outlier_d8", "sphere2k_d2", "sphere2k_d3"]
+DEEP_CASES = ["tiny_sphere60k_d10", "sparse80_d10", "sparse300_d11"]

@@ -81,3 +81,49 @@ def test_teacher_forced_report_is_bit_exact():
     v = REPORT["oracle_vs_ref"]
     for k in ("vertex_owner", "vertex_kind", "vertex_pos", "edge_owner", "edge_kind", "neighs", "parent", "key"):
         assert v[k]["n_diff"] == 0, k
+
+
+# ---- config 2 (torus, 1 M points, maxDepth 9 = the reference's depth limit): same pinning, made on a B200 in round 2 with
+# oracle/_ref/ref_poisson_d9 (tests/golden/ref_torus1m_d9.json, ..._report.json by tools/ref_compare.py)
+G9 = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_torus1m_d9.json")))
+REPORT9 = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_torus1m_d9_report.json")))
+
+
+def test_config2_octree_and_solution_against_the_reference_dump(oracle_cls):
+    from poissonrecon_gpu_b200 import synth
+    p, n, D = synth.make("torus1m_d9")
+    o = oracle_cls()
+    o.run(p, n, D, 3)          # octree .. iso value (the mesh passes of the CPU oracle take minutes at this size)
+    base = o.get("base", "<i4")
+    assert D == G9["depth"] and base[:D + 1].tolist() == G9["base"] and o.get("count", "<i4").tolist() == G9["count"] and int(base[D + 1]) == G9["M"]
+    assert np.array_equal(o.get("center_scale", "<f4"), np.array(G9["center_scale"], np.float32))
+    assert sha(o.get("key", "<i8").astype("<i4")) == G9["sha"]["key"]
+    for name in ("pnum", "parent", "neighs", "didx", "dnum", "p2n"):
+        assert sha(o.get(name, "<i4")) == G9["sha"][name], name
+    assert sha(o.get("points", "<f4")) == G9["sha"]["points"] and sha(o.get("normals", "<f4")) == G9["sha"]["normals"]
+    assert sha(o.get("children", "<i4").reshape(-1, 8)[: int(base[D])]) == G9["sha"]["children_lt_D"]
+    x, dv = o.get("x", "<f4").astype(np.float64), o.get("divergence", "<f4").astype(np.float64)
+    for d in range(D + 1):
+        sl = slice(int(base[d]), int(base[d + 1]))
+        assert abs(np.linalg.norm(x[sl]) / G9["x_l2_per_depth"][d] - 1) < 1e-2, d      # the reference's own run-to-run spread is 4e-3 (pidx race)
+        assert abs(np.linalg.norm(dv[sl]) / G9["div_l2_per_depth"][d] - 1) < 1e-2, d
+    assert [c[1] for c in G9["cg"]] == o.get("cg_iters", "<i4").tolist()
+    assert abs(float(o.get("iso", "<f4")[0]) / G9["iso"] - 1) < 1e-3
+
+
+def test_config2_teacher_forced_report_is_bit_exact():
+    f = REPORT9["oracle_forced_vs_ref"]
+    assert f["divergence_given_ref_V"]["rel_l2"] < 1e-7
+    assert all(e["rel_l2"] < 1e-6 for e in f["x_given_ref_div_per_depth"])
+    assert f["cg_iters_given_ref_div"] == [c[1] for c in G9["cg"]]
+    assert f["pointvalue_given_ref_x"]["n_diff"] == 0
+    assert f["vvalue_given_ref_x_iso"]["n_diff"] == 0 and f["vvalue_sign_flips"] == 0
+    assert f["subdivide"]["n_diff"] == 0
+    assert f["passes_oracle"] == f["passes_ref"]
+    assert f["mesh_counts"]["oracle"] == f["mesh_counts"]["ref"] == [G9["mesh"]["nv"], G9["mesh"]["nt"]]
+    assert f["mesh_v"]["n_diff"] == 0 and f["mesh_t"]["n_diff"] == 0
+    v = REPORT9["oracle_vs_ref"]
+    for k in ("vertex_owner", "vertex_kind", "vertex_pos", "edge_owner", "edge_kind", "neighs", "parent", "key", "pnum", "didx", "dnum", "p2n", "points", "normals"):
+        assert v[k]["n_diff"] == 0, k
+    # the oracle's pidx differs from the reference's only where the reference differs from itself (racy atomics on EMPTY nodes)
+    assert v["pidx"]["n_diff"] <= REPORT9["ref_run_to_run"]["pidx"]["n_diff"]

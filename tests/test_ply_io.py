@@ -132,3 +132,45 @@ def test_mesh_writer_matches_reference_format(tmp_path):
     assert lib.prbio_write_mesh(str(tmp_path / "m2.ply").encode(), v.ctypes.data, v.shape[0], t.ctypes.data, t.shape[0], c.ctypes.data, s, 1) == 0
     v3, t3 = plyio.read_mesh_ply(str(tmp_path / "m2.ply"))
     assert np.array_equal(t3, t) and np.array_equal(v3, w)
+
+
+def test_weld_merges_identical_positions_and_keeps_order():
+    """prbio_weld_mesh (poisson_recon --weld): duplicate seam vertices collapse onto their first occurrence, triangles follow."""
+    lib = _lib()
+    lib.prbio_weld_mesh.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
+    g = np.random.default_rng(9)
+    base = g.random((500, 3)).astype(np.float32)
+    dup = g.integers(0, 500, 300)
+    v = np.concatenate([base, base[dup]]).astype(np.float32)          # 300 seam copies appended, like a second pass
+    v[7] = [0.0, 0.5, 0.25]
+    v = np.concatenate([v, np.array([[-0.0, 0.5, 0.25]], np.float32)])  # -0.0 welds with +0.0
+    t = g.integers(0, v.shape[0], (2000, 3)).astype(np.int32)
+    pos_before = v[t].copy()
+    v2, t2 = v.copy(), t.copy()
+    nv_out = ctypes.c_int64()
+    assert lib.prbio_weld_mesh(v2.ctypes.data, v2.shape[0], t2.ctypes.data, t2.shape[0], ctypes.byref(nv_out)) == 0
+    assert nv_out.value == 500
+    assert np.array_equal(v2[:500], v[:500])                           # first occurrences, original order
+    assert t2.max() < 500 and np.array_equal(v2[t2], pos_before)       # every triangle still has the same corner positions (+0 == -0)
+    bad = np.array([[0, 1, 900]], np.int32)
+    assert lib.prbio_weld_mesh(v2.ctypes.data, 500, bad.ctypes.data, 1, ctypes.byref(nv_out)) != 0
+
+
+def test_truncated_or_hostile_headers_are_rejected(tmp_path):
+    """Counts from the header are untrusted: absurd vertex counts and list lengths must fail cleanly, not overrun."""
+    f = tmp_path / "huge.ply"
+    f.write_bytes(b"ply\nformat binary_little_endian 1.0\nelement vertex 4611686018427387904\nproperty float x\nproperty float y\nproperty float z\n"
+                  b"property float nx\nproperty float ny\nproperty float nz\nend_header\n" + b"\0" * 48)
+    with pytest.raises(RuntimeError):
+        read_points(f)
+    f = tmp_path / "list.ply"
+    body = np.zeros(6, "<f4").tobytes() + np.array([-5], "<i4").tobytes() + b"\0" * 64
+    f.write_bytes(b"ply\nformat binary_little_endian 1.0\nelement vertex 2\nproperty float x\nproperty float y\nproperty float z\n"
+                  b"property float nx\nproperty float ny\nproperty float nz\nproperty list int int junk\nend_header\n" + body)
+    with pytest.raises(RuntimeError):
+        read_points(f)
+    f = tmp_path / "ascii.ply"
+    f.write_bytes(b"ply\nformat ascii 1.0\nelement vertex 1000000000\nproperty float x\nproperty float y\nproperty float z\n"
+                  b"property float nx\nproperty float ny\nproperty float nz\nend_header\n1 2 3 4 5 6\n")
+    with pytest.raises(RuntimeError):
+        read_points(f)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
-"""Multi-GPU check + timing (torchrun, one rank per GPU): every rank reconstructs the same cloud
-with the sharded divergence / CG / iso value and compares its result with a single-GPU run of the
-same context (x bit-identical up to the dot-product summation order, identical mesh)."""
+"""Multi-GPU check + timing (torchrun, one rank per GPU): the ranks reconstruct one cloud together (every rank uploads its slice of
+the samples; splat / divergence / CG / iso value / marching cubes sharded by Morton range, refinement passes dealt out) and the
+gathered result is compared with a single-GPU run on the same GPU: x, pass list and the whole mesh BIT-IDENTICAL."""
 import os
 import sys
 import time
@@ -27,6 +27,7 @@ def main():
     ref.set_points(p, n)
     ref.run()
     rx, (rv, rt), rst = ref.get("x", "<f4"), ref.mesh(), ref.stats()
+    rpasses = ref.get("passes", "<i4").tolist()
     for _ in range(2):
         ref.set_points(p, n); ref.run()
     t1 = ref.stats()
@@ -37,14 +38,16 @@ def main():
     for k in range(reps):
         dist.barrier()
         t0 = time.time()
-        pr.set_points(p, n)
+        s0, s1 = (p.shape[0] * rank) // world, (p.shape[0] * (rank + 1)) // world
+        pr.set_points_sharded(p[s0:s1], n[s0:s1], p.shape[0])
         pr.run()
         st = pr.stats()
         wall = time.time() - t0
         x = pr.get("x", "<f4")
-        v, t = pr.mesh()
+        v, t = pr.mesh_global()
         rel = float(np.linalg.norm(x.astype(np.float64) - rx) / np.linalg.norm(rx.astype(np.float64)))
         same_mesh = v.shape == rv.shape and t.shape == rt.shape and np.array_equal(t, rt) and (v.size == 0 or float(np.abs(v - rv).max()) <= 1e-6)
+        same_mesh = same_mesh and np.array_equal(v, rv) and np.array_equal(x, rx) and pr.get("passes", "<i4").tolist() == rpasses
         ok &= rel <= 1e-5 and same_mesh and st["cg_iters"] == rst["cg_iters"]
         print(f"[rank {rank}] run {k}: wall {wall * 1e3:.1f} ms  stages " + str({a: round(b, 2) for a, b in st.items() if a.startswith('ms_')}) +
               f"  x rel-L2 vs 1-GPU {rel:.2e}  mesh identical {same_mesh}  iters equal {st['cg_iters'] == rst['cg_iters']}", flush=True)
