@@ -136,6 +136,7 @@ int prb_set_option(prb_context* ctx, const char* key, double value);
  *   prb_mg_set_peer  opens the arena of another rank from its handle (exchange the handles with
  *                    any host-side transport, e.g. torch.distributed.all_gather_object);
  *   prb_mg_barrier   box-wide barrier through the arena flags (all ranks must call it);
+ *   prb_set_points_sharded / the distributed mesh: see below;
  *   prb_mg_plan      host-only helper: the contiguous split of `count` units over `world` ranks
  *                    used for every sharded range (out[world + 1]). */
 int prb_mg_init(prb_context* ctx, int rank, int world, int64_t arena_bytes, void* ipc_handle_out_64_bytes);
@@ -146,6 +147,9 @@ int prb_set_points_sharded(prb_context* ctx, const float* xyz_slice, const float
 int prb_mg_set_peer(prb_context* ctx, int peer_rank, const void* ipc_handle_64_bytes);
 int prb_mg_barrier(prb_context* ctx);
 int prb_mg_plan(int64_t count, int world, int64_t* out);
+/* Host-only: the deal of whole refinement passes to ranks used by prb_extract (pass i: count[i] roots at depth depth[i]; largest
+ * estimated cost first, to the least loaded rank): owner_out[i] = rank. */
+int prb_mg_deal_passes(int depth_max, int n_passes, const int32_t* depth, const int32_t* count, int world, int32_t* owner_out);
 
 /* Host-side B-spline precompute (replaces FunctionData<2,double>::set / setDotTables,
  * FunctionData.inl:112-215, and the table uploads of main.cu:3308-3359).  Needs no GPU: copies

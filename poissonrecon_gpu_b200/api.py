@@ -52,6 +52,31 @@ def shard_plan(count: int, world: int):
     return list(out)
 
 
+def deal_passes(depth_max: int, depths, counts, world: int):
+    """Rank that runs each refinement pass (prb_mg_deal_passes; host only, no GPU)."""
+    lib = load_library()
+    d = np.ascontiguousarray(depths, np.int32)
+    c = np.ascontiguousarray(counts, np.int32)
+    o = np.zeros(d.size, np.int32)
+    rc = lib.prb_mg_deal_passes(int(depth_max), int(d.size), d.ctypes.data, c.ctypes.data, int(world), o.ctypes.data)
+    if rc != 0:
+        raise PrbError(f"prb_mg_deal_passes: {lib.prb_last_error().decode()}")
+    return o.tolist()
+
+
+def assemble_mesh(parts, nv: int, nt: int):
+    """The whole mesh from every rank's (layout, vertices, triangles): pieces written at their global offsets."""
+    V = np.zeros((nv, 3), np.float32)
+    T = np.zeros((nt, 3), np.int32)
+    for lay_r, v_r, t_r in parts:
+        av = at = 0
+        for _, vb, pv, tb, pt in np.asarray(lay_r).reshape(-1, 5).tolist():
+            V[vb:vb + pv] = v_r[av:av + pv]
+            T[tb:tb + pt] = t_r[at:at + pt]
+            av += pv; at += pt
+    return V, T
+
+
 def lib_path() -> str:
     return os.path.join(_HERE, "libprb.so")
 
@@ -90,6 +115,7 @@ def load_library():
     lib.prb_mg_set_peer.argtypes = [vp, ci, vp]
     lib.prb_mg_barrier.argtypes = [vp]
     lib.prb_mg_plan.argtypes = [cll, ci, ctypes.POINTER(cll)]
+    lib.prb_mg_deal_passes.argtypes = [ci, ci, vp, vp, ci, vp]
     lib.prb_host_tables.argtypes = [ci, ctypes.c_char_p, vp, cll]
     lib.prb_host_tables.restype = cll
     lib.prb_debug_scan.argtypes = [vp, vp, cll, vp, ctypes.POINTER(cll)]
@@ -101,7 +127,7 @@ def load_library():
 EXPORTS = ["prb_create", "prb_destroy", "prb_last_error", "prb_set_points", "prb_set_points_sharded", "prb_build_octree", "prb_splat", "prb_solve",
            "prb_extract", "prb_run", "prb_get_mesh", "prb_get_mesh_device", "prb_get_stats", "prb_get_array", "prb_set_array",
            "prb_set_option", "prb_run_stage", "prb_get_stream", "prb_host_tables", "prb_mg_init", "prb_mg_set_peer", "prb_mg_barrier",
-           "prb_mg_plan", "prb_debug_scan", "prb_debug_sort"]
+           "prb_mg_plan", "prb_mg_deal_passes", "prb_debug_scan", "prb_debug_sort"]
 
 
 class PoissonRecon:
@@ -244,15 +270,7 @@ class PoissonRecon:
             return v, t
         parts = [None] * dist.get_world_size(group)
         dist.all_gather_object(parts, (lay, v, t), group=group)
-        V = np.zeros((st["n_vertices"], 3), np.float32)
-        T = np.zeros((st["n_triangles"], 3), np.int32)
-        for lay_r, v_r, t_r in parts:
-            av = at = 0
-            for _, vb, nv, tb, nt in lay_r.tolist():
-                V[vb:vb + nv] = v_r[av:av + nv]
-                T[tb:tb + nt] = t_r[at:at + nt]
-                av += nv; at += nt
-        return V, T
+        return assemble_mesh(parts, st["n_vertices"], st["n_triangles"])
 
     def mesh_device_size(self):
         nv, nt = ctypes.c_int64(), ctypes.c_int64()

@@ -169,6 +169,7 @@ int mg_barrier(struct Context& c);            // device-side flag barrier on the
 // rank r: barrier, pull the other ranks' ranges over NVLink (each rank starts with its successor), barrier
 // all-gather of up to 64 ints per rank through the arena headers: all[r * stride + k] = value k of rank r (all ranks must call it)
 int mg_exchange_ints(struct Context& c, const int* mine, int n, int* all, int stride = -1);
+void deal_passes(int D, int n, const int* depth, const int* count, int world, int* owner);     // mc.cu
 int mg_allgather(struct Context& c, size_t arenaOffset, size_t elemBytes, const long long* lo /* [world + 1] */);
 
 // One pass (the main depth-D pass or a refinement pass) of mesh output.
@@ -194,6 +195,7 @@ struct Context {
     double cgTol = 1e-5;
     int cgMaxIter = 10000;
     int cgZigzag = 1;
+    int cgBulk = 1;                // CG streaming phases through TMA bulk copies (solver.cu stream_pairs_bulk); 0: per-thread cp.async ring
     int refineBoundCheck = 0;      // 1: evaluate every refinement brick and verify the certified signs (tests)
     long long boundChecked = 0, boundEvaluated = 0;
     int doRefine = 1;

@@ -1660,6 +1660,21 @@ static double pass_weight(int D, int rd, int nr) {
     return (double)nr * std::pow(8.0, lv) * 40.0;                                                  // materialised subtrees: every virtual cell is evaluated
 }
 
+// whole passes -> ranks: largest estimated cost first, each to the least loaded rank (ties: lowest rank).  Pure host arithmetic on
+// replicated inputs, so every rank computes the same deal (exported as prb_mg_deal_passes for the CPU tests).
+void deal_passes(int D, int n, const int* depth, const int* count, int world, int* owner) {
+    std::vector<int> order((size_t)n);
+    for (int i = 0; i < n; i++) order[(size_t)i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pass_weight(D, depth[a], count[a]) > pass_weight(D, depth[b], count[b]); });
+    double load[kMaxRanks] = {0};
+    for (int i : order) {
+        int best = 0;
+        for (int r = 1; r < world; r++) if (load[r] < load[best]) best = r;
+        owner[i] = best;
+        load[best] += pass_weight(D, depth[i], count[i]);
+    }
+}
+
 int stage_extract(Context& c) {
     cudaStream_t st = c.stream;
     const int D = c.D, M = c.M;
@@ -1783,18 +1798,10 @@ int stage_extract(Context& c) {
             for (int k = firstOfDepth[d]; k < firstOfDepth[d + 1]; k++) plan.push_back({1, d, k, 1, 0, -1});
         for (int d = finerDepth; d < D; d++) plan.push_back({2, d, firstOfDepth[d], firstOfDepth[d + 1] - firstOfDepth[d], 0, -1});
         if (mg) {
-            std::vector<int> order(plan.size());
-            for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
-            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pass_weight(D, plan[a].depth, plan[a].count) > pass_weight(D, plan[b].depth, plan[b].count); });
-            double load[kMaxRanks] = {0};
-            // the main pass is not free either: start from every rank's share of it
-            for (int r = 0; r < W; r++) load[r] = 0.0;
-            for (int i : order) {
-                int best = 0;
-                for (int r = 1; r < W; r++) if (load[r] < load[best]) best = r;
-                plan[i].owner = best;
-                load[best] += pass_weight(D, plan[i].depth, plan[i].count);
-            }
+            std::vector<int> dep(plan.size()), cnt(plan.size()), own(plan.size());
+            for (size_t i = 0; i < plan.size(); i++) { dep[i] = plan[i].depth; cnt[i] = plan[i].count; }
+            deal_passes(D, (int)plan.size(), dep.data(), cnt.data(), W, own.data());
+            for (size_t i = 0; i < plan.size(); i++) plan[i].owner = own[i];
         }
         DBuf<int> rootMap;
         PRB_TRY(rootMap.alloc((size_t)M, st));

@@ -112,6 +112,14 @@ int prb_mg_barrier(prb_context* h) {
     return PRB_OK;
 }
 
+// Host-only: which rank runs which refinement pass (pass i = `count[i]` roots at depth `depth[i]`, maxDepth `depth_max`); the deal every
+// rank derives for itself in prb_extract.
+int prb_mg_deal_passes(int depth_max, int n_passes, const int32_t* depth, const int32_t* count, int world, int32_t* owner_out) {
+    if (n_passes < 0 || world < 1 || world > kMaxRanks || (n_passes > 0 && (!depth || !count || !owner_out))) { set_error("prb_mg_deal_passes: bad argument"); return PRB_ERR_ARG; }
+    deal_passes(depth_max, n_passes, depth, count, world, owner_out);
+    return PRB_OK;
+}
+
 // Host-only shard plan (no GPU needed): splits `count` units into `world` contiguous chunks of
 // (nearly) equal size; out[r] = first unit of rank r, out[world] = count.  Every rank computes the
 // same plan from the same replicated counts.

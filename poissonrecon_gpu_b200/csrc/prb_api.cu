@@ -120,6 +120,7 @@ int prb_set_option(prb_context* h, const char* key, double value) {
     if (k == "cg_tol") h->c.cgTol = value;
     else if (k == "cg_max_iter") h->c.cgMaxIter = (int)value;
     else if (k == "cg_zigzag") h->c.cgZigzag = (int)value;
+    else if (k == "cg_bulk") h->c.cgBulk = (int)value;
     else if (k == "refine_bound_check") h->c.refineBoundCheck = (int)value;
     else if (k == "div_mode") h->c.divMode = (int)value;
     else if (k == "refine") h->c.doRefine = (int)value;

@@ -113,6 +113,7 @@ struct CgParams {
     const int* tab4;
     int nSg;
     int zigzag;                    // sweep memory in alternating directions phase by phase (L2 reuse across phase boundaries)
+    int bulk;                      // streaming phases through TMA bulk copies + mbarriers (1) or per-thread cp.async (0)
     const float* stencil;          // [D+1][27]
     const float* b;                // divergence
     // vectors indexed by node id; node 1 sits on a 32-byte boundary (pointer = allocation + 7)
@@ -277,6 +278,72 @@ __device__ __forceinline__ void stream_pairs(const int* pre, int total, const in
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
+// The same streaming phases through the TMA engine (default): the two vectors of a batch are contiguous 512-byte runs of a depth
+// slab, so ONE lane issues two bulk copies (cp.async.bulk.shared::cluster.global, SASS UBLKCP) per batch into the warp's ring slot
+// and arms the slot's mbarrier with the byte count (expect_tx); the warp waits on the barrier's phase parity before reading the
+// slot.  32 LDGSTS instructions with 32 address computations each become two instructions issued by one thread.
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE_%=;\n"
+        "bra MBAR_WAIT_%=;\n"
+        "MBAR_DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+template <class F>
+__device__ __forceinline__ void stream_pairs_bulk(const int* pre, int total, const int* row0, const int* row1, const float* __restrict__ A0, const float* __restrict__ A1,
+                                                  bool rev, float* ring /* this warp's smem */, unsigned barS /* this warp's kStreamQ mbarriers */, unsigned& phaseBits,
+                                                  int gwarp, int nwarps, int lane, F&& consume) {
+    const unsigned ringS = (unsigned)__cvta_generic_to_shared(ring);
+    // what the generic proxy (LDGSTS / LDS of the previous phase) did to these buffers is ordered before the async-proxy writes below
+    __syncwarp();
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    BatchCursor ci, cc;
+    ci.init(pre, row0, row1); cc.init(pre, row0, row1);
+    int bi = gwarp;                                    // next batch to issue
+    auto issue = [&](int slot) {
+        if (bi < total) {
+            const int u = rev ? total - 1 - bi : bi;
+            const int i0 = ci.locate(pre, row0, row1, u, 0);                       // first float of the batch (a batch is never empty)
+            const int cnt4 = min(32, ci.n4 - (u - ci.lo) * 32);
+            if (lane == 0) {
+                const unsigned bytes = 16u * (unsigned)cnt4, bar = barS + 8u * (unsigned)slot;
+                mbar_expect_tx(bar, 2u * bytes);
+                bulk_g2s(ringS + 512u * (unsigned)slot, A0 + i0, bytes, bar);
+                bulk_g2s(ringS + 512u * (unsigned)(kStreamQ + slot), A1 + i0, bytes, bar);
+            }
+        }
+        bi += nwarps;
+    };
+#pragma unroll 1
+    for (int q = 0; q < kStreamQ; q++) issue(q);
+    int slot = 0;
+    for (int b = gwarp; b < total; b += nwarps) {
+        mbar_wait(barS + 8u * (unsigned)slot, (phaseBits >> slot) & 1u);
+        phaseBits ^= 1u << slot;
+        const int i = cc.locate(pre, row0, row1, rev ? total - 1 - b : b, lane);
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+        if (i >= 0) {
+            v0 = *reinterpret_cast<const float4*>(ring + 4 * (slot * 32 + lane));
+            v1 = *reinterpret_cast<const float4*>(ring + 4 * ((kStreamQ + slot) * 32 + lane));
+        }
+        consume(cc.d, i, v0, v1);           // called by ALL lanes (i < 0: no element), the depth is warp-uniform
+        __syncwarp();                       // every lane has read the slot before it is refilled
+        issue(slot);
+        slot = slot + 1 == kStreamQ ? 0 : slot + 1;
+    }
+}
+
 extern __shared__ __align__(16) float sDyn[];   // [kCgWarps][2][kWarpBufFloats]
 
 template <bool MG>
@@ -289,6 +356,7 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
     __shared__ int sPend[kMaxDepth + 1];      // x of depth d still lacks alpha_{k-1} p_{k-1} (applied under the next SpMV)
     __shared__ int sXup[kMaxDepth + 3];       // sXup[d] = first flat 32-lane batch of the pending x updates of depth d
     __shared__ int sAct4[kMaxDepth + 3];      // the same over the ACTIVE depths (streaming phases)
+    __shared__ __align__(8) unsigned long long sBar[kCgWarps][kStreamQ];   // mbarriers of the bulk-copy ring, one per warp and slot
     const int D = P.D, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gwarp = blockIdx.x * kCgWarps + warp, nwarps = gridDim.x * kCgWarps;
     const int gthread = blockIdx.x * kCgBlock + tid, nthreads = gridDim.x * kCgBlock;
@@ -298,6 +366,12 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
         sSt[tid >> 2][tid & 3] = P.stencil[(tid >> 2) * 27 + rep[tid & 3]];
     }
     if (tid <= D) sAcc[tid] = 0.0;
+    const unsigned barS = (unsigned)__cvta_generic_to_shared(&sBar[warp][0]);
+    unsigned phaseBits = 0u;                  // parity of the next completion of every ring slot (warp-uniform)
+    if (P.bulk && lane == 0) {
+        for (int q = 0; q < kStreamQ; q++) mbar_init(barS + 8u * (unsigned)q, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
     __syncthreads();
 
     // ---- depth 0: a 1x1 system, solved by one thread with the same recurrences
@@ -413,17 +487,20 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
 
         // ---------------- phase C: p = r + beta p   (beta = 0 and p = 0 in the first iteration)
         const bool revC = P.zigzag && (phase++ & 1) != 0;
-        stream_pairs(sAct4, sAct4[D + 1], P.row0, P.row1, P.r, pOld, revC, wbuf, gwarp, nwarps, lane,
-                     [&](int d, int i, const float4& rv, const float4& pv) {
-                         if (i < 0) return;
-                         const float be = sBeta[d];
-                         float4 o;
-                         o.x = __fadd_rn(rv.x, __fmul_rn(be, pv.x));
-                         o.y = __fadd_rn(rv.y, __fmul_rn(be, pv.y));
-                         o.z = __fadd_rn(rv.z, __fmul_rn(be, pv.z));
-                         o.w = __fadd_rn(rv.w, __fmul_rn(be, pv.w));
-                         *reinterpret_cast<float4*>(pNew + i) = o;
-                     });
+        {
+            auto stepC = [&](int d, int i, const float4& rv, const float4& pv) {
+                if (i < 0) return;
+                const float be = sBeta[d];
+                float4 o;
+                o.x = __fadd_rn(rv.x, __fmul_rn(be, pv.x));
+                o.y = __fadd_rn(rv.y, __fmul_rn(be, pv.y));
+                o.z = __fadd_rn(rv.z, __fmul_rn(be, pv.z));
+                o.w = __fadd_rn(rv.w, __fmul_rn(be, pv.w));
+                *reinterpret_cast<float4*>(pNew + i) = o;
+            };
+            if (P.bulk) stream_pairs_bulk(sAct4, sAct4[D + 1], P.row0, P.row1, P.r, pOld, revC, wbuf, barS, phaseBits, gwarp, nwarps, lane, stepC);
+            else stream_pairs(sAct4, sAct4[D + 1], P.row0, P.row1, P.r, pOld, revC, wbuf, gwarp, nwarps, lane, stepC);
+        }
         cg_sync<MG>(P, epoch, gen, -1, nullptr);
         // ---------------- phase A: Ap = A p ; p.Ap over the flat step list of all active depths
         {
@@ -626,23 +703,24 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
         {
             double part = 0.0;
             int partDepth = 0;
-            stream_pairs(sAct4, sAct4[D + 1], P.row0, P.row1, P.Ap, P.r, revB, wbuf, gwarp, nwarps, lane,
-                         [&](int d, int i, const float4& av, const float4& rv) {
-                             if (d != partDepth) {           // (warp-uniform: a batch never mixes depths)
-                                 if (partDepth) warp_add(part, sAcc, partDepth, lane);
-                                 part = 0.0;
-                                 partDepth = d;
-                             }
-                             if (i < 0) return;
-                             const float al = sAlpha[d];
-                             float4 ro;
-                             ro.x = __fmaf_rn(-al, av.x, rv.x); ro.y = __fmaf_rn(-al, av.y, rv.y); ro.z = __fmaf_rn(-al, av.z, rv.z); ro.w = __fmaf_rn(-al, av.w, rv.w);
-                             *reinterpret_cast<float4*>(P.r + i) = ro;
-                             part += (double)(ro.x * ro.x);
-                             part += (double)(ro.y * ro.y);
-                             part += (double)(ro.z * ro.z);
-                             part += (double)(ro.w * ro.w);
-                         });
+            auto stepB = [&](int d, int i, const float4& av, const float4& rv) {
+                if (d != partDepth) {           // (warp-uniform: a batch never mixes depths)
+                    if (partDepth) warp_add(part, sAcc, partDepth, lane);
+                    part = 0.0;
+                    partDepth = d;
+                }
+                if (i < 0) return;
+                const float al = sAlpha[d];
+                float4 ro;
+                ro.x = __fmaf_rn(-al, av.x, rv.x); ro.y = __fmaf_rn(-al, av.y, rv.y); ro.z = __fmaf_rn(-al, av.z, rv.z); ro.w = __fmaf_rn(-al, av.w, rv.w);
+                *reinterpret_cast<float4*>(P.r + i) = ro;
+                part += (double)(ro.x * ro.x);
+                part += (double)(ro.y * ro.y);
+                part += (double)(ro.z * ro.z);
+                part += (double)(ro.w * ro.w);
+            };
+            if (P.bulk) stream_pairs_bulk(sAct4, sAct4[D + 1], P.row0, P.row1, P.Ap, P.r, revB, wbuf, barS, phaseBits, gwarp, nwarps, lane, stepB);
+            else stream_pairs(sAct4, sAct4[D + 1], P.row0, P.row1, P.Ap, P.r, revB, wbuf, gwarp, nwarps, lane, stepB);
             if (partDepth) warp_add(part, sAcc, partDepth, lane);
         }
         __syncthreads();
@@ -729,7 +807,7 @@ int stage_solve(Context& c) {
     P.sgStart[0] = 0;
     P.sgStart[1] = 0;
     for (int d = 2; d <= D + 1; d++) P.sgStart[d] = 1 + (c.base[d - 1] - 1) / 8;
-    P.tab4 = c.sgTab4.p; P.nSg = c.nSg; P.zigzag = c.cgZigzag; P.stencil = c.dStencil.p; P.b = c.divgv;
+    P.tab4 = c.sgTab4.p; P.nSg = c.nSg; P.zigzag = c.cgZigzag; P.bulk = c.cgBulk; P.stencil = c.dStencil.p; P.b = c.divgv;
     P.x = c.xv; P.r = r.p + 7; P.p = pBuf + 7; P.pStride = (i64)padN; P.Ap = Ap.p + 7;
     P.world = c.mg.world; P.rank = c.mg.rank; P.shardFrom = mg ? c.shardFrom : D + 1;
     for (int d = 0; d <= D + 1; d++) {

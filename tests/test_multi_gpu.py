@@ -37,11 +37,42 @@ blob = bytes([rank]) * 64
 got = [None] * world
 dist.all_gather_object(got, blob)
 assert [g[0] for g in got] == list(range(world)) and all(len(g) == 64 for g in got)
+# refinement passes are dealt out whole: every rank derives the same deal, heaviest passes are spread, nothing is lost
+import numpy as np
+from poissonrecon_gpu_b200 import deal_passes, assemble_mesh
+D = 10
+depths = [1, 2, 2, 3, 4, 5, 6, 7, 8, 9]
+roots = [1, 1, 1, 4, 37, 210, 1400, 9000, 52000, 301000]
+own = deal_passes(D, depths, roots, world)
+owns = [None] * world
+dist.all_gather_object(owns, own)
+assert all(o == owns[0] for o in owns), "ranks disagree on the deal of the passes"
+assert len(own) == len(depths) and set(own) <= set(range(world)) and len(set(own)) == world
+assert deal_passes(D, [], [], world) == []
+# the distributed mesh: every rank holds pieces (pass, first vertex, vertices, first triangle, triangles); writing all pieces at
+# their offsets reproduces the whole mesh.  Pieces here: the main pass split by rank + one refinement pass per rank
+g = np.random.default_rng(3)
+NV, NT = 1000, 1800
+Vfull = g.random((NV, 3)).astype(np.float32)
+Tfull = g.integers(0, NV, (NT, 3)).astype(np.int32)
+cutsV = [0, 300, 700, 850, 1000]
+cutsT = [0, 500, 1100, 1500, 1800]
+pieces = {0: [(0, 0, 1)], 1: [(0, 1, 2)]}                       # (pass, piece index range) per rank
+pieces[0].append((2, 3, 4)); pieces[1].append((1, 2, 3))
+lay, vv, tt = [], [], []
+for ps, a, b in pieces[rank % 2] if world == 2 else []:
+    lay.append([ps, cutsV[a], cutsV[b] - cutsV[a], cutsT[a], cutsT[b] - cutsT[a]])
+    vv.append(Vfull[cutsV[a]:cutsV[b]]); tt.append(Tfull[cutsT[a]:cutsT[b]])
+parts = [None] * world
+dist.all_gather_object(parts, (np.array(lay, np.int64), np.concatenate(vv), np.concatenate(tt)))
+V, T = assemble_mesh(parts, NV, NT)
+assert np.array_equal(V, Vfull) and np.array_equal(T, Tfull)
 # without a GPU the multi-GPU entry points fail loudly too
 lib = api.load_library()
 assert lib.prb_mg_init(None, 0, 2, 1 << 20, None) == -1
 out = (ctypes.c_int64 * 3)()
 assert lib.prb_mg_plan(-1, 2, out) == -1 and lib.prb_mg_plan(10, 9, out) == -1
+assert lib.prb_set_points_sharded(None, None, None, 10) == -1
 dist.barrier()
 dist.destroy_process_group()
 print("WORKER_OK", rank)
