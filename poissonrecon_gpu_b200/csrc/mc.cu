@@ -706,50 +706,68 @@ __global__ void __launch_bounds__(256) k_vmask(VTree V, i64 total, const int* __
     }
 }
 // corner values of the depth-D virtual cells: only REAL nodes carry a solution; a virtual root
-// stands for the real leaf it replaces (main.cu:2328-2442).  One thread per cell, looping over
-// the corners it owns; virtual levels without any real neighbour are skipped via vmask.
-__global__ void __launch_bounds__(128) k_vvertex_values(VTree V, Topo T, const int* __restrict__ vneigh, const unsigned* __restrict__ vmask,
+// stands for the real leaf it replaces (main.cu:2328-2442).  Two steps: k_vcorner_list -- one thread per (cell, corner): the
+// corners a cell owns are appended to a list (warp-aggregated atomic; the order is irrelevant, a value is stored at its
+// (cell, corner) slot) -- then k_vvertex_values with one thread per OWNED corner, so that no lane idles while another walks the
+// levels of eight corners (one thread per cell: 66 ms for the two passes of the 20 M-point depth-11 scene).
+// Virtual levels without any real neighbour are skipped via vmask.
+__global__ void __launch_bounds__(256) k_vcorner_list(Topo T, int* __restrict__ list, int* __restrict__ count) {
+    const i64 total = (i64)T.nCells * 8;
+    const int lane = threadIdx.x & 31;
+    for (i64 t0 = (i64)blockIdx.x * blockDim.x; t0 < total; t0 += (i64)gridDim.x * blockDim.x) {
+        const i64 t = t0 + threadIdx.x;
+        bool own = false;
+        if (t < total) {
+            const int l = (int)(t >> 3), j = (int)(t & 7);
+            int m;
+            own = corner_owner(T, T.cellBase + l, j, m) == T.cellBase + l;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, own);
+        int base = 0;
+        if (lane == 0 && mask) base = atomicAdd(count, __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (own) list[base + __popc(mask & ((1u << lane) - 1u))] = (int)t;
+    }
+}
+__global__ void __launch_bounds__(128) k_vvertex_values(VTree V, const int* __restrict__ list, const int* __restrict__ count, const int* __restrict__ vneigh, const unsigned* __restrict__ vmask,
                                                         const ushort4* __restrict__ voffs,
                                                         const int* __restrict__ neighs, const int* __restrict__ parent, const ushort4* __restrict__ offs,
                                                         const float* __restrict__ x, const float4* __restrict__ gridLo, const float4* __restrict__ cellD,
                                                         const float* __restrict__ baseFn, float iso, float* __restrict__ sval) {
     const int perD = vt_per(V, V.D);
-    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < T.nCells; l += gridDim.x * blockDim.x) {
-        const int id = T.cellBase + l;
+    const int n = *count;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int t = list[e], l = t >> 3, j = t & 7;
         const ushort4 o = voffs[l];
         const int r = l / perD;
-        for (int j = 0; j < 8; j++) {
-            int m;
-            if (corner_owner(T, id, j, m) != id) continue;
-            const int P[3] = {(int)o.x + (j & 1), (int)o.y + ((j >> 1) & 1), (int)o.z + ((j >> 2) & 1)};     // the corner on the depth-D grid
-            float val = 0.f;
-            int loc = l - r * perD;
-            for (int d = V.D; d >= V.rd; --d) {           // virtual levels D .. rd
-                int per = vt_per(V, d);
-                int v = V.depthAddr[d] + r * per + loc;
-                loc >>= 3;
-                unsigned mk = vmask[v];
-                if (!mk) continue;
-                const int* nb = vneigh + 27 * (i64)v;
-                const int od = V.D - d;
-                const float4 bx = bv_grid(gridLo, cellD, baseFn, V.D, d, P[0], (int)o.x >> od), by = bv_grid(gridLo, cellD, baseFn, V.D, d, P[1], (int)o.y >> od),
-                             bz = bv_grid(gridLo, cellD, baseFn, V.D, d, P[2], (int)o.z >> od);
-                const float vx[3] = {bx.x, bx.y, bx.z}, vy[3] = {by.x, by.y, by.z}, vz[3] = {bz.x, bz.y, bz.z};
+        const int P[3] = {(int)o.x + (j & 1), (int)o.y + ((j >> 1) & 1), (int)o.z + ((j >> 2) & 1)};     // the corner on the depth-D grid
+        float val = 0.f;
+        int loc = l - r * perD;
+        for (int d = V.D; d >= V.rd; --d) {           // virtual levels D .. rd
+            int per = vt_per(V, d);
+            int v = V.depthAddr[d] + r * per + loc;
+            loc >>= 3;
+            unsigned mk = vmask[v];
+            if (!mk) continue;
+            const int* nb = vneigh + 27 * (i64)v;
+            const int od = V.D - d;
+            const float4 bx = bv_grid(gridLo, cellD, baseFn, V.D, d, P[0], (int)o.x >> od), by = bv_grid(gridLo, cellD, baseFn, V.D, d, P[1], (int)o.y >> od),
+                         bz = bv_grid(gridLo, cellD, baseFn, V.D, d, P[2], (int)o.z >> od);
+            const float vx[3] = {bx.x, bx.y, bx.z}, vy[3] = {by.x, by.y, by.z}, vz[3] = {bz.x, bz.y, bz.z};
 #pragma unroll
-                for (int jj = 0; jj < 27; jj++) {
-                    if (!(mk & (1u << jj))) continue;
-                    int q = nb[jj];
-                    if (q >= V.M) q = V.roots[q - V.M - V.depthAddr[V.rd]];   // virtual root -> the real leaf it replaces
-                    val = __fmaf_rn(__fmul_rn(__fmul_rn(x[q], vx[jj / 9]), vy[(jj / 3) % 3]), vz[jj % 3], val);
-                }
+            for (int jj = 0; jj < 27; jj++) {
+                if (!(mk & (1u << jj))) continue;
+                int q = nb[jj];
+                if (q >= V.M) q = V.roots[q - V.M - V.depthAddr[V.rd]];   // virtual root -> the real leaf it replaces
+                val = __fmaf_rn(__fmul_rn(__fmul_rn(x[q], vx[jj / 9]), vy[(jj / 3) % 3]), vz[jj % 3], val);
             }
-            int now = parent[V.roots[r]];                 // real ancestors
-            while (now != -1) {
-                accumulate_level_grid(val, neighs + 27 * (i64)now, offs[now], x, gridLo, cellD, baseFn, V.D, P);
-                now = parent[now];
-            }
-            sval[8 * (i64)l + j] = __fsub_rn(val, iso);
         }
+        int now = parent[V.roots[r]];                 // real ancestors
+        while (now != -1) {
+            accumulate_level_grid(val, neighs + 27 * (i64)now, offs[now], x, gridLo, cellD, baseFn, V.D, P);
+            now = parent[now];
+        }
+        sval[8 * (i64)l + j] = __fsub_rn(val, iso);
     }
 }
 __global__ void __launch_bounds__(256) k_offset_triangles(int* __restrict__ t, i64 n, int off) {
@@ -1616,7 +1634,16 @@ static int refine_pass(Context& c, const int* dRoots, int nr, int rd, bool singl
     PRB_TRY(vmask.alloc((size_t)total, st));
     PRB_LAUNCH(c, k_vmask, grid_for(c, total, 256), 256, 0, V, total, vneigh.p, vmask.p);
     PRB_TRY(ensure_bv_tables(c));
-    PRB_LAUNCH(c, k_vvertex_values, grid_for(c, nD, 128, 16), 128, 0, V, T, vneigh.p, vmask.p, voffs.p, c.neighs.p, c.parent.p, c.offs.p, c.xv, (const float4*)c.dBvGrid.p, (const float4*)c.dBvCell.p, c.dBaseFn.p, c.iso, sval.p);
+    {
+        if ((i64)nD * 8 > 0x7fffffffll) { set_error("refinement pass too large"); return PRB_ERR_NOMEM; }
+        DBuf<int> clist, ccount;
+        PRB_TRY(clist.alloc(4 * (size_t)nD, st));         // a grid point has ONE owner and a root's cells have (n+1)^3 <= 3.375 n^3 grid points
+        PRB_TRY(ccount.alloc(1, st));
+        PRB_CUDA(cudaMemsetAsync(ccount.p, 0, sizeof(int), st));
+        PRB_LAUNCH(c, k_vcorner_list, grid_for(c, (i64)nD * 8, 256, 8), 256, 0, T, clist.p, ccount.p);
+        PRB_LAUNCH(c, k_vvertex_values, grid_for(c, (i64)nD * 2, 128, 16), 128, 0, V, (const int*)clist.p, (const int*)ccount.p, vneigh.p, vmask.p, voffs.p, c.neighs.p, c.parent.p, c.offs.p, c.xv,
+                   (const float4*)c.dBvGrid.p, (const float4*)c.dBvCell.p, c.dBaseFn.p, c.iso, sval.p);
+    }
     outs.emplace_back();
     PassOut& po = outs.back();
     PRB_TRY(run_mc_on_cells(c, T, local_view(sval.p, T.cellBase), voffs.p, false, nullptr, po));

@@ -46,3 +46,47 @@ def test_cli_errors(tmp_path):
     assert r.returncode != 0
     r = subprocess.run([EXE, "--out", str(tmp_path / "o.ply")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
     assert r.returncode == 2 and "usage" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cli_dump_and_weld(tmp_path):
+    """--dump writes the parity arrays of prb_get_array as raw files; --weld merges the seam vertices the passes duplicate."""
+    from poissonrecon_gpu_b200 import PoissonRecon, plyio, synth
+    p, n = synth.sphere(8_000, seed=9)          # sparse deep tree: several refinement passes with seams
+    depth = 8
+    inp, out, outw, dump = str(tmp_path / "in.bnpts"), str(tmp_path / "out.ply"), str(tmp_path / "outw.ply"), str(tmp_path / "dump")
+    plyio.write_bnpts(inp, p, n)
+    r = subprocess.run([EXE, "--in", inp, "--out", out, "--depth", str(depth), "--binary", "--dump", dump], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:]
+    pr = PoissonRecon(depth)
+    pr.set_points(p, n)
+    pr.run()
+    for name, dt in (("key", "<u8"), ("neighs", "<i4"), ("x", "<f4"), ("divergence", "<f4"), ("passes", "<i4"), ("iso", "<f4")):
+        assert np.array_equal(np.fromfile(os.path.join(dump, name + ".bin"), dt), pr.get(name, dt)), name
+    v, t = plyio.read_mesh_ply(out)
+    r = subprocess.run([EXE, "--in", inp, "--out", outw, "--depth", str(depth), "--binary", "--weld"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:]
+    vw, tw = plyio.read_mesh_ply(outw)
+    assert tw.shape == t.shape and vw.shape[0] < v.shape[0]
+    assert np.array_equal(vw[tw], v[t])                               # same triangles, position by position
+    assert np.unique(vw, axis=0).shape[0] == vw.shape[0]              # no two welded vertices coincide
+    pr.close()
+
+
+@pytest.mark.gpu
+def test_cli_two_gpus_matches_one(tmp_path):
+    """--gpus 2 (forked ranks, CUDA-IPC arenas, distributed mesh assembled by rank 0) writes the same file as --gpus 1."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from poissonrecon_gpu_b200 import plyio, synth
+    p, n, depth = synth.make("torus1m_d9", 300_000)
+    inp = str(tmp_path / "in.bnpts")
+    plyio.write_bnpts(inp, p, n)
+    outs = []
+    for g in (1, 2):
+        out = str(tmp_path / f"out{g}.ply")
+        r = subprocess.run([EXE, "--in", inp, "--out", out, "--depth", str(depth), "--binary", "--gpus", str(g)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:]
+        outs.append(open(out, "rb").read())
+    assert outs[0] == outs[1]
