@@ -880,7 +880,7 @@ __device__ __noinline__ float rv_fine_levels(const RGeom& G, const int* __restri
     return val;
 }
 
-__global__ void __launch_bounds__(64) k_rv_brick_values(RGeom G, const int* __restrict__ list) {
+__global__ void __launch_bounds__(64) k_rv_brick_values(RGeom G, const int* __restrict__ list, const int* __restrict__ listCount, int nAll) {
     __shared__ __align__(16) float sX[kMaxDepth + 1][28];
     __shared__ int sIds[27];
     __shared__ int sAny[kMaxDepth + 1];
@@ -892,7 +892,11 @@ __global__ void __launch_bounds__(64) k_rv_brick_values(RGeom G, const int* __re
         lut_parent_child(t / 27, t % 27, pj, cc);
         sLut[t] = (unsigned char)(pj | (cc << 5));
     }
-    const i64 cell0 = (i64)(list ? list[blockIdx.x] : (int)blockIdx.x) * 512;
+    // the list length stays on the device (no host round trip between the brick selection and the evaluation): persistent CTAs
+    const int nWork = list ? *listCount : nAll;
+    for (int work = blockIdx.x; work < nWork; work += gridDim.x) {
+    __syncthreads();
+    const i64 cell0 = (i64)(list ? list[work] : work) * 512;
     const int r = (int)(cell0 / G.per);
     const unsigned l0 = (unsigned)(cell0 - (i64)r * G.per);
     const int L = G.D - 3;                                   // level of the brick
@@ -963,6 +967,7 @@ __global__ void __launch_bounds__(64) k_rv_brick_values(RGeom G, const int* __re
     }
 #pragma unroll
     for (int cz = 0; cz < 8; cz++) G.val7[cell0 + (lxy - l0) + spread3((unsigned)cz)] = __fsub_rn(val[cz], G.iso);
+    }
 }
 
 // virtual cell at root-local coordinates (x,y,z), each in [-1, n]: which root of the pass holds
@@ -1370,11 +1375,14 @@ __global__ void __launch_bounds__(256) k_brick_flags(const int* __restrict__ bri
 }
 // emission of one active brick per CTA: vertices of the owned crossed edges, then the triangles
 // (vertex ids through the owner cell's brick base + in-brick prefix + rank of the edge in its mask)
-__global__ void __launch_bounds__(512) k_rv_emit_brick(RGeom G, const int* __restrict__ active, const unsigned char* __restrict__ cat, const unsigned short* __restrict__ emask,
+__global__ void __launch_bounds__(512) k_rv_emit_brick(RGeom G, const int* __restrict__ active, const int* __restrict__ activeCount, const unsigned char* __restrict__ cat, const unsigned short* __restrict__ emask,
                                                        const unsigned short* __restrict__ vpre, const int* __restrict__ brickVBase, const int* __restrict__ brickTBase,
                                                        float* __restrict__ outV, int* __restrict__ outT) {
     __shared__ int sScan[33];
-    const int b = active[blockIdx.x], tid = threadIdx.x;
+    const int tid = threadIdx.x;
+    const int nWork = *activeCount;
+    for (int work = blockIdx.x; work < nWork; work += gridDim.x) {
+    const int b = active[work];
     const i64 t = (i64)b * 512 + tid;
     const int r = (int)(t / G.per);
     const unsigned l = (unsigned)(t - (i64)r * G.per);
@@ -1410,6 +1418,7 @@ __global__ void __launch_bounds__(512) k_rv_emit_brick(RGeom G, const int* __res
         int e = cMcTri[c][j], e2;
         const i64 ow = rv_edge_owner(G, r, cx, cy, cz, e, e2);
         outT[3 * (i64)tb + j] = brickVBase[(int)(ow >> 9)] + (int)vpre[ow] + __popc((unsigned)emask[ow] & ((1u << e2) - 1u));
+    }
     }
 }
 struct PassOut {
@@ -1530,11 +1539,16 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     }
     PRB_LAUNCH(c, k_rv_brick_full, grid_for(c, nBricks, 256), 256, 0, G, nBricks, cert.p, full.p);
     PRB_LAUNCH(c, k_rv_brick_needed, grid_for(c, nBricks, 256), 256, 0, G, nBricks, full.p, needFlag.p, needLow.p);
+    // (the counts of the selected bricks stay on the device: the kernels that consume the lists read them there)
+    DBuf<int> dCounts;
+    PRB_TRY(dCounts.alloc(2, st));
     i64 nNeeded = 0;
-    PRB_TRY(exclusive_scan(c, needFlag.p, needExcl.p, nBricks, &nNeeded));
+    PRB_TRY(exclusive_scan(c, needFlag.p, needExcl.p, nBricks, c.refineBoundCheck ? &nNeeded : nullptr));
+    PRB_CUDA(cudaMemcpyAsync(dCounts.p, c.scanWork.ticket + 1, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    const unsigned persist = (unsigned)std::min<i64>(nBricks, (i64)c.smCount * 32);
     if (c.refineBoundCheck) {
         // debug / test mode: evaluate everything and verify every certificate against the real values
-        PRB_LAUNCH(c, k_rv_brick_values, (unsigned)nBricks, 64, 0, G, (const int*)nullptr);
+        PRB_LAUNCH(c, k_rv_brick_values, persist, 64, 0, G, (const int*)nullptr, (const int*)nullptr, nBricks);
         DBuf<unsigned char> sign;
         DBuf<int> bad;
         PRB_TRY(sign.alloc((size_t)nBricks, st)); PRB_TRY(bad.alloc(1, st));
@@ -1547,10 +1561,10 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
         sign.release(); bad.release();
         c.boundChecked += nBricks; c.boundEvaluated += nNeeded;
         if (hb) { set_error("refinement: " + std::to_string(hb) + " bricks certified with the wrong sign (depth " + std::to_string(rd) + " pass)"); return PRB_ERR_STATE; }
-    } else if (nNeeded) {
-        PRB_TRY(needList.alloc((size_t)nNeeded, st));
+    } else {
+        PRB_TRY(needList.alloc((size_t)nBricks, st));
         PRB_LAUNCH(c, k_compact_ids, grid_for(c, nBricks, 256), 256, 0, needFlag.p, needExcl.p, nBricks, needList.p);
-        PRB_LAUNCH(c, k_rv_brick_values, (unsigned)nNeeded, 64, 0, G, (const int*)needList.p);
+        PRB_LAUNCH(c, k_rv_brick_values, persist, 64, 0, G, (const int*)needList.p, (const int*)dCounts.p, 0);
     }
     PRB_LAUNCH(c, k_rv_low_values, grid_for(c, (i64)nr * 3 * n1 * n1, 128, 16), 128, 0, G, c.refineBoundCheck ? (const unsigned char*)nullptr : (const unsigned char*)needLow.p);
     cert.release(); needFlag.release(); needExcl.release(); needList.release(); needLow.release();
@@ -1564,30 +1578,24 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     PRB_LAUNCH(c, k_rv_classify_brick, (unsigned)std::min(nBricks, c.smCount * 4), 512, 0, G, full.p, cat.p, emask.p, c.wsVpre.p, brickV.p, brickT.p, nBricks);
     full.release();
     PRB_LAUNCH(c, k_brick_flags, grid_for(c, nBricks, 256), 256, 0, brickV.p, brickT.p, nBricks, bflag.p);
-    i64 totV = 0, totT = 0, nActive = 0;
+    i64 totV = 0, totT = 0;
+    PRB_TRY(exclusive_scan(c, bflag.p, bexcl.p, nBricks, nullptr));
+    PRB_CUDA(cudaMemcpyAsync(dCounts.p + 1, c.scanWork.ticket + 1, sizeof(int), cudaMemcpyDeviceToDevice, st));
     PRB_TRY(exclusive_scan(c, brickV.p, brickVBase.p, nBricks, nullptr));
-    PRB_TRY(exclusive_scan(c, brickT.p, brickTBase.p, nBricks, nullptr));
-    PRB_TRY(exclusive_scan(c, bflag.p, bexcl.p, nBricks, &nActive));
-    {
-        int last[4] = {0, 0, 0, 0};     // totals = base + count of the last brick
-        PRB_CUDA(cudaMemcpyAsync(&last[0], brickVBase.p + nBricks - 1, 4, cudaMemcpyDeviceToHost, st));
-        PRB_CUDA(cudaMemcpyAsync(&last[1], brickV.p + nBricks - 1, 4, cudaMemcpyDeviceToHost, st));
-        PRB_CUDA(cudaMemcpyAsync(&last[2], brickTBase.p + nBricks - 1, 4, cudaMemcpyDeviceToHost, st));
-        PRB_CUDA(cudaMemcpyAsync(&last[3], brickT.p + nBricks - 1, 4, cudaMemcpyDeviceToHost, st));
-        PRB_CUDA(cudaStreamSynchronize(st));
-        totV = (i64)last[0] + last[1];
-        totT = (i64)last[2] + last[3];
-    }
+    PRB_CUDA(cudaMemcpyAsync(c.hScanTotal + 1, c.scanWork.ticket + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PRB_TRY(exclusive_scan(c, brickT.p, brickTBase.p, nBricks, &totT));       // (the one host round trip of the pass: the output sizes)
+    totV = c.hScanTotal[1];
     outs.emplace_back();
     PassOut& po = outs.back();
     po.nv = (int)totV;
     po.nt = (int)totT;
     PRB_TRY(po.v.alloc(3 * (size_t)totV, st));
     PRB_TRY(po.t.alloc(3 * (size_t)totT, st));
-    if (nActive) {
-        PRB_TRY(active.alloc((size_t)nActive, st));
+    if (totV || totT) {
+        PRB_TRY(active.alloc((size_t)nBricks, st));
         PRB_LAUNCH(c, k_compact_ids, grid_for(c, nBricks, 256), 256, 0, bflag.p, bexcl.p, nBricks, active.p);
-        PRB_LAUNCH(c, k_rv_emit_brick, (unsigned)nActive, 512, 0, G, active.p, cat.p, emask.p, c.wsVpre.p, brickVBase.p, brickTBase.p, po.v.p, po.t.p);
+        PRB_LAUNCH(c, k_rv_emit_brick, (unsigned)std::min<i64>(nBricks, (i64)c.smCount * 8), 512, 0, G, active.p, (const int*)(dCounts.p + 1), cat.p, emask.p, c.wsVpre.p, brickVBase.p,
+                   brickTBase.p, po.v.p, po.t.p);
     }
     brickV.release(); brickT.release(); brickVBase.release(); brickTBase.release(); bflag.release(); bexcl.release(); active.release();
     if (single && po.nv == 0) {      // main.cu:4095-4103: nothing is inserted for a coarse root without crossings

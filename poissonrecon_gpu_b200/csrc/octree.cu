@@ -128,6 +128,26 @@ int sort_passes(int keyBits);
 int sort_digit_bits(int keyBits);
 int radix_sort_gather(Context& c, u64* keys0, int* idx0, u64* keysTmp, int* idxTmp, int* counts, i64 n, int keyBits, const float* P0, const float* N0,
                       u64* keysOut, int* idxOut, float* P, float* Nr);
+// number of non-empty nodes of EVERY depth in one pass over the sorted keys: sample i starts a new node at depth d iff its key differs from
+// its predecessor's in the top 3 d bits, i.e. at every depth >= h(i) = the level of the highest differing bit.  hist[h] counts the samples
+// by h; U_d = sum_{h <= d} hist[h].  One host round trip for all levels instead of one per level.
+__global__ void __launch_bounds__(256) k_level_counts(const u64* __restrict__ key, i64 n, int D, int* __restrict__ hist) {
+    __shared__ int sH[kMaxDepth + 2];
+    if (threadIdx.x <= kMaxDepth) sH[threadIdx.x] = 0;
+    __syncthreads();
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        int h = 0;                                      // sample 0 starts a node at every depth
+        if (i > 0) {
+            const u64 x = key[i] ^ key[i - 1];
+            if (x == 0) continue;
+            const int top = 63 - __clzll((long long)x);  // highest differing bit; level l owns the bits [3 (D - l), 3 (D - l) + 2]
+            h = D - top / 3;
+        }
+        atomicAdd(&sH[h], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x <= kMaxDepth && sH[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sH[threadIdx.x]);
+}
 // run heads: first element of every run of equal (key >> shift)
 __global__ void __launch_bounds__(256) k_head_flags(const u64* __restrict__ key, i64 n, int shift, int* __restrict__ flag) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
@@ -420,13 +440,22 @@ int stage_octree(Context& c) {
     PRB_TRY(flagN.alloc((size_t)N, st));
     PRB_TRY(exclN.alloc((size_t)N, st));
     PRB_LAUNCH(c, k_head_flags, grid_for(c, N, 256), 256, 0, c.sortedKey.p, N, 0, flagN.p);
-    i64 nLeaves = 0;
-    PRB_TRY(exclusive_scan(c, flagN.p, exclN.p, N, &nLeaves));
-    // per-level lists of non-empty nodes
+    PRB_TRY(exclusive_scan(c, flagN.p, exclN.p, N, nullptr));
+    // per-level lists of non-empty nodes; their sizes U_d for all depths from one kernel + one host round trip
     std::vector<DBuf<u64>> lkey(D + 1);
     std::vector<DBuf<int>> fp(D + 1), fc(D + 1), fdm1(D + 1), prank(D + 1), slot(D + 1);
     std::vector<int> U(D + 1, 0);
-    U[D] = (int)nLeaves;
+    {
+        DBuf<int> hist;
+        PRB_TRY(hist.alloc(kMaxDepth + 2, st));
+        PRB_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(int) * (kMaxDepth + 2), st));
+        PRB_LAUNCH(c, k_level_counts, grid_for(c, N, 256, 4), 256, 0, c.sortedKey.p, N, D, hist.p);
+        int h[kMaxDepth + 2];
+        PRB_CUDA(cudaMemcpyAsync(h, hist.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+        PRB_CUDA(cudaStreamSynchronize(st));
+        int acc = 0;
+        for (int d = 0; d <= D; d++) { acc += h[d]; U[d] = acc; }
+    }
     PRB_TRY(lkey[D].alloc((size_t)U[D], st));
     PRB_TRY(fp[D].alloc((size_t)U[D] + 1, st));
     PRB_LAUNCH(c, k_compact_leaves, grid_for(c, N, 256), 256, 0, c.sortedKey.p, flagN.p, exclN.p, N, lkey[D].p, fp[D].p, U[D]);
@@ -437,9 +466,8 @@ int stage_octree(Context& c) {
         PRB_TRY(fl.alloc((size_t)n, st));
         PRB_TRY(ex.alloc((size_t)n, st));
         PRB_LAUNCH(c, k_head_flags, grid_for(c, n, 256), 256, 0, lkey[d].p, (i64)n, 3 * (D - d + 1), fl.p);
-        i64 np = 0;
-        PRB_TRY(exclusive_scan(c, fl.p, ex.p, n, &np));
-        U[d - 1] = (int)np;
+        const i64 np = U[d - 1];
+        PRB_TRY(exclusive_scan(c, fl.p, ex.p, n, nullptr));
         PRB_TRY(lkey[d - 1].alloc((size_t)np, st));
         PRB_TRY(fp[d - 1].alloc((size_t)np + 1, st));
         PRB_TRY(fc[d - 1].alloc((size_t)np + 1, st));
