@@ -195,6 +195,8 @@ struct Context {
     double cgTol = 1e-5;
     int cgMaxIter = 10000;
     int cgZigzag = 1;
+    int cgTiming = 0;              // 1: CTA 0 of the CG kernel records the time it spends in every phase and barrier ("cg_phase_ns")
+    long long cgPhaseNs[8] = {0};
     int cgBulk = 1;                // CG streaming phases through TMA bulk copies (solver.cu stream_pairs_bulk); 0: per-thread cp.async ring
     int refineBoundCheck = 0;      // 1: evaluate every refinement brick and verify the certified signs (tests)
     long long boundChecked = 0, boundEvaluated = 0;
@@ -260,6 +262,12 @@ struct Context {
     DBuf<unsigned short> wsEmask, wsVpre;
     DBuf<int> wsVbase, wsTbase;
     prb_stats stats;
+    // ---- optional sub-stage timeline (prb_set_option "detail", 1): events recorded at named points of the run; the intervals between
+    // consecutive marks are reported by prb_get_array("detail_ms") / ("detail_names", NUL-separated)
+    int detail = 0;
+    std::vector<cudaEvent_t> detailEv;
+    std::vector<std::string> detailName;
+    size_t detailUsed = 0;
     // ---- multi-GPU
     MgState mg;
     int shardFrom = 0;                         // first sharded depth (D+1: none); set by stage_octree
@@ -272,6 +280,13 @@ struct Context {
     size_t mgVvalOff = 0;
     float* vvalPtr = nullptr;                  // where the corner values of the current run live (vval.p or mgVval)
 };
+
+inline void mark(Context& c, const char* name) {
+    if (!c.detail) return;
+    if (c.detailUsed == c.detailEv.size()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; c.detailEv.push_back(e); c.detailName.emplace_back(); }
+    c.detailName[c.detailUsed] = name;
+    cudaEventRecord(c.detailEv[c.detailUsed++], c.stream);
+}
 
 // stages (implemented in the .cu files)
 int stage_octree(Context& c);

@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(256) k_profile_up(const int* __restrict__ chil
 // b_o for the nodes of ONE depth d <= D-2 from the profiles of their 27 neighbours.
 // k = 2^(D-d) <= 8: one warp per node, lane j = neighbour j: its 3k profile entries are one contiguous run of doubles.
 template <int LK>
-__global__ void __launch_bounds__(256) k_div_coarse_small(const int* __restrict__ neighs, const double* __restrict__ prof, const float* __restrict__ row, int base, int count,
+__global__ void __launch_bounds__(256) k_div_coarse_small(const int* __restrict__ neighs, const double* __restrict__ prof, const float* __restrict__ row, int base, int first, int count,
                                                           float* __restrict__ divg) {
     constexpr int K = 1 << LK;
     const int lane = threadIdx.x & 31;
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(256) k_div_coarse_small(const int* __restrict_
 #pragma unroll
             for (int t = 0; t < K; t++) T[a * K + t] = (double)row[(dj[a] << LK) + t];
     }
-    for (int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; l < count; l += (gridDim.x * blockDim.x) >> 5) {
+    for (int l = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); l < first + count; l += (gridDim.x * blockDim.x) >> 5) {
         double acc = 0.0;
         if (lane < 27) {
             const int n = neighs[27 * (i64)(base + l) + lane];
@@ -514,14 +514,15 @@ __global__ void __launch_bounds__(256) k_div_coarse_small(const int* __restrict_
 // k >= 16: a group of G threads (a warp, or a whole block for the coarse depths with few nodes and thousands of entries per
 // neighbour) per node; the 81 (neighbour, axis) runs of k entries are flattened over the group, entries fastest (coalesced)
 template <int G>
-__global__ void __launch_bounds__(256) k_div_coarse_wide(const int* __restrict__ neighs, const double* __restrict__ prof, const float* __restrict__ row, int base, int count, int lk,
+__global__ void __launch_bounds__(256) k_div_coarse_wide(const int* __restrict__ neighs, const double* __restrict__ prof, const float* __restrict__ row, int base, int first, int nRows, int lk,
                                                          float* __restrict__ divg) {
     __shared__ double sRed[8];
     __shared__ int sNb[8][27];
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const int k = 1 << lk, total = 81 << lk;
     const int groupsPerBlock = 256 / G, gInBlock = threadIdx.x / G, tInGroup = threadIdx.x % G;
-    for (int l0 = blockIdx.x * groupsPerBlock; l0 < count; l0 += gridDim.x * groupsPerBlock) {
+    const int count = first + nRows;
+    for (int l0 = first + blockIdx.x * groupsPerBlock; l0 < count; l0 += gridDim.x * groupsPerBlock) {
         const int l = l0 + gInBlock;
         __syncthreads();
         if (tInGroup < 27 && l < count) sNb[gInBlock][tInGroup] = neighs[27 * (i64)(base + l) + tInGroup];
@@ -574,11 +575,13 @@ int stage_splat(Context& c) {
         if (g1 > g0) PRB_LAUNCH(c, k_splat, grid_for(c, (i64)(g1 - g0) * 8, 128, 16), 128, 0, W.p, c.Nr.p, c.neighs.p, c.pidx.p, c.pnum.p, c.base[D], g0, g1, c.Vp);
         W.release();
     }
+    mark(c, "splat:kernels");
     if (shard) {
         long long lo[kMaxRanks + 1];
         for (int r = 0; r <= c.mg.world; r++) lo[r] = c.rowLo[D][r] - c.base[D];
         PRB_TRY(mg_allgather(c, c.mgVOff, 12, lo));
     }
+    mark(c, "splat:done");
     PRB_CUDA(cudaEventRecord(c.ev[3], st));
     PRB_TRY(stage_divergence(c));
     PRB_CUDA(cudaGetLastError());
@@ -609,6 +612,7 @@ static int stage_divergence_blocks(Context& c) {
                        leaf0, leaf1, dm0, dm1, c.divgv);
         }
     }
+    mark(c, "div:fine");
     if (D < 2) return PRB_OK;
     // ---- depths <= D-2 through the per-axis profiles (every rank computes all of them: 6 % of the nodes)
     std::vector<size_t> off(D + 1, 0);
@@ -622,11 +626,16 @@ static int stage_divergence_blocks(Context& c) {
     for (int d = D - 2; d >= 0; --d) {
         const float* row = c.dDfT.p + c.tab.dfOffset[d];
         const int lk = D - d;
-        if (lk == 2) PRB_LAUNCH(c, k_div_coarse_small<2>, grid_for(c, (i64)c.cnt[d] * 32, 256), 256, 0, c.neighs.p, prof.p + off[d], row, c.base[d], c.cnt[d], c.divgv);
-        else if (lk == 3) PRB_LAUNCH(c, k_div_coarse_small<3>, grid_for(c, (i64)c.cnt[d] * 32, 256), 256, 0, c.neighs.p, prof.p + off[d], row, c.base[d], c.cnt[d], c.divgv);
-        else if (lk == 4) PRB_LAUNCH(c, k_div_coarse_wide<32>, grid_for(c, (i64)c.cnt[d] * 32, 256), 256, 0, c.neighs.p, prof.p + off[d], row, c.base[d], c.cnt[d], lk, c.divgv);
-        else PRB_LAUNCH(c, k_div_coarse_wide<256>, std::max(1, std::min(c.cnt[d], c.smCount * 8)), 256, 0, c.neighs.p, prof.p + off[d], row, c.base[d], c.cnt[d], lk, c.divgv);
+        // multi-GPU: at a sharded depth a rank only needs the right-hand side of its own rows (the profiles are complete everywhere)
+        const bool sh = mg && d >= c.shardFrom;
+        const int first = sh ? c.rowLo[d][c.mg.rank] - c.base[d] : 0, n = sh ? c.rowLo[d][c.mg.rank + 1] - c.rowLo[d][c.mg.rank] : c.cnt[d];
+        if (n <= 0) continue;
+        if (lk == 2) PRB_LAUNCH(c, k_div_coarse_small<2>, grid_for(c, (i64)n * 32, 256), 256, 0, c.neighs.p, prof.p + off[d], row, c.base[d], first, n, c.divgv);
+        else if (lk == 3) PRB_LAUNCH(c, k_div_coarse_small<3>, grid_for(c, (i64)n * 32, 256), 256, 0, c.neighs.p, prof.p + off[d], row, c.base[d], first, n, c.divgv);
+        else if (lk == 4) PRB_LAUNCH(c, k_div_coarse_wide<32>, grid_for(c, (i64)n * 32, 256), 256, 0, c.neighs.p, prof.p + off[d], row, c.base[d], first, n, lk, c.divgv);
+        else PRB_LAUNCH(c, k_div_coarse_wide<256>, std::max(1, std::min(n, c.smCount * 8)), 256, 0, c.neighs.p, prof.p + off[d], row, c.base[d], first, n, lk, c.divgv);
     }
+    mark(c, "div:coarse");
     prof.release();
     PRB_CUDA(cudaGetLastError());
     return PRB_OK;

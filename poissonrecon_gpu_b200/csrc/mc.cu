@@ -141,6 +141,7 @@ __global__ void k_mg_publish_sum(MgDev mg, const double* __restrict__ v) {
 
 int stage_iso(Context& c) {
     cudaStream_t st = c.stream;
+    mark(c, "iso:begin");
     PRB_TRY(c.pointValue.alloc((size_t)c.N, st));
     DBuf<double> sum;
     PRB_TRY(sum.alloc(1, st));
@@ -371,7 +372,14 @@ __device__ __forceinline__ void accumulate_level_grid(float& val, const int* __r
 // lanes busy instead of one in four.
 constexpr int kVsWarps = 4, kVsChunk = 32, kVsSlots = 4;
 constexpr int kVsSlotStride = kMaxDepth * 28 + 8;     // floats; 8 mod 32 apart: the four slots sit in different banks
-__global__ void __launch_bounds__(kVsWarps * 32) k_vertex_values_stream(Topo T, int gFirst, int nGroups, int D, const int* __restrict__ parent, const int* __restrict__ child0,
+// The groups to evaluate: up to 16 contiguous ranges (multi-GPU: the replicated depths + this rank's share of every sharded depth) cut
+// into chunks of `chunk` groups; the chunks of all ranges form one index space, so ONE launch covers them and a small problem is
+// spread over many short chunks instead of a few long sequential ones.
+struct VsRanges {
+    int n, chunk;
+    int first[16], count[16], chunk0[17];
+};
+__global__ void __launch_bounds__(kVsWarps * 32) k_vertex_values_stream(Topo T, const __grid_constant__ VsRanges RG, int D, const int* __restrict__ parent, const int* __restrict__ child0,
                                                                         const ushort4* __restrict__ offs, const float* __restrict__ x,
                                                                         const float* __restrict__ baseFn, const __grid_constant__ BvTables B, float iso, float* __restrict__ vval) {
     __shared__ __align__(16) float sX[kVsWarps][kVsSlots * kVsSlotStride];   // [slot][level][28]: neighbour values of the slot's cached ancestors
@@ -381,11 +389,14 @@ __global__ void __launch_bounds__(kVsWarps * 32) k_vertex_values_stream(Topo T, 
     __shared__ ushort4 sO0[kVsWarps][kVsSlots];
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const int px = lane / 9, py = (lane / 3) % 3, pz = lane % 3;      // lane -> point of a group's 3x3x3 corner grid (staging)
-    const int nChunks = (nGroups + kVsChunk - 1) / kVsChunk;
+    const int nChunks = RG.chunk0[RG.n];
     for (int ch = blockIdx.x * kVsWarps + wp; ch < nChunks; ch += gridDim.x * kVsWarps) {
-        const int gEnd = min(gFirst + nGroups, gFirst + (ch + 1) * kVsChunk);
+        int rg = 0;
+        while (rg + 1 < RG.n && ch >= RG.chunk0[rg + 1]) rg++;
+        const int gFirst = RG.first[rg] + (ch - RG.chunk0[rg]) * RG.chunk;
+        const int gEnd = min(RG.first[rg] + RG.count[rg], gFirst + RG.chunk);
         int curDepth = -1;
-        for (int g0 = gFirst + ch * kVsChunk; g0 < gEnd;) {
+        for (int g0 = gFirst; g0 < gEnd;) {
             const int d0 = offs[1 + 8 * g0].w;
             const float w = 1.0f / (float)(1 << d0);
             __syncwarp();
@@ -1740,17 +1751,33 @@ int stage_extract(Context& c) {
         BvTables B;
         B.anc = (const float4*)c.dBvAnc.p; B.own = (const float4*)c.dBvOwn.p; B.cellD = (const float4*)c.dBvCell.p; B.gridLo = (const float4*)c.dBvGrid.p;
         for (int d = 0; d <= kMaxDepth; d++) { B.ancOff[d] = c.bvAncOff[d]; B.ownOff[d] = c.bvOwnOff[d]; }
-        auto launch = [&](int g0, int g1) {
-            if (g1 <= g0) return;
-            const i64 nChunks = ((i64)(g1 - g0) + kVsChunk - 1) / kVsChunk;
-            PRB_LAUNCH(c, k_vertex_values_stream, grid_for(c, nChunks * 32, kVsWarps * 32, 8), kVsWarps * 32, 0, R, g0, g1 - g0, D, c.parent.p, c.child0.p, c.offs.p,
+        VsRanges RG;
+        RG.n = 0;
+        i64 totalGroups = 0;
+        auto add = [&](int g0, int g1) {
+            if (g1 <= g0 || RG.n >= 16) return;
+            RG.first[RG.n] = g0; RG.count[RG.n] = g1 - g0; RG.n++;
+            totalGroups += g1 - g0;
+        };
+        auto launch = [&]() {
+            if (!RG.n) return;
+            // chunk length: long enough to reuse the cached ancestors, short enough that every SM gets several warps' worth of chunks
+            i64 ck = totalGroups / ((i64)c.smCount * 32);
+            RG.chunk = (int)std::min<i64>(kVsChunk, std::max<i64>(4, ck & ~(i64)3));
+            RG.chunk0[0] = 0;
+            for (int k = 0; k < RG.n; k++) RG.chunk0[k + 1] = RG.chunk0[k] + (RG.count[k] + RG.chunk - 1) / RG.chunk;
+            for (int k = RG.n; k < 16; k++) { RG.first[k] = 0; RG.count[k] = 0; RG.chunk0[k + 1] = RG.chunk0[RG.n]; }
+            const i64 nChunks = RG.chunk0[RG.n];
+            PRB_LAUNCH(c, k_vertex_values_stream, grid_for(c, nChunks * 32, kVsWarps * 32, 8), kVsWarps * 32, 0, R, RG, D, c.parent.p, c.child0.p, c.offs.p,
                        c.xv, c.dBaseFn.p, B, c.iso, c.vvalPtr);
         };
         if (!shard) {
-            launch(0, (M - 1) / 8);
+            add(0, (M - 1) / 8);
+            launch();
         } else {
-            launch(0, (c.base[c.shardFrom] - 1) / 8);
-            for (int d = c.shardFrom; d <= D; d++) launch((c.rowLo[d][me] - 1) / 8, (c.rowLo[d][me + 1] - 1) / 8);
+            add(0, (c.base[c.shardFrom] - 1) / 8);
+            for (int d = c.shardFrom; d <= D; d++) add((c.rowLo[d][me] - 1) / 8, (c.rowLo[d][me + 1] - 1) / 8);
+            launch();
             PRB_TRY(mg_barrier(c));
             for (int qi = 1; qi < W; qi++) {          // start with the next rank: the peers are not all pulled from in the same order
                 const int q = (me + qi) % W;
@@ -1763,6 +1790,7 @@ int stage_extract(Context& c) {
             PRB_TRY(mg_barrier(c));
         }
     }
+    mark(c, "extract:corner_values");
     // ---- main pass
     DBuf<unsigned> fmarkL;
     unsigned* fmark = nullptr;
@@ -1794,6 +1822,7 @@ int stage_extract(Context& c) {
         PRB_TRY(run_mc_on_cells(c, R, local_view(c.vvalPtr, 0), c.offs.p + c.base[D], true, fmark, outs.back()));
         sh.rankV[0] = outs.back().nv; sh.rankT[0] = outs.back().nt;
     }
+    mark(c, "extract:main_pass");
     const int nMainParts = shard ? W : 1;
     // ---- leaves to refine (multi-GPU: the same list on every rank, from the OR of all ranks' face marks)
     DBuf<int> flag, excl, subIds;
@@ -1814,6 +1843,7 @@ int stage_extract(Context& c) {
         PRB_CUDA(cudaMemcpyAsync(c.subdivide.data(), subIds.p, sizeof(int) * (size_t)nSub, cudaMemcpyDeviceToHost, st));
         PRB_CUDA(cudaStreamSynchronize(st));
     }
+    mark(c, "extract:subdivide_list");
     flag.release(); excl.release();
     // ---- refinement passes in the reference's order: single roots of depth 1, 2 (main.cu:3887-4202), then one batch per depth
     // (main.cu:4211-4561).  Passes are independent of each other (vertices are shared inside a pass only), so with several GPUs whole
@@ -1847,10 +1877,12 @@ int stage_extract(Context& c) {
             const size_t passesBefore = c.passes.size();
             PRB_TRY(refine_pass(c, subIds.p + pp.first, pp.count, pp.depth, pp.kind == 1, rootMap, outs));
             c.passes.resize(passesBefore);              // (the global list is rebuilt below)
+            if (c.detail) { static const char* nm[13] = {"pass:d0", "pass:d1", "pass:d2", "pass:d3", "pass:d4", "pass:d5", "pass:d6", "pass:d7", "pass:d8", "pass:d9", "pass:d10", "pass:d11", "pass:d12"}; mark(c, nm[pp.depth]); }
             pp.out = outs.size() > before ? (int)outs.size() - 1 : -1;
         }
         rootMap.release();
     }
+    mark(c, "extract:passes");
     subIds.release();
     // ---- counts of every pass on every rank -> global pass list, vertex / triangle bases of the local pieces
     const int nPlan = (int)plan.size();
@@ -1867,6 +1899,7 @@ int stage_extract(Context& c) {
         }
         if (nPlan == 0) PRB_TRY(mg_barrier(c));      // nobody leaves while a peer may still read this rank's arena
     }
+    mark(c, "extract:counts_exchanged");
     i64 gv = 0, gt = 0;
     struct Piece { int out; i64 vBase, tBase; int nv, nt, pass; };
     std::vector<Piece> mine;
@@ -1903,6 +1936,7 @@ int stage_extract(Context& c) {
         c.layout.push_back({(i64)pc.pass, pc.vBase, (i64)pc.nv, pc.tBase, (i64)pc.nt});
         av += pc.nv; at += pc.nt;
     }
+    mark(c, "extract:assembled");
     for (auto& o : outs) { o.v.release(); o.t.release(); }
     c.nMeshV = tv;
     c.nMeshT = tt;

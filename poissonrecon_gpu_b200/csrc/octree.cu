@@ -339,16 +339,28 @@ __global__ void __launch_bounds__(256) k_sg_table(const int* __restrict__ parent
         sgTab[t] = out;
     }
 }
-// first node of every rank's share at the sharded depths: the first existing sibling group at or
-// after the rank's first super-group (interior table entries in child order)
-__global__ void k_shard_rows(const int* __restrict__ sgTab, const int* __restrict__ sgLo /* [(D+2)][kMaxRanks+1] */, const int* __restrict__ sgEnd,
-                             const int* __restrict__ baseNext, int D, int world, int* __restrict__ rowLo) {
+// Multi-GPU shard plan of the sharded depths.  Rank r's share of depth d starts at the super-group that holds the row at fraction
+// r / world of the depth (so every rank gets about the same number of ROWS -- the cost of all phases follows the rows, while
+// super-groups hold anything from 8 to 64 of them) and its first node is the first existing sibling group at or after that
+// super-group (interior table entries in child order).
+__global__ void k_shard_plan(const int* __restrict__ sgTab, const int* __restrict__ parent, const int* __restrict__ sgStart /* [D+2] */, const int* __restrict__ base /* [D+2] */,
+                             int D, int world, int shardFrom, int* __restrict__ sgLo /* [(D+2)][kMaxRanks+1] */, int* __restrict__ rowLo) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (D + 2) * (kMaxRanks + 1)) return;
     int d = t / (kMaxRanks + 1), r = t % (kMaxRanks + 1);
-    if (d < 1 || d > D || r > world) { rowLo[t] = 0; return; }
-    int sg = sgLo[t], out = baseNext[d];
-    if (sg < sgEnd[d]) {
+    if (d < shardFrom || d > D || r > world) return;          // (the host keeps its own values for the replicated depths)
+    const int cntD = base[d + 1] - base[d];
+    int sg;
+    if (r == 0) sg = sgStart[d];
+    else if (r == world) sg = sgStart[d + 1];
+    else {
+        const int g = (int)(((long long)(cntD >> 3) * r) / world);         // sibling group (of this depth) at the target fraction
+        const int P = parent[base[d] + 8 * g];
+        sg = 1 + (P - 1) / 8;
+    }
+    sgLo[t] = sg;
+    int out = base[d + 1];
+    if (sg < sgStart[d + 1]) {
         const int idx[8] = {21, 22, 25, 26, 37, 38, 41, 42};
         for (int k = 0; k < 8; k++) {
             int v = sgTab[64 * (i64)sg + idx[k]];
@@ -385,6 +397,7 @@ int stage_octree(Context& c) {
         PRB_TRY(mg_barrier(c));
         c.rawSharded = false;
     }
+    mark(c, "octree:gathered");
     // ---- A0 bounding box -> scale / centre (host float arithmetic of main.cu:539-545)
     {
         int nb = grid_for(c, N, 256, 4);
@@ -409,6 +422,7 @@ int stage_octree(Context& c) {
     }
     // ---- A1/A2 keys + sort (thrust::sort_by_key x2 on 64-bit codes in the reference, main.cu:598-602;
     //      here one stable LSD sort over the 3D key bits with the sample index as payload)
+    mark(c, "octree:bbox");
     DBuf<float> P0, N0;
     DBuf<u64> keys0;
     DBuf<int> idx0;
@@ -435,6 +449,7 @@ int stage_octree(Context& c) {
         PRB_TRY(radix_sort_gather(c, keys0.p, idx0.p, keysTmp.p, idxTmp.p, counts.p, N, 3 * D, P0.p, N0.p, c.sortedKey.p, c.sortedIdx.p, c.P.p, c.Nr.p));
     }
     P0.release(); N0.release(); keys0.release(); idx0.release();
+    mark(c, "octree:sorted");
     // ---- A3 unique leaves
     DBuf<int> flagN, exclN;
     PRB_TRY(flagN.alloc((size_t)N, st));
@@ -483,6 +498,7 @@ int stage_octree(Context& c) {
     }
     PRB_TRY(slot[0].alloc(1, st));
     PRB_CUDA(cudaMemsetAsync(slot[0].p, 0, sizeof(int), st));
+    mark(c, "octree:levels");
     // ---- node slabs
     c.cnt[0] = 1;
     for (int d = 1; d <= D; d++) c.cnt[d] = 8 * U[d - 1];
@@ -511,15 +527,18 @@ int stage_octree(Context& c) {
     PRB_TRY(c.p2n.alloc((size_t)N, st));
     PRB_LAUNCH(c, k_point_to_leaf, grid_for(c, N, 256), 256, 0, flagN.p, exclN.p, slot[D].p, N, c.p2n.p);
     for (int d = 0; d <= D; d++) PRB_LAUNCH(c, k_node_offsets, grid_for(c, c.cnt[d], 256), 256, 0, c.key.p, c.base[d], c.cnt[d], d, D, c.offs.p);
+    mark(c, "octree:nodes");
     // ---- A6 neighbours, level by level
     PRB_LAUNCH(c, k_root_neighbours, 1, 32, 0, c.neighs.p);
     for (int d = 1; d <= D; d++)
         PRB_LAUNCH(c, k_neighbours, grid_for(c, (i64)c.cnt[d] * 4, 256), 256, 0, c.parent.p, c.child0.p, c.neighs.p, c.base[d], c.cnt[d]);
+    mark(c, "octree:neighbours");
     // super-groups: depth 1, then one per sibling group of depths 1..D-1
     c.nSg = 1 + (c.base[D] - 1) / 8;
     PRB_TRY(c.sgTab.alloc(64 * (size_t)c.nSg, st));
     PRB_LAUNCH(c, k_sg_table, grid_for(c, (i64)c.nSg * 64, 256), 256, 0, c.parent.p, c.child0.p, c.neighs.p, c.nSg, c.sgTab.p);
     PRB_TRY(build_cg_table(c));
+    mark(c, "octree:sgtable");
     // ---- multi-GPU shard plan: depths with at least minShardRows nodes (and every deeper one) are
     // split into contiguous super-group ranges, the shallower ones are replicated on every rank
     {
@@ -540,21 +559,19 @@ int stage_octree(Context& c) {
             }
         }
         if (c.shardFrom <= D) {
-            DBuf<int> dSgLo, dSgEnd, dBaseNext, dRowLo;
+            DBuf<int> dSgLo, dRowLo, dSgStart;
             const int nt = (D + 2) * (kMaxRanks + 1);
-            PRB_TRY(dSgLo.alloc(nt, st)); PRB_TRY(dRowLo.alloc(nt, st)); PRB_TRY(dSgEnd.alloc(kMaxDepth + 2, st)); PRB_TRY(dBaseNext.alloc(kMaxDepth + 2, st));
-            int hEnd[kMaxDepth + 2] = {0}, hNext[kMaxDepth + 2] = {0};
-            for (int d = 1; d <= D; d++) { hEnd[d] = sgStart[d + 1]; hNext[d] = c.base[d + 1]; }
-            PRB_CUDA(cudaMemcpyAsync(dSgLo.p, &c.sgLo[0][0], sizeof(int) * nt, cudaMemcpyHostToDevice, st));
-            PRB_CUDA(cudaMemcpyAsync(dSgEnd.p, hEnd, sizeof(hEnd), cudaMemcpyHostToDevice, st));
-            PRB_CUDA(cudaMemcpyAsync(dBaseNext.p, hNext, sizeof(hNext), cudaMemcpyHostToDevice, st));
-            PRB_LAUNCH(c, k_shard_rows, 1, 256, 0, c.sgTab.p, dSgLo.p, dSgEnd.p, dBaseNext.p, D, W, dRowLo.p);
-            int hRow[kMaxDepth + 2][kMaxRanks + 1];
+            PRB_TRY(dSgLo.alloc(nt, st)); PRB_TRY(dRowLo.alloc(nt, st)); PRB_TRY(dSgStart.alloc(kMaxDepth + 2, st));
+            int hStart[kMaxDepth + 2] = {0};
+            for (int d = 0; d <= D + 1; d++) hStart[d] = sgStart[d];
+            PRB_CUDA(cudaMemcpyAsync(dSgStart.p, hStart, sizeof(hStart), cudaMemcpyHostToDevice, st));
+            PRB_LAUNCH(c, k_shard_plan, 1, 256, 0, c.sgTab.p, c.parent.p, dSgStart.p, c.dBase.p, D, W, c.shardFrom, dSgLo.p, dRowLo.p);
+            int hRow[kMaxDepth + 2][kMaxRanks + 1], hSg[kMaxDepth + 2][kMaxRanks + 1];
             PRB_CUDA(cudaMemcpyAsync(&hRow[0][0], dRowLo.p, sizeof(int) * nt, cudaMemcpyDeviceToHost, st));
+            PRB_CUDA(cudaMemcpyAsync(&hSg[0][0], dSgLo.p, sizeof(int) * nt, cudaMemcpyDeviceToHost, st));
             PRB_CUDA(cudaStreamSynchronize(st));
             for (int d = c.shardFrom; d <= D; d++)
-                for (int r = 0; r <= W; r++) c.rowLo[d][r] = hRow[d][r];
-            dSgLo.release(); dSgEnd.release(); dBaseNext.release(); dRowLo.release();
+                for (int r = 0; r <= W; r++) { c.rowLo[d][r] = hRow[d][r]; c.sgLo[d][r] = hSg[d][r]; }
         }
     }
     flagN.release(); exclN.release();

@@ -110,6 +110,7 @@ void prb_destroy(prb_context* h) {
     if (c.mg.arena) cudaFree(c.mg.arena);
     c.hMeshV.release(); c.hMeshT.release();
     for (auto& e : c.ev) cudaEventDestroy(e);
+    for (auto& e : c.detailEv) cudaEventDestroy(e);
     cudaStreamDestroy(c.stream);
     delete h;
 }
@@ -121,6 +122,8 @@ int prb_set_option(prb_context* h, const char* key, double value) {
     else if (k == "cg_max_iter") h->c.cgMaxIter = (int)value;
     else if (k == "cg_zigzag") h->c.cgZigzag = (int)value;
     else if (k == "cg_bulk") h->c.cgBulk = (int)value;
+    else if (k == "cg_timing") h->c.cgTiming = (int)value;
+    else if (k == "detail") h->c.detail = (int)value;
     else if (k == "refine_bound_check") h->c.refineBoundCheck = (int)value;
     else if (k == "div_mode") h->c.divMode = (int)value;
     else if (k == "refine") h->c.doRefine = (int)value;
@@ -138,6 +141,8 @@ static int begin_run(Context& c, int64_t n) {
     c.rawSharded = false;
     c.N = n;
     c.launches = 0;
+    c.detailUsed = 0;
+    mark(c, "set_points");
     return PRB_OK;
 }
 
@@ -355,6 +360,16 @@ int64_t prb_get_array(prb_context* h, const char* name, void* dst, int64_t cap) 
     else if (s == "iso") H_(&c.iso, 4);
     else if (s == "center_scale") { float v[4] = {c.center[0], c.center[1], c.center[2], c.scale}; H_(v, 16); }
     else if (s == "cg_iters") H_(c.cgIters, sizeof(int) * (D + 1));
+    else if (s == "cg_phase_ns") H_(c.cgPhaseNs, sizeof(c.cgPhaseNs));
+    else if (s == "detail_ms") {
+        std::vector<float> ms;
+        for (size_t k = 0; k + 1 < c.detailUsed; k++) { float v = 0; if (cudaEventElapsedTime(&v, c.detailEv[k], c.detailEv[k + 1]) != cudaSuccess) { cudaGetLastError(); v = -1; } ms.push_back(v); }
+        H_(ms.data(), ms.size() * 4);
+    } else if (s == "detail_names") {
+        std::string all;
+        for (size_t k = 0; k + 1 < c.detailUsed; k++) { all += c.detailName[k] + " -> " + c.detailName[k + 1]; all.push_back('\0'); }
+        H_(all.data(), all.size());
+    }
     else if (s == "lap_stencil") H_(c.tab.stencil.data(), c.tab.stencil.size() * 4);
     else if (s == "df_table") H_(c.tab.dfT.data(), c.tab.dfT.size() * 4);
     else if (s == "passes") { std::vector<int> v; for (auto& p : c.passes) { v.push_back(p.kind); v.push_back(p.nv); v.push_back(p.nt); } H_(v.data(), v.size() * 4); }

@@ -141,6 +141,7 @@ struct CgParams {
     unsigned epoch0;
     unsigned* barCount;            // arrival counter / release flag of cg_sync (zeroed before the launch)
     unsigned* barRelease;
+    long long* phaseNs;            // optional [8]: time CTA 0 spent in phase C / its barrier / SpMV / barrier / phase B / barrier (ns, %globaltimer)
 };
 
 // Grid-wide (world == 1) or box-wide barrier between the phases of an iteration.  Every CTA arrives on a counter; the LAST one
@@ -170,12 +171,15 @@ __device__ __forceinline__ void cg_sync(const CgParams& P, unsigned& epoch, unsi
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {
             if (MG) {
-                __threadfence();
+                // lane 0 observed every CTA's arrival (each one fenced its writes first); the shuffle above orders that before the
+                // other lanes' stores, and release / acquire are cumulative: the epoch store below publishes this rank's whole
+                // phase to the peer, and the release of the local CTAs after the polls publishes the peers' phases to them
                 if (lane < P.world && !P.mg.hdr->error) {
                     MgCgLine* out = &P.mg.peerHdr[lane]->cg[epoch & 1u][P.rank];
-                    if (kind >= 0)
-                        for (int d = 1; d <= P.D; d++) out->v[d] = __ldcg(local + d);
-                    __threadfence_system();
+                    if (kind >= 0) {
+                        double2* o2 = reinterpret_cast<double2*>(out->v);              // v[0] is unused: pairs (0,1), (2,3), ...
+                        for (int d = 0; d <= P.D; d += 2) o2[d >> 1] = make_double2(__ldcg(local + d), __ldcg(local + d + 1));
+                    }
                     mg_store_release_sys(&out->epoch, epoch);
                     const unsigned* in = &P.mg.hdr->cg[epoch & 1u][lane].epoch;
                     const long long t0 = clock64();
@@ -183,7 +187,6 @@ __device__ __forceinline__ void cg_sync(const CgParams& P, unsigned& epoch, unsi
                         if (clock64() - t0 > kMgSpinCycles) { P.mg.hdr->error = 1; break; }
                 }
                 __syncwarp();
-                __threadfence_system();
             }
             if (lane == 0) st_release_gpu(P.barRelease, gen);
         } else if (lane == 0) {
@@ -451,6 +454,16 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
     }
     const int outOff = 2 * Ylo;          // the lane's rows (y = Y & 1) start 2 (Y & 1) floats after the block base
 
+    long long tPrev = 0;
+    const bool timing = P.phaseNs != nullptr && blockIdx.x == 0 && tid == 0;
+    auto tick = [&](int slot) {
+        if (!timing) return;
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+        if (slot >= 0) P.phaseNs[slot] += t - tPrev;
+        tPrev = t;
+    };
+    tick(-1);
     int phase = 0;
     int it = 1;
     for (;; it++) {
@@ -501,7 +514,9 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
             if (P.bulk) stream_pairs_bulk(sAct4, sAct4[D + 1], P.row0, P.row1, P.r, pOld, revC, wbuf, barS, phaseBits, gwarp, nwarps, lane, stepC);
             else stream_pairs(sAct4, sAct4[D + 1], P.row0, P.row1, P.r, pOld, revC, wbuf, gwarp, nwarps, lane, stepC);
         }
+        tick(0);
         cg_sync<MG>(P, epoch, gen, -1, nullptr);
+        tick(1);
         // ---------------- phase A: Ap = A p ; p.Ap over the flat step list of all active depths
         {
             const int total = sStep[D + 1];
@@ -691,7 +706,9 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
         }
         __syncthreads();
         if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&dPAp[tid], sAcc[tid]);
+        tick(2);
         cg_sync<MG>(P, epoch, gen, 0, dPAp);
+        tick(3);
         // both accumulators of the NEXT iteration are zeroed here: every block has passed this
         // iteration's syncs, hence finished reading them after the previous iteration's syncs
         if (blockIdx.x == 0 && tid < 32) P.dots[nxt * 32 + tid] = 0.0;
@@ -725,7 +742,9 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
         }
         __syncthreads();
         if (tid >= 1 && tid <= D && sAcc[tid] != 0.0) atomicAdd(&dRRn[tid], sAcc[tid]);
+        tick(4);
         cg_sync<MG>(P, epoch, gen, 1, dRRn);
+        tick(5);
         if (tid >= 1 && tid <= D && sActive[tid]) {
             float r0 = sR1[tid], r1 = (float)cg_total<MG>(P, epoch, tid, dRRn);
             sR1[tid] = r1;
@@ -825,6 +844,13 @@ int stage_solve(Context& c) {
     P.barCount = reinterpret_cast<unsigned*>(dots.p + 96);
     P.barRelease = P.barCount + 32;       // (its own 128-byte line)
     P.dots = dots.p; P.itersOut = itersOut.p; P.resOut = resOut.p;
+    DBuf<long long> phaseNs;
+    P.phaseNs = nullptr;
+    if (c.cgTiming) {
+        PRB_TRY(phaseNs.alloc(8, st));
+        PRB_CUDA(cudaMemsetAsync(phaseNs.p, 0, 8 * sizeof(long long), st));
+        P.phaseNs = phaseNs.p;
+    }
     float tol = (float)c.cgTol;
     P.tol2 = tol * tol;
     P.maxIter = c.cgMaxIter;
@@ -841,10 +867,13 @@ int stage_solve(Context& c) {
     if (gridSize > needBlocks) gridSize = (int)(((needBlocks + c.smCount - 1) / c.smCount) * c.smCount);   // small problems: fewer CTAs, cheaper grid syncs
     if (gridSize > c.smCount * perSM) gridSize = c.smCount * perSM;
     if (gridSize < 1) gridSize = 1;
+    mark(c, "solve:setup");
     void* args[] = {(void*)&P};
     PRB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(gridSize), dim3(kCgBlock), args, dynSmem, st));
     c.launches++;
+    mark(c, "solve:kernel");
     int hIters[16];
+    if (c.cgTiming) PRB_CUDA(cudaMemcpyAsync(c.cgPhaseNs, phaseNs.p, 8 * sizeof(long long), cudaMemcpyDeviceToHost, st));
     PRB_CUDA(cudaMemcpyAsync(hIters, itersOut.p, sizeof(hIters), cudaMemcpyDeviceToHost, st));
     PRB_CUDA(cudaStreamSynchronize(st));
     c.cgRowIters = 0;
@@ -867,6 +896,7 @@ int stage_solve(Context& c) {
         PRB_CUDA(cudaStreamSynchronize(st));
         if (err) { set_error("multi-GPU solve: timed out waiting for a peer"); return PRB_ERR_CUDA; }
     }
+    mark(c, "solve:gathered");
     r.release(); p.release(); Ap.release(); dots.release(); itersOut.release(); resOut.release();
     return PRB_OK;
 }
