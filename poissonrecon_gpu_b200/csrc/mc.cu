@@ -387,6 +387,7 @@ __global__ void __launch_bounds__(kVsWarps * 32) k_vertex_values_stream(Topo T, 
     __shared__ float sXc[kVsWarps][kVsSlots][64];                             // solution on the 4x4x4 node cube around each group (own level)
     __shared__ unsigned short sPt[kVsWarps][kVsSlots * 27];                  // owned points: slot | point << 2 | (owner - gb) << 7 | jo << 10
     __shared__ ushort4 sO0[kVsWarps][kVsSlots];
+    __shared__ unsigned char sPair[kVsWarps][kVsSlots * kMaxDepth];              // ancestors to refresh this step: slot << 4 | level
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const int px = lane / 9, py = (lane / 3) % 3, pz = lane % 3;      // lane -> point of a group's 3x3x3 corner grid (staging)
     const int nChunks = RG.chunk0[RG.n];
@@ -397,7 +398,10 @@ __global__ void __launch_bounds__(kVsWarps * 32) k_vertex_values_stream(Topo T, 
         const int gEnd = min(RG.first[rg] + RG.count[rg], gFirst + RG.chunk);
         int curDepth = -1;
         for (int g0 = gFirst; g0 < gEnd;) {
-            const int d0 = offs[1 + 8 * g0].w;
+            // ---- (1) headers of up to four groups: lane q < 4 looks at group g0 + q; the step takes the leading groups of one depth
+            ushort4 oq = make_ushort4(0, 0, 0, 0xffff);
+            if (lane < kVsSlots && g0 + lane < gEnd) oq = offs[1 + 8 * (g0 + lane)];      // first sibling (root vertices are dropped, main.cu:1634-1638)
+            const int d0 = __shfl_sync(0xffffffffu, (int)oq.w, 0);
             const float w = 1.0f / (float)(1 << d0);
             __syncwarp();
             if (d0 != curDepth) {
@@ -405,47 +409,86 @@ __global__ void __launch_bounds__(kVsWarps * 32) k_vertex_values_stream(Topo T, 
                 curDepth = d0;
                 __syncwarp();
             }
-            // ---- stage up to four groups of this depth
-            int nq = 0, np = 0;
-            for (; nq < kVsSlots && g0 + nq < gEnd; nq++) {
-                const int gb = 1 + 8 * (g0 + nq);            // first sibling (root vertices are dropped, main.cu:1634-1638)
-                const ushort4 o0 = offs[gb];
-                if (o0.w != d0) break;                        // the next depth starts here: it gets its own step
-                bool mine = false;
-                int owner = -1, jo = 0;
-                if (lane < 27) {
-                    const int sx = (px + 1) >> 1, sy = (py + 1) >> 1, sz = (pz + 1) >> 1;
-                    const int id = gb + ((sx << 2) | (sy << 1) | sz);
-                    const int j = (px - sx) | ((py - sy) << 1) | ((pz - sz) << 2);
-                    int m;
-                    owner = corner_owner(T, id, j, m);
-                    mine = owner >= gb && owner < gb + 8;
-                    jo = j ^ m;
-                }
-                const unsigned mm = __ballot_sync(0xffffffffu, mine);
-                if (mine) sPt[wp][np + __popc(mm & ((1u << lane) - 1u))] = (unsigned short)(nq | (lane << 2) | ((owner - gb) << 7) | (jo << 10));
-                np += __popc(mm);
-                if (lane == 0) sO0[wp][nq] = o0;
-                // own level: every neighbour of every sibling lies in the 4x4x4 cube around the group
+            const unsigned same = __ballot_sync(0xffffffffu, lane < kVsSlots && (int)oq.w == d0);
+            const int nq = __ffs(~same) - 1;                  // 1..4: the next depth, if it starts inside, gets its own step
+            if (lane < nq) sO0[wp][lane] = oq;
+            // ---- (2) ancestors whose node changed since the slot's previous group: the four parent chains are walked in parallel
+            // (lane q), every (slot, level) to refresh goes on a list ...
+            int nref = 0;
+            if (lane < nq) {
+                int a = parent[1 + 8 * (g0 + lane)];
+                for (int l = d0 - 1; l >= 0 && sAnc[wp][lane][l] != a; --l) { sAnc[wp][lane][l] = a; a = parent[a]; nref++; }
+            }
+            int pre = nref;
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int e = lane + 32 * h, ux = e >> 4, uy = (e >> 2) & 3, uz = e & 3;
-                    const int sx = ux >> 1, sy = uy >> 1, sz = uz >> 1;
-                    const int j = 9 * (ux - sx) + 3 * (uy - sy) + (uz - sz);          // 9(dx+1)+3(dy+1)+(dz+1) with d = u - 1 - s
-                    const int q = T.nbr[27 * (i64)(gb + ((sx << 2) | (sy << 1) | sz)) + j];
-                    sXc[wp][nq][e] = q >= 0 ? x[q] : 0.f;
-                }
-                // ancestors: re-gather the levels whose node changed since this slot's previous group (warp-uniform walk)
-                int a = parent[gb];
-                float* sx_ = &sX[wp][nq * kVsSlotStride];
-                for (int l = d0 - 1; l >= 0 && sAnc[wp][nq][l] != a; --l) {
-                    if (lane < 27) {
-                        const int q = T.nbr[27 * (i64)a + lane];
-                        sx_[l * 28 + lane] = q >= 0 ? x[q] : 0.f;
+            for (int o = 1; o < kVsSlots; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
+            const int nPairs = __shfl_sync(0xffffffffu, pre, kVsSlots - 1);
+            for (int k = 0; k < nref; k++) sPair[wp][pre - nref + k] = (unsigned char)((lane << 4) | (d0 - 1 - k));
+            __syncwarp();
+            // ---- (3) ... and the 27 neighbour values of all listed ancestors are gathered in one flat, four-deep batched loop: the
+            // latency of the (table -> value) pairs overlaps instead of adding up group after group, level after level
+            {
+                const int total = nPairs * 27;
+                for (int e0 = lane; e0 < total; e0 += 128) {
+                    int nb[4], dst[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int e = e0 + 32 * u;
+                        nb[u] = -2;
+                        if (e < total) {
+                            const int pr = sPair[wp][e / 27], j = e % 27, q = pr >> 4, l = pr & 15;
+                            dst[u] = q * kVsSlotStride + l * 28 + j;
+                            nb[u] = T.nbr[27 * (i64)sAnc[wp][q][l] + j];
+                        }
                     }
-                    __syncwarp();
-                    if (lane == 0) sAnc[wp][nq][l] = a;
-                    a = parent[a];
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (nb[u] != -2) sX[wp][dst[u]] = nb[u] >= 0 ? x[nb[u]] : 0.f;
+                }
+            }
+            // ---- (4) owners of the 27 corner-grid points and the own-level 4x4x4 cube of every group, loads of all groups in flight together
+            int np = 0;
+            {
+                int ownerQ[kVsSlots], joQ[kVsSlots], cubeQ[kVsSlots][2];
+#pragma unroll
+                for (int q = 0; q < kVsSlots; q++) {
+                    ownerQ[q] = -1; joQ[q] = 0; cubeQ[q][0] = cubeQ[q][1] = -1;
+                    if (q < nq) {
+                        const int gb = 1 + 8 * (g0 + q);
+                        if (lane < 27) {
+                            const int sx = (px + 1) >> 1, sy = (py + 1) >> 1, sz = (pz + 1) >> 1;
+                            const int id = gb + ((sx << 2) | (sy << 1) | sz);
+                            const int j = (px - sx) | ((py - sy) << 1) | ((pz - sz) << 2);
+                            int m;
+                            ownerQ[q] = corner_owner(T, id, j, m);
+                            joQ[q] = j ^ m;
+                        }
+                        // own level: every neighbour of every sibling lies in the 4x4x4 cube around the group
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int e = lane + 32 * h, ux = e >> 4, uy = (e >> 2) & 3, uz = e & 3;
+                            const int sx = ux >> 1, sy = uy >> 1, sz = uz >> 1;
+                            const int j = 9 * (ux - sx) + 3 * (uy - sy) + (uz - sz);          // 9(dx+1)+3(dy+1)+(dz+1) with d = u - 1 - s
+                            cubeQ[q][h] = T.nbr[27 * (i64)(gb + ((sx << 2) | (sy << 1) | sz)) + j];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < kVsSlots; q++) {
+                    if (q < nq) {
+                        sXc[wp][q][lane] = cubeQ[q][0] >= 0 ? x[cubeQ[q][0]] : 0.f;
+                        sXc[wp][q][lane + 32] = cubeQ[q][1] >= 0 ? x[cubeQ[q][1]] : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < kVsSlots; q++) {
+                    if (q < nq) {                                          // (warp-uniform)
+                        const int gb = 1 + 8 * (g0 + q);
+                        const bool mine = lane < 27 && ownerQ[q] >= gb && ownerQ[q] < gb + 8;
+                        const unsigned mm = __ballot_sync(0xffffffffu, mine);
+                        if (mine) sPt[wp][np + __popc(mm & ((1u << lane) - 1u))] = (unsigned short)(q | (lane << 2) | ((ownerQ[q] - gb) << 7) | (joQ[q] << 10));
+                        np += __popc(mm);
+                    }
                 }
             }
             __syncwarp();
@@ -473,11 +516,15 @@ __global__ void __launch_bounds__(kVsWarps * 32) k_vertex_values_stream(Topo T, 
                             val = __fmaf_rn(__fmul_rn(__fmul_rn(xc[(j / 9) * 16 + ((j / 3) % 3) * 4 + (j % 3)], vx[j / 9]), vy[(j / 3) % 3]), vz[j % 3], val);
                     }
                     // shared ancestor levels d0-1 .. 0
-                    const float* sx_ = &sX[wp][q * kVsSlotStride];
-                    for (int l = d0 - 1; l >= 0; --l) {
-                        const float4 bx = ba[(l * ng + gx) * 3 + qx], by = ba[(l * ng + gy) * 3 + qy], bz = ba[(l * ng + gz) * 3 + qz];
+                    const float4* sx4 = reinterpret_cast<const float4*>(&sX[wp][q * kVsSlotStride]) + 7 * (d0 - 1);      // 28 floats per level
+                    const float4 *pbx = ba + ((d0 - 1) * ng + gx) * 3 + qx, *pby = ba + ((d0 - 1) * ng + gy) * 3 + qy, *pbz = ba + ((d0 - 1) * ng + gz) * 3 + qz;
+                    for (int l = d0 - 1; l >= 0; --l, sx4 -= 7, pbx -= 3 * ng, pby -= 3 * ng, pbz -= 3 * ng) {
+                        const float4 bx = *pbx, by = *pby, bz = *pbz;
                         const float vx[3] = {bx.x, bx.y, bx.z}, vy[3] = {by.x, by.y, by.z}, vz[3] = {bz.x, bz.y, bz.z};
-                        RV_ACC27(val, sx_ + l * 28, vx, vy, vz);
+                        float X[28];
+#pragma unroll
+                        for (int t = 0; t < 7; t++) { const float4 v4 = sx4[t]; X[4 * t] = v4.x; X[4 * t + 1] = v4.y; X[4 * t + 2] = v4.z; X[4 * t + 3] = v4.w; }
+                        RV_ACC27(val, X, vx, vy, vz);
                     }
                     // finer nodes at this corner (vertices owned above depth D)
                     const int owner = gb + k;
@@ -615,13 +662,27 @@ __global__ void __launch_bounds__(128) k_emit_triangles(Topo T, const unsigned c
 }
 // empty leaves below depth D that must be refined (main.cu:2957-2992)
 struct MarkView { const unsigned* p[kMaxRanks]; int world; };      // face marks of every rank's own cells (multi-GPU: OR of the peers' arrays)
-__global__ void __launch_bounds__(128) k_find_subdivide(Topo T, int nNodes, const int* __restrict__ child0, const __grid_constant__ ValView W,
+// corner values of ALL depths above D: multi-GPU, the node ranges rowLo[d][.] of the sharded depths live on their ranks (read in place)
+struct UpperView {
+    const float* p[kMaxRanks];
+    int world, shardFrom;
+    int rowLo[kMaxDepth + 1][kMaxRanks + 1];
+};
+__global__ void __launch_bounds__(128) k_find_subdivide(Topo T, int nNodes, const int* __restrict__ child0, const ushort4* __restrict__ offs, const __grid_constant__ UpperView U,
                                                         const __grid_constant__ MarkView F, int* __restrict__ flag) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nNodes; i += gridDim.x * blockDim.x) {
         int f = 0;
         if (i > 0 && child0[i] < 0) {
             float v[8];
-            cell_corner_values(T, i, W, v);
+            const int d = offs[i].w;
+            const bool remote = U.world > 1 && d >= U.shardFrom;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                int j = ring_to_bits(r), m;
+                const int ow = corner_owner(T, i, j, m);              // (same depth as i)
+                const int rk = remote ? view_rank(U.rowLo[d], U.world, ow) : 0;
+                v[r] = U.p[rk][8 * (i64)ow + (j ^ m)];
+            }
             int sign = (v[0] < 0.f) ? -1 : 1;
             int ht = 0;
 #pragma unroll
@@ -1744,8 +1805,8 @@ int stage_extract(Context& c) {
         c.vvalPtr = c.vval.p;
     }
     // ---- corner values.  Multi-GPU: a rank evaluates its node range of every sharded depth (and all of the small replicated
-    // depths); the values of the depths above D are then gathered (they feed k_find_subdivide on every rank), those of depth D stay
-    // where they are: only cells on a shard boundary read a neighbour rank's values, in place over NVLink
+    // depths) and the values stay where they are: the marching cubes of a rank's own cells only reads a neighbour rank's values on
+    // a shard boundary, and k_find_subdivide (every rank, the leaves above depth D) reads them in place over NVLink
     {
         PRB_TRY(ensure_bv_tables(c));
         BvTables B;
@@ -1778,16 +1839,7 @@ int stage_extract(Context& c) {
             add(0, (c.base[c.shardFrom] - 1) / 8);
             for (int d = c.shardFrom; d <= D; d++) add((c.rowLo[d][me] - 1) / 8, (c.rowLo[d][me + 1] - 1) / 8);
             launch();
-            PRB_TRY(mg_barrier(c));
-            for (int qi = 1; qi < W; qi++) {          // start with the next rank: the peers are not all pulled from in the same order
-                const int q = (me + qi) % W;
-                const float* src = (const float*)(c.mg.peer[q] + c.mgVvalOff);
-                for (int d = c.shardFrom; d < D; d++) {
-                    const size_t a = (size_t)c.rowLo[d][q], b = (size_t)c.rowLo[d][q + 1];
-                    if (b > a) PRB_CUDA(cudaMemcpyAsync(c.vvalPtr + 8 * a, src + 8 * a, 32 * (b - a), cudaMemcpyDeviceToDevice, st));
-                }
-            }
-            PRB_TRY(mg_barrier(c));
+            PRB_TRY(mg_barrier(c));               // every rank's values are complete before anyone reads a neighbour rank's
         }
     }
     mark(c, "extract:corner_values");
@@ -1832,7 +1884,12 @@ int stage_extract(Context& c) {
         MarkView F;
         F.world = shard ? W : 1;
         for (int r = 0; r < kMaxRanks; r++) F.p[r] = (shard && r < W) ? (const unsigned*)(c.mg.peer[r] + fmarkOff) : fmark;
-        PRB_LAUNCH(c, k_find_subdivide, grid_for(c, nUpper, 128, 16), 128, 0, R, nUpper, c.child0.p, local_view(c.vvalPtr, 0), F, flag.p);
+        UpperView U;
+        U.world = shard ? W : 1; U.shardFrom = c.shardFrom;
+        for (int r = 0; r < kMaxRanks; r++) U.p[r] = (shard && r < W) ? (const float*)(c.mg.peer[r] + c.mgVvalOff) : c.vvalPtr;
+        for (int d = 0; d <= kMaxDepth; d++)
+            for (int r = 0; r <= kMaxRanks; r++) U.rowLo[d][r] = (d <= D && r <= W) ? c.rowLo[d][r] : 0;
+        PRB_LAUNCH(c, k_find_subdivide, grid_for(c, nUpper, 128, 16), 128, 0, R, nUpper, c.child0.p, c.offs.p, U, F, flag.p);
     }
     i64 nSub = 0;
     PRB_TRY(exclusive_scan(c, flag.p, excl.p, nUpper, &nSub));

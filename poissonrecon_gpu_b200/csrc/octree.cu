@@ -340,8 +340,7 @@ __global__ void __launch_bounds__(256) k_sg_table(const int* __restrict__ parent
     }
 }
 // Multi-GPU shard plan of the sharded depths.  Rank r's share of depth d starts at the super-group that holds the row at fraction
-// r / world of the depth (so every rank gets about the same number of ROWS -- the cost of all phases follows the rows, while
-// super-groups hold anything from 8 to 64 of them) and its first node is the first existing sibling group at or after that
+// r / world of the depth's COST (rows plus a fixed part per super-group, see below: super-groups hold anything from 8 to 64 rows) and its first node is the first existing sibling group at or after that
 // super-group (interior table entries in child order).
 __global__ void k_shard_plan(const int* __restrict__ sgTab, const int* __restrict__ parent, const int* __restrict__ sgStart /* [D+2] */, const int* __restrict__ base /* [D+2] */,
                              int D, int world, int shardFrom, int* __restrict__ sgLo /* [(D+2)][kMaxRanks+1] */, int* __restrict__ rowLo) {
@@ -354,9 +353,21 @@ __global__ void k_shard_plan(const int* __restrict__ sgTab, const int* __restric
     if (r == 0) sg = sgStart[d];
     else if (r == world) sg = sgStart[d + 1];
     else {
-        const int g = (int)(((long long)(cntD >> 3) * r) / world);         // sibling group (of this depth) at the target fraction
-        const int P = parent[base[d] + 8 * g];
-        sg = 1 + (P - 1) / 8;
+        // cost of a share = its rows + 0.3 x (average rows per super-group) x its super-groups: the SpMV pays a fixed part for every
+        // super-group it stages, however few rows it holds (measured on 8 GPUs: equal rows left the SpMV times 1.48 .. 2.20 ms apart).
+        // The cost of the sibling groups before g is monotone in g: binary search for the target fraction
+        const int nG = cntD >> 3, nSg = sgStart[d + 1] - sgStart[d];
+        const double cPerSg = 0.3 * (double)cntD / (double)(nSg > 0 ? nSg : 1);
+        const double target = ((double)cntD + cPerSg * nSg) * (double)r / (double)world;
+        int lo = 0, hi = nG;                                               // smallest g with cost(g) >= target
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const int sgm = 1 + (parent[base[d] + 8 * mid] - 1) / 8;
+            const double cost = 8.0 * mid + cPerSg * (double)(sgm - sgStart[d]);
+            if (cost < target) lo = mid + 1; else hi = mid;
+        }
+        const int g = lo < nG ? lo : nG - 1;
+        sg = 1 + (parent[base[d] + 8 * g] - 1) / 8;
     }
     sgLo[t] = sg;
     int out = base[d + 1];

@@ -169,7 +169,7 @@ def test_depth10_depth11_free_and_forced(name, oracle_cls):
         assert pr.get("passes", "<i4").tolist() == passes, opt
         assert np.array_equal(t, t2), opt
         if opt == "div_mode":      # the first-version coarse divergence sums in another order: x, hence the positions, move in the last bits
-            assert np.abs(v - v2).max() <= 1e-6
+            assert np.abs(v - v2).max() <= 1e-5
         else:
             assert np.array_equal(v, v2), opt
         pr.set_option(opt, 1 - val)
