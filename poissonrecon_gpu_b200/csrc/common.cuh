@@ -170,6 +170,7 @@ int mg_barrier(struct Context& c);            // device-side flag barrier on the
 // all-gather of up to 64 ints per rank through the arena headers: all[r * stride + k] = value k of rank r (all ranks must call it)
 int mg_exchange_ints(struct Context& c, const int* mine, int n, int* all, int stride = -1);
 void deal_passes(int D, int n, const int* depth, const int* count, int world, int* owner);     // mc.cu
+int mg_pull(struct Context& c, int n, const void* const* src, void* const* dst, const size_t* bytes);     // one-launch pull of segments from peer arenas
 int mg_allgather(struct Context& c, size_t arenaOffset, size_t elemBytes, const long long* lo /* [world + 1] */);
 
 // One pass (the main depth-D pass or a refinement pass) of mesh output.

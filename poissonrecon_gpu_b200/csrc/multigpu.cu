@@ -3,6 +3,7 @@
 // (devID = 0 hard-coded, CG_CUDA.cuh:356); this layer is new.
 #include "common.cuh"
 #include "mg_device.cuh"
+#include <algorithm>
 #include <cstring>
 
 namespace prb {
@@ -41,15 +42,74 @@ int mg_exchange_ints(Context& c, const int* mine, int n, int* all, int stride) {
     return PRB_OK;
 }
 
+// Pull of up to 32 segments from the peers' arenas with the SMs (one launch, all peers' NVLink paths busy at once; a chain of
+// cudaMemcpyAsync calls on one stream moves one peer's share after the other: 0.3 GB/ms measured on 8 GPUs).  16-byte words when
+// source, destination and length allow, 4-byte words otherwise.
+struct PullSegs {
+    int n;
+    const char* src[32];
+    char* dst[32];
+    unsigned long long bytes[32], first[33];      // first[k]: first 256-thread tile of segment k (tiles of 4096 x 16 bytes)
+};
+constexpr unsigned long long kPullTileBytes = 65536;
+__global__ void __launch_bounds__(256) k_mg_pull(const __grid_constant__ PullSegs S) {
+    const unsigned long long nTiles = S.first[S.n];
+    for (unsigned long long t = blockIdx.x; t < nTiles; t += gridDim.x) {
+        int k = 0;
+        while (k + 1 < S.n && t >= S.first[k + 1]) k++;
+        const unsigned long long off = (t - S.first[k]) * kPullTileBytes;
+        const unsigned long long len = S.bytes[k] - off < kPullTileBytes ? S.bytes[k] - off : kPullTileBytes;
+        const char* src = S.src[k] + off;
+        char* dst = S.dst[k] + off;
+        if (((((unsigned long long)src) | ((unsigned long long)dst) | len) & 15ull) == 0) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            const unsigned n4 = (unsigned)(len >> 4);
+#pragma unroll 4
+            for (unsigned i = threadIdx.x; i < n4; i += 256) d4[i] = s4[i];
+        } else {
+            const unsigned* s1 = reinterpret_cast<const unsigned*>(src);
+            unsigned* d1 = reinterpret_cast<unsigned*>(dst);
+            const unsigned n1 = (unsigned)(len >> 2);
+#pragma unroll 4
+            for (unsigned i = threadIdx.x; i < n1; i += 256) d1[i] = s1[i];
+        }
+    }
+}
+int mg_pull(Context& c, int n, const void* const* src, void* const* dst, const size_t* bytes) {
+    PullSegs S;
+    S.n = 0;
+    unsigned long long tiles = 0;
+    for (int k = 0; k < n; k++) {
+        if (!bytes[k]) continue;
+        if (S.n == 32) { set_error("mg_pull: too many segments"); return PRB_ERR_ARG; }
+        if (bytes[k] & 3) { set_error("mg_pull: lengths are multiples of 4 bytes"); return PRB_ERR_ARG; }
+        S.src[S.n] = (const char*)src[k]; S.dst[S.n] = (char*)dst[k]; S.bytes[S.n] = bytes[k]; S.first[S.n] = tiles;
+        tiles += (bytes[k] + kPullTileBytes - 1) / kPullTileBytes;
+        S.n++;
+    }
+    if (!S.n) return PRB_OK;
+    for (int k = S.n; k <= 32; k++) S.first[k] = tiles;
+    for (int k = S.n; k < 32; k++) { S.src[k] = nullptr; S.dst[k] = nullptr; S.bytes[k] = 0; }
+    const unsigned grid = (unsigned)std::min<unsigned long long>(tiles, (unsigned long long)c.smCount * 16);
+    PRB_LAUNCH(c, k_mg_pull, grid, 256, 0, S);
+    return PRB_OK;
+}
+
 int mg_allgather(Context& c, size_t arenaOffset, size_t elemBytes, const long long* lo) {
     if (!c.mg.active()) return PRB_OK;
     const int W = c.mg.world, me = c.mg.rank;
     PRB_TRY(mg_barrier(c));
+    const void* src[kMaxRanks];
+    void* dst[kMaxRanks];
+    size_t bytes[kMaxRanks];
+    int n = 0;
     for (int qi = 1; qi < W; qi++) {
         const int q = (me + qi) % W;
         const size_t a = (size_t)lo[q] * elemBytes, b = (size_t)lo[q + 1] * elemBytes;
-        if (b > a) PRB_CUDA(cudaMemcpyAsync(c.mg.arena + arenaOffset + a, c.mg.peer[q] + arenaOffset + a, b - a, cudaMemcpyDeviceToDevice, c.stream));
+        src[n] = c.mg.peer[q] + arenaOffset + a; dst[n] = c.mg.arena + arenaOffset + a; bytes[n] = b - a; n++;
     }
+    PRB_TRY(mg_pull(c, n, src, dst, bytes));
     PRB_TRY(mg_barrier(c));
     return PRB_OK;
 }

@@ -397,13 +397,18 @@ int stage_octree(Context& c) {
         for (int q = 0; q < c.mg.world; q++)
             if (!c.mg.peer[q]) { set_error("multi-GPU: peer arenas not exchanged (prb_mg_set_peer)"); return PRB_ERR_STATE; }
         PRB_TRY(mg_barrier(c));
-        for (int qi = 1; qi < c.mg.world; qi++) {
-            const int q = (c.mg.rank + qi) % c.mg.world;
-            const size_t a = 12 * (size_t)lo[q], b = 12 * (size_t)lo[q + 1];
-            if (b > a) {
-                PRB_CUDA(cudaMemcpyAsync((char*)c.rawPp + a, c.mg.peer[q] + c.mgRawPOff + a, b - a, cudaMemcpyDeviceToDevice, st));
-                PRB_CUDA(cudaMemcpyAsync((char*)c.rawNp + a, c.mg.peer[q] + c.mgRawNOff + a, b - a, cudaMemcpyDeviceToDevice, st));
+        {
+            const void* src[2 * kMaxRanks];
+            void* dst[2 * kMaxRanks];
+            size_t bytes[2 * kMaxRanks];
+            int n = 0;
+            for (int qi = 1; qi < c.mg.world; qi++) {
+                const int q = (c.mg.rank + qi) % c.mg.world;
+                const size_t a = 12 * (size_t)lo[q], b = 12 * (size_t)lo[q + 1];
+                src[n] = c.mg.peer[q] + c.mgRawPOff + a; dst[n] = (char*)c.rawPp + a; bytes[n] = b - a; n++;
+                src[n] = c.mg.peer[q] + c.mgRawNOff + a; dst[n] = (char*)c.rawNp + a; bytes[n] = b - a; n++;
             }
+            PRB_TRY(mg_pull(c, n, src, dst, bytes));
         }
         PRB_TRY(mg_barrier(c));
         c.rawSharded = false;

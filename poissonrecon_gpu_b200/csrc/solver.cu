@@ -882,13 +882,23 @@ int stage_solve(Context& c) {
         c.mg.cgEpoch = (unsigned)hIters[15];
         // collect the other ranks' parts of the solution (pull over NVLink), then let nobody run ahead
         PRB_TRY(mg_barrier(c));
-        for (int qi = 1; qi < c.mg.world; qi++) {     // start with the next rank: the peers are not all pulled from in the same order
-            const int q = (c.mg.rank + qi) % c.mg.world;
-            const float* px = (const float*)(c.mg.peer[q] + c.mgXOff) + 7;
-            for (int d = c.shardFrom; d <= D; d++) {
-                size_t n = (size_t)(c.rowLo[d][q + 1] - c.rowLo[d][q]);
-                if (n) PRB_CUDA(cudaMemcpyAsync(c.xv + c.rowLo[d][q], px + c.rowLo[d][q], n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        {
+            const void* src[32];
+            void* dst[32];
+            size_t bytes[32];
+            int n = 0;
+            for (int qi = 1; qi < c.mg.world; qi++) {     // start with the next rank: the peers are not all pulled from in the same order
+                const int q = (c.mg.rank + qi) % c.mg.world;
+                const float* px = (const float*)(c.mg.peer[q] + c.mgXOff) + 7;
+                // one segment per peer when the depths' ranges would not fit the segment list (they are disjoint: fall back to a launch per peer)
+                for (int d = c.shardFrom; d <= D; d++) {
+                    const size_t cnt = (size_t)(c.rowLo[d][q + 1] - c.rowLo[d][q]);
+                    if (!cnt) continue;
+                    if (n == 32) { PRB_TRY(mg_pull(c, n, src, dst, bytes)); n = 0; }
+                    src[n] = px + c.rowLo[d][q]; dst[n] = c.xv + c.rowLo[d][q]; bytes[n] = cnt * sizeof(float); n++;
+                }
             }
+            PRB_TRY(mg_pull(c, n, src, dst, bytes));
         }
         PRB_TRY(mg_barrier(c));
         int err = 0;
