@@ -143,6 +143,8 @@ static int begin_run(Context& c, int64_t n) {
     c.launches = 0;
     c.detailUsed = 0;
     mark(c, "set_points");
+    // a peer wait that timed out in an earlier run (first-run skew: lazy module loading, large allocations) must not poison this one
+    if (c.mg.active() && c.mg.arena) PRB_CUDA(cudaMemsetAsync(&((MgHeader*)c.mg.arena)->error, 0, sizeof(int), c.stream));
     return PRB_OK;
 }
 
