@@ -900,9 +900,15 @@ struct RGeom {
     const float* baseFn;
     float iso;
     const float4* bvCell;         // BvTables::cellD
-    float* val7;                  // [nr * per]
+    float* val7;                  // corner-7 values, 512 per STORED brick: slot[brick] * 512 + (cell & 511)
     float* low;                   // [nr][3][(n+1)^2]
+    const int* slot;              // brick -> storage slot (its position among the bricks that are evaluated); null: every brick is stored
 };
+// storage index of virtual cell `cell` (= brick * 512 + position) in the per-brick arrays val7 / cat / emask / vpre: only the bricks
+// that are evaluated -- a few per cent of a pass -- are stored
+__device__ __forceinline__ i64 rv_store(const RGeom& G, i64 cell) {
+    return G.slot ? (((i64)G.slot[cell >> 9]) << 9) | (cell & 511) : cell;
+}
 
 static int ensure_bv_tables(Context& c);
 
@@ -1089,7 +1095,7 @@ __global__ void __launch_bounds__(64) k_rv_brick_values(RGeom G, const int* __re
         }
     }
 #pragma unroll
-    for (int cz = 0; cz < 8; cz++) G.val7[cell0 + (lxy - l0) + spread3((unsigned)cz)] = __fsub_rn(val[cz], G.iso);
+    for (int cz = 0; cz < 8; cz++) G.val7[rv_store(G, cell0) + (lxy - l0) + spread3((unsigned)cz)] = __fsub_rn(val[cz], G.iso);
     }
 }
 
@@ -1125,10 +1131,10 @@ __device__ __forceinline__ i64 rv_low_index(const RGeom& G, int r, int gx, int g
 }
 // value at grid point g of root r
 __device__ __forceinline__ float rv_point_value(const RGeom& G, int r, int gx, int gy, int gz) {
-    if (gx >= 1 && gy >= 1 && gz >= 1) return G.val7[(i64)r * G.per + rv_morton(gx - 1, gy - 1, gz - 1)];
+    if (gx >= 1 && gy >= 1 && gz >= 1) return G.val7[rv_store(G, (i64)r * G.per + rv_morton(gx - 1, gy - 1, gz - 1))];
     int r2, ox, oy, oz, jb;
     rv_point_owner(G, r, gx, gy, gz, r2, ox, oy, oz, jb);
-    if (jb == 7) return G.val7[(i64)r2 * G.per + rv_morton(ox, oy, oz)];
+    if (jb == 7) return G.val7[rv_store(G, (i64)r2 * G.per + rv_morton(ox, oy, oz))];
     return G.low[rv_low_index(G, r2, ox + (jb & 1), oy + ((jb >> 1) & 1), oz + ((jb >> 2) & 1))];
 }
 // corner jb of virtual cell (r, c) evaluated by one thread (lower faces of the pass region only)
@@ -1444,7 +1450,8 @@ __global__ void __launch_bounds__(512) k_rv_classify_brick(RGeom G, const unsign
         continue;
     }
     const int cx = (int)compact3((unsigned)tid >> 2), cy = (int)compact3((unsigned)tid >> 1), cz = (int)compact3((unsigned)tid);
-    const float own = G.val7[cell0 + tid];
+    const i64 store0 = rv_store(G, cell0);
+    const float own = G.val7[store0 + tid];
     sV[(cx + 1) * 81 + (cy + 1) * 9 + (cz + 1)] = own;
     bool pos = own > 0.f, neg = own < 0.f;
     if (tid < 217) {
@@ -1487,9 +1494,9 @@ __global__ void __launch_bounds__(512) k_rv_classify_brick(RGeom G, const unsign
     block_exclusive_scan((int)cMcCount[c], &totT, sScan);
     if (tid == 0) { brickV[brick] = totV; brickT[brick] = totT; }
     if (totV | totT) {
-        cat[t] = (unsigned char)c;
-        emask[t] = (unsigned short)m;
-        vpre[t] = (unsigned short)pre;
+        cat[store0 + tid] = (unsigned char)c;
+        emask[store0 + tid] = (unsigned short)m;
+        vpre[store0 + tid] = (unsigned short)pre;
     }
     }
 }
@@ -1510,8 +1517,9 @@ __global__ void __launch_bounds__(512) k_rv_emit_brick(RGeom G, const int* __res
     const int r = (int)(t / G.per);
     const unsigned l = (unsigned)(t - (i64)r * G.per);
     const int cx = (int)compact3(l >> 2), cy = (int)compact3(l >> 1), cz = (int)compact3(l);
-    const unsigned m = emask[t];
-    const int c = cat[t], nt = cMcCount[c];
+    const i64 ts = rv_store(G, t);
+    const unsigned m = emask[ts];
+    const int c = cat[ts], nt = cMcCount[c];
     int totT;
     const int tb = brickTBase[b] + block_exclusive_scan(nt, &totT, sScan);
     if (m) {
@@ -1520,7 +1528,7 @@ __global__ void __launch_bounds__(512) k_rv_emit_brick(RGeom G, const int* __res
         rv_cell_values(G, r, cx, cy, cz, v);
         const ushort4 ro = G.offs[G.roots[r]];
         const int ox = ((int)ro.x << G.lv) + cx, oy = ((int)ro.y << G.lv) + cy, oz = ((int)ro.z << G.lv) + cz;
-        int k = brickVBase[b] + (int)vpre[t];
+        int k = brickVBase[b] + (int)vpre[ts];
         for (int e = 0; e < 12; e++) {
             if (!(m & (1u << e))) continue;
             int r1 = cEdgeVertex[e][0], r2 = cEdgeVertex[e][1], dim = e >> 2;
@@ -1540,7 +1548,8 @@ __global__ void __launch_bounds__(512) k_rv_emit_brick(RGeom G, const int* __res
     for (int j = 0; j < 3 * nt; j++) {
         int e = cMcTri[c][j], e2;
         const i64 ow = rv_edge_owner(G, r, cx, cy, cz, e, e2);
-        outT[3 * (i64)tb + j] = brickVBase[(int)(ow >> 9)] + (int)vpre[ow] + __popc((unsigned)emask[ow] & ((1u << e2) - 1u));
+        const i64 os = rv_store(G, ow);
+        outT[3 * (i64)tb + j] = brickVBase[(int)(ow >> 9)] + (int)vpre[os] + __popc((unsigned)emask[os] & ((1u << e2) - 1u));
     }
     }
 }
@@ -1622,7 +1631,8 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     const int n = 1 << lv, n1 = n + 1;
     const unsigned per = 1u << (3 * lv);
     const i64 total = (i64)nr * per;
-    if ((double)total * 20.0 > (double)c.deviceMemBytes * 0.8) { set_error("refinement pass too large for device memory"); return PRB_ERR_NOMEM; }
+    if (total / 512 > 0x7fffffffll) { set_error("refinement pass too large (more than 2^31 bricks)"); return PRB_ERR_NOMEM; }
+    if ((double)total / 512.0 * 40.0 > (double)c.deviceMemBytes * 0.5) { set_error("refinement pass too large for device memory (per-brick tables)"); return PRB_ERR_NOMEM; }
     DBuf<int> rootNb;
     DBuf<float> rootX;
     DBuf<float>& low = c.wsLow;
@@ -1631,8 +1641,6 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     DBuf<unsigned short>& emask = c.wsEmask;
     PRB_TRY(rootNb.alloc(27 * (size_t)nr, st));
     PRB_TRY(rootX.alloc((size_t)nr * (rd + 1) * 27, st));
-    PRB_TRY(c.wsVal7.ensure((size_t)total, st));
-    float* val7p = c.wsVal7.p;
     PRB_TRY(low.ensure((size_t)nr * 3 * n1 * n1, st));
     PRB_LAUNCH(c, k_set_rootmap, grid_for(c, nr, 256), 256, 0, dRoots, nr, 0, 0, rootMap.p);
     PRB_LAUNCH(c, k_rv_roots, div_up((i64)nr * 32, 256), 256, 0, nr, rd, c.M, dRoots, rootMap.p, c.neighs.p, c.parent.p, c.xv, rootNb.p, rootX.p);
@@ -1642,7 +1650,7 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     G.roots = dRoots; G.rootNb = rootNb.p; G.rootX = rootX.p; G.offs = c.offs.p; G.child0 = c.child0.p; G.x = c.xv; G.baseFn = c.dBaseFn.p;
     PRB_TRY(ensure_bv_tables(c));
     G.bvCell = (const float4*)c.dBvCell.p;
-    G.iso = c.iso; G.val7 = val7p; G.low = low.p;
+    G.iso = c.iso; G.val7 = nullptr; G.low = low.p; G.slot = nullptr;
     const int nBricks = (int)(total / 512);
     // certified signs -> bricks to classify -> bricks to evaluate (every rank evaluates the same short list:
     // it is a few per cent of the pass, less than a rank's share of all bricks plus the peer pulls would be)
@@ -1666,9 +1674,17 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     DBuf<int> dCounts;
     PRB_TRY(dCounts.alloc(2, st));
     i64 nNeeded = 0;
-    PRB_TRY(exclusive_scan(c, needFlag.p, needExcl.p, nBricks, c.refineBoundCheck ? &nNeeded : nullptr));
+    PRB_TRY(exclusive_scan(c, needFlag.p, needExcl.p, nBricks, &nNeeded));       // (host round trip: the number of stored bricks sizes the value arrays)
     PRB_CUDA(cudaMemcpyAsync(dCounts.p, c.scanWork.ticket + 1, sizeof(int), cudaMemcpyDeviceToDevice, st));
     const unsigned persist = (unsigned)std::min<i64>(nBricks, (i64)c.smCount * 32);
+    // values, cases, masks and prefixes are stored for the bricks that are evaluated only (slot = position in that list; the test mode
+    // that evaluates everything stores everything)
+    const i64 nStored = c.refineBoundCheck ? (i64)nBricks : nNeeded;
+    if ((double)nStored * 512.0 * 9.0 > (double)c.deviceMemBytes * 0.6) { set_error("refinement pass too large for device memory (" + std::to_string(nStored) + " bricks to evaluate)"); return PRB_ERR_NOMEM; }
+    PRB_TRY(c.wsVal7.ensure((size_t)std::max<i64>(nStored, 1) * 512, st));
+    float* val7p = c.wsVal7.p;
+    G.val7 = val7p;
+    G.slot = c.refineBoundCheck ? nullptr : needExcl.p;
     if (c.refineBoundCheck) {
         // debug / test mode: evaluate everything and verify every certificate against the real values
         PRB_LAUNCH(c, k_rv_brick_values, persist, 64, 0, G, (const int*)nullptr, (const int*)nullptr, nBricks);
@@ -1690,10 +1706,10 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
         PRB_LAUNCH(c, k_rv_brick_values, persist, 64, 0, G, (const int*)needList.p, (const int*)dCounts.p, 0);
     }
     PRB_LAUNCH(c, k_rv_low_values, grid_for(c, (i64)nr * 3 * n1 * n1, 128, 16), 128, 0, G, c.refineBoundCheck ? (const unsigned char*)nullptr : (const unsigned char*)needLow.p);
-    cert.release(); needFlag.release(); needExcl.release(); needList.release(); needLow.release();
-    PRB_TRY(cat.ensure((size_t)total, st));
-    PRB_TRY(emask.ensure((size_t)total, st));
-    PRB_TRY(c.wsVpre.ensure((size_t)total, st));
+    cert.release(); needFlag.release(); needList.release(); needLow.release();
+    PRB_TRY(cat.ensure((size_t)std::max<i64>(nStored, 1) * 512, st));
+    PRB_TRY(emask.ensure((size_t)std::max<i64>(nStored, 1) * 512, st));
+    PRB_TRY(c.wsVpre.ensure((size_t)std::max<i64>(nStored, 1) * 512, st));
     DBuf<int> brickV, brickT, brickVBase, brickTBase, bflag, bexcl, active;
     PRB_TRY(brickV.alloc((size_t)nBricks, st)); PRB_TRY(brickT.alloc((size_t)nBricks, st));
     PRB_TRY(brickVBase.alloc((size_t)nBricks, st)); PRB_TRY(brickTBase.alloc((size_t)nBricks, st));
