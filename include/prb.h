@@ -121,7 +121,13 @@ int prb_debug_sort(prb_context* ctx, const uint64_t* keys, int64_t n, int key_bi
  * "refine" (1 = run the refinement passes, main.cu:3799-4564), "refine_implicit" (1; 0 = materialise
  * the virtual subtrees of every pass: cross-check path), "cg_zigzag" (1 = the CG phases sweep memory
  * in alternating directions for L2 reuse; results do not depend on it), "refine_bound_check" (0; 1 = evaluate
- * every refinement brick and fail if a certified sign is wrong: test mode). */
+ * every refinement brick and fail if a certified sign is wrong: test mode), "iso_density_weighted" (0; 1 = OPT-IN mode outside reference
+ * parity, SURVEY.md 8f-4: the iso value becomes the mean of chi over the samples weighted by 1 / (samples in the sample's ancestor cell
+ * at depth D-3), i.e. a mean over the surface instead of over the samples of an unevenly dense scan; prb_get_array("iso_modes") returns
+ * both means), "cascadic" (0; 1 = OPT-IN mode outside reference parity, SURVEY.md 8f-3: the depths are solved coarse to fine and the
+ * right-hand side of depth d first loses what the coarser solutions explain, b' = b - sum_{e<d} L_{d,e} x_e -- the coupling the
+ * reference's independent per-depth systems omit; single GPU; prb_get_array("cascadic_rhs") returns b'), "cg_bulk", "div_mode",
+ * "cg_timing", "detail" (INTEGRATION.md). */
 int prb_set_option(prb_context* ctx, const char* key, double value);
 
 /* ---- Multi-GPU (new: the reference is single-GPU, devID = 0 hard-coded at CG_CUDA.cuh:356).
@@ -156,7 +162,8 @@ int prb_mg_deal_passes(int depth_max, int n_passes, const int32_t* depth, const 
  * the named table for `depth` to `dst` and returns its size in bytes.  Names: gauss (4x4 f32),
  * max_depth_fn (4x4 f32), base_fn (res x 4 x 5 f32), df_table (f32), df_offset (i32, depth+2),
  * stencil ((depth+1) x 27 f32), ff0 ff1 d20 d21 (f64 per depth: same-depth 1-D <F,F> and
- * <F',F'> at centre distance 0 and 1). */
+ * <F',F'> at centre distance 0 and 1), ff_cross d2_cross (f64) + cross_offset (i32 (depth+1)^2): cross-depth 1-D integrals of the
+ * opt-in cascadic mode: entry cross_offset[d][e] + u, u = off_o - 2^(d-e) (off_n - 1), for a depth-d node o and a depth-e node n, e < d). */
 int64_t prb_host_tables(int depth, const char* name, void* dst, int64_t cap_bytes);
 
 #ifdef __cplusplus

@@ -256,6 +256,28 @@ void build_bspline_tables(int D, BSplineTables& T) {
             T.stencil[(size_t)d * 27 + j] = (float)e;
         }
     }
+    // cross-depth integrals (cascadic mode): function 1 = the finer node o (depth d), function 2 = the coarser node n (depth e)
+    T.crossOff.assign((size_t)(D + 1) * (D + 1), 0);
+    int total = 0;
+    for (int d = 0; d <= D; d++)
+        for (int e = 0; e < d; e++) { T.crossOff[(size_t)d * (D + 1) + e] = total; total += 3 << (d - e); }
+    T.ffX.assign((size_t)total, 0.0);
+    T.d2X.assign((size_t)total, 0.0);
+    for (int d = 0; d <= D; d++)
+        for (int e = 0; e < d; e++) {
+            const int k = 1 << (d - e);
+            const double w1 = 1.0 / (1 << d), w2 = 1.0 / (1 << e);
+            for (int u = 0; u < 3 * k; u++) {
+                const double ratio = (double)k, shift = 1.5 * k - u - 0.5;
+                double f = 0, s2 = 0;
+                if (bs.overlaps(ratio, shift)) {
+                    f = bs.ff(ratio, shift, w1);
+                    if (std::fabs(f) < 1e-15) f = 0; else s2 = bs.d2(ratio, shift, w2);
+                }
+                T.ffX[(size_t)T.cross_offset(d, e) + u] = f;
+                T.d2X[(size_t)T.cross_offset(d, e) + u] = s2;
+            }
+        }
 }
 
 }  // namespace prb

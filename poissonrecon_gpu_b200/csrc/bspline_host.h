@@ -31,6 +31,12 @@ struct BSplineTables {
     std::vector<float> stencil;        // (D+1) * 27
     // raw same-depth 1-D values per depth, (delta = 0, 1): for tests
     std::vector<double> ff0, ff1, d20, d21;
+    // cross-depth 1-D integrals of the OPT-IN cascadic solver mode (not in the reference, which solves the depths independently):
+    // for a node o of depth d and a node n of a coarser depth e < d, k = 2^(d-e), u = off_o - k * (off_n - 1) in [0, 3k):
+    //   ffX[crossOffset(d, e) + u] = <F_o, F_n>,   d2X[...] = <F_o', F_n'>          (same integration code as the tables above)
+    std::vector<double> ffX, d2X;
+    std::vector<int> crossOff;         // (D+1) x (D+1), row d, column e (valid for e < d)
+    int cross_offset(int d, int e) const { return crossOff[(size_t)d * (depth + 1) + e]; }
 };
 
 void build_bspline_tables(int depth, BSplineTables& out);

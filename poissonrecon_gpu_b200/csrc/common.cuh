@@ -232,6 +232,10 @@ struct Context {
     BSplineTables tab;
     DBuf<float> dMaxDepthFn, dBaseFn, dDfT, dStencil;
     DBuf<int> dDfOffset;
+    DBuf<double> dFfX, dD2X;       // cross-depth 1-D integrals (cascadic mode)
+    DBuf<int> dCrossOff;
+    DBuf<float> bCas;              // right-hand side of the cascadic mode (divg stays the reference's divergence)
+    int cascadic = 0;              // OPT-IN, outside reference parity: coarse-to-fine coupling of the depths (solver.cu k_cascadic_rhs)
     DBuf<float> dBvAnc, dBvOwn, dBvCell, dBvGrid;    // base-function values at cell corners per (depth, ancestor level) (mc.cu k_build_bv)
     int bvAncOff[kMaxDepth + 1] = {0}, bvOwnOff[kMaxDepth + 1] = {0};
     // ---- fields
@@ -242,6 +246,8 @@ struct Context {
     int divMode = 1;               // 1: block-table / profile divergence (field.cu); 0: first-version kernels through the 27-neighbour rows (cross-check)
     DBuf<float> pointValue;
     float iso = 0;
+    float isoPlain = 0, isoWeighted = 0;   // the reference's mean of chi over the samples / the density-weighted mean (opt-in, "iso_density_weighted")
+    int isoDensityWeighted = 0;
     int cgIters[kMaxDepth + 1] = {0};
     i64 cgRowIters = 0;
     // ---- mesh

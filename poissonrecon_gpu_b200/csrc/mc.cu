@@ -110,33 +110,47 @@ __device__ __forceinline__ void accumulate_level(float& val, const int* __restri
         val = __fmaf_rn(__fmul_rn(__fmul_rn((X)[j_], (vx)[j_ / 9]), (vy)[(j_ / 3) % 3]), (vz)[j_ % 3], val)
 
 // ------------------------------------------------------------------ A11 iso value
+// sum[0] = sum of chi over the samples (the reference's iso value is their plain mean, main.cu:3494-3496); sum[1], sum[2] = the
+// density-weighted sums of the opt-in mode (not in the reference): weight 1 / (samples in the sample's ancestor cell
+// at depth dk), so that the mean runs over the SURFACE rather than over the samples of an unevenly dense scan.
 __global__ void __launch_bounds__(128) k_point_values(const float* __restrict__ P, const int* __restrict__ p2n, i64 N, int baseD,
                                                       const int* __restrict__ neighs, const int* __restrict__ parent, const ushort4* __restrict__ offs,
+                                                      const int* __restrict__ pnum, int dk,
                                                       const float* __restrict__ x, const float* __restrict__ baseFn, float* __restrict__ pv, double* __restrict__ sum) {
-    double acc = 0.0;
+    double acc = 0.0, accW = 0.0, accWX = 0.0;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (i64)gridDim.x * blockDim.x) {
         float pos[3] = {P[3 * i], P[3 * i + 1], P[3 * i + 2]};
         int now = baseD + p2n[i];
         float val = 0.f;
+        int cellSamples = 1;
         while (now != -1) {
-            accumulate_level(val, neighs + 27 * (i64)now, offs[now], x, baseFn, pos);
+            const ushort4 o = offs[now];
+            if ((int)o.w == dk) cellSamples = pnum[now];
+            accumulate_level(val, neighs + 27 * (i64)now, o, x, baseFn, pos);
             now = parent[now];
         }
         pv[i] = val;
         acc += (double)val;
+        const double w = 1.0 / (double)(cellSamples > 0 ? cellSamples : 1);
+        accW += w;
+        accWX += w * (double)val;
     }
-    __shared__ double red[4];
+    __shared__ double red[3][4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_down_sync(0xffffffffu, acc, o);
+        accW += __shfl_down_sync(0xffffffffu, accW, o);
+        accWX += __shfl_down_sync(0xffffffffu, accWX, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = acc; red[1][threadIdx.x >> 5] = accWX; red[2][threadIdx.x >> 5] = accW; }
     __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(sum, red[0] + red[1] + red[2] + red[3]);
+    if (threadIdx.x < 3) atomicAdd(sum + threadIdx.x, red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3]);
 }
 
-// multi-GPU: every rank writes its partial sum into slot 31 of every rank's header
+// multi-GPU: every rank writes its partial sums into slots 29..31 of every rank's header
 __global__ void k_mg_publish_sum(MgDev mg, const double* __restrict__ v) {
-    if (threadIdx.x == 0 && blockIdx.x == 0)
-        for (int r = 0; r < mg.world; r++) mg.peerHdr[r]->slots[0][mg.rank][31] = *v;
+    if (threadIdx.x < 3 && blockIdx.x == 0)
+        for (int r = 0; r < mg.world; r++) mg.peerHdr[r]->slots[0][mg.rank][31 - threadIdx.x] = v[threadIdx.x];
 }
 
 int stage_iso(Context& c) {
@@ -144,35 +158,38 @@ int stage_iso(Context& c) {
     mark(c, "iso:begin");
     PRB_TRY(c.pointValue.alloc((size_t)c.N, st));
     DBuf<double> sum;
-    PRB_TRY(sum.alloc(1, st));
-    PRB_CUDA(cudaMemsetAsync(sum.p, 0, sizeof(double), st));
+    PRB_TRY(sum.alloc(3, st));
+    PRB_CUDA(cudaMemsetAsync(sum.p, 0, 3 * sizeof(double), st));
+    const int dk = c.D >= 3 ? c.D - 3 : 0;                 // depth of the density estimate of the weighted mode
     // multi-GPU: the samples are split evenly; the partial sums meet in the arena header
     const i64 p0 = c.mg.active() ? (c.N * c.mg.rank) / c.mg.world : 0, p1 = c.mg.active() ? (c.N * (c.mg.rank + 1)) / c.mg.world : c.N;
     if (p1 > p0)
-        PRB_LAUNCH(c, k_point_values, grid_for(c, p1 - p0, 128, 16), 128, 0, c.P.p + 3 * p0, c.p2n.p + p0, p1 - p0, c.base[c.D], c.neighs.p, c.parent.p, c.offs.p, c.xv,
+        PRB_LAUNCH(c, k_point_values, grid_for(c, p1 - p0, 128, 16), 128, 0, c.P.p + 3 * p0, c.p2n.p + p0, p1 - p0, c.base[c.D], c.neighs.p, c.parent.p, c.offs.p, c.pnum.p, dk, c.xv,
                    c.dBaseFn.p, c.pointValue.p + p0, sum.p);
-    double h = 0;
+    double h[3] = {0, 0, 0};
     if (c.mg.active()) {
         PRB_LAUNCH(c, k_mg_publish_sum, 1, 32, 0, c.mg.dev(), sum.p);
         PRB_TRY(mg_barrier(c));
         double parts[kMaxRanks][32];
         PRB_CUDA(cudaMemcpyAsync(parts, &((MgHeader*)c.mg.arena)->slots[0][0][0], sizeof(parts), cudaMemcpyDeviceToHost, st));
         PRB_CUDA(cudaStreamSynchronize(st));
-        for (int r = 0; r < c.mg.world; r++) h += parts[r][31];
+        for (int r = 0; r < c.mg.world; r++) { h[0] += parts[r][31]; h[1] += parts[r][30]; h[2] += parts[r][29]; }
     } else {
-        PRB_CUDA(cudaMemcpyAsync(&h, sum.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        PRB_CUDA(cudaMemcpyAsync(h, sum.p, sizeof(h), cudaMemcpyDeviceToHost, st));
         PRB_CUDA(cudaStreamSynchronize(st));
     }
-    // thrust::reduce(float) + "isoValue /= count" (main.cu:3494-3496)
     if (c.mg.active()) {
         int err = 0;
         PRB_CUDA(cudaMemcpyAsync(&err, &((MgHeader*)c.mg.arena)->error, sizeof(int), cudaMemcpyDeviceToHost, st));
         PRB_CUDA(cudaStreamSynchronize(st));
         if (err) { set_error("multi-GPU iso value: timed out waiting for a peer"); return PRB_ERR_CUDA; }
     }
-    float iso = (float)h;
+    // thrust::reduce(float) + "isoValue /= count" (main.cu:3494-3496)
+    float iso = (float)h[0];
     iso /= (float)c.N;
-    c.iso = iso;
+    c.isoPlain = iso;
+    c.isoWeighted = h[2] > 0 ? (float)(h[1] / h[2]) : iso;
+    c.iso = c.isoDensityWeighted ? c.isoWeighted : iso;
     sum.release();
     return PRB_OK;
 }

@@ -35,6 +35,14 @@ int upload_tables(Context& c) {
     PRB_CUDA(cudaMemcpyAsync(c.dDfT.p, c.tab.dfT.data(), c.dDfT.bytes(), cudaMemcpyHostToDevice, st));
     PRB_CUDA(cudaMemcpyAsync(c.dDfOffset.p, c.tab.dfOffset.data(), c.dDfOffset.bytes(), cudaMemcpyHostToDevice, st));
     PRB_CUDA(cudaMemcpyAsync(c.dStencil.p, c.tab.stencil.data(), c.dStencil.bytes(), cudaMemcpyHostToDevice, st));
+    PRB_TRY(c.dFfX.alloc(c.tab.ffX.size(), st));
+    PRB_TRY(c.dD2X.alloc(c.tab.d2X.size(), st));
+    PRB_TRY(c.dCrossOff.alloc(c.tab.crossOff.size(), st));
+    if (!c.tab.ffX.empty()) {
+        PRB_CUDA(cudaMemcpyAsync(c.dFfX.p, c.tab.ffX.data(), c.dFfX.bytes(), cudaMemcpyHostToDevice, st));
+        PRB_CUDA(cudaMemcpyAsync(c.dD2X.p, c.tab.d2X.data(), c.dD2X.bytes(), cudaMemcpyHostToDevice, st));
+    }
+    PRB_CUDA(cudaMemcpyAsync(c.dCrossOff.p, c.tab.crossOff.data(), c.dCrossOff.bytes(), cudaMemcpyHostToDevice, st));
     PRB_CUDA(cudaStreamSynchronize(st));
     return PRB_OK;
 }
@@ -87,6 +95,7 @@ int prb_create(int device, int depth, prb_context** out) {
     int r = upload_tables(c);
     if (r != PRB_OK) {
         c.dMaxDepthFn.release(); c.dBaseFn.release(); c.dDfT.release(); c.dDfOffset.release(); c.dStencil.release();
+        c.dFfX.release(); c.dD2X.release(); c.dCrossOff.release();
         return fail(r);
     }
     *out = h;
@@ -99,6 +108,7 @@ void prb_destroy(prb_context* h) {
     DeviceGuard guard__(c.device);
     release_all(c);
     c.wsVal7.release(); c.wsLow.release(); c.wsCat.release(); c.wsNtri.release(); c.wsEmask.release(); c.wsVpre.release(); c.wsVbase.release(); c.wsTbase.release();
+    c.dFfX.release(); c.dD2X.release(); c.dCrossOff.release(); c.bCas.release();
     c.dBvAnc.release(); c.dBvOwn.release(); c.dBvCell.release(); c.dBvGrid.release(); c.dMaxDepthFn.release(); c.dBaseFn.release(); c.dDfT.release(); c.dDfOffset.release(); c.dStencil.release();
     c.scanDesc.release(); c.scanTicket.release();
     if (c.hScanTotal) cudaFreeHost(c.hScanTotal);
@@ -123,6 +133,8 @@ int prb_set_option(prb_context* h, const char* key, double value) {
     else if (k == "cg_zigzag") h->c.cgZigzag = (int)value;
     else if (k == "cg_bulk") h->c.cgBulk = (int)value;
     else if (k == "cg_timing") h->c.cgTiming = (int)value;
+    else if (k == "iso_density_weighted") h->c.isoDensityWeighted = (int)value;
+    else if (k == "cascadic") h->c.cascadic = (int)value;
     else if (k == "detail") h->c.detail = (int)value;
     else if (k == "refine_bound_check") h->c.refineBoundCheck = (int)value;
     else if (k == "div_mode") h->c.divMode = (int)value;
@@ -360,9 +372,11 @@ int64_t prb_get_array(prb_context* h, const char* name, void* dst, int64_t cap) 
     else if (s == "mesh_v") D_(c.meshV.p, 12 * (size_t)c.nMeshV);
     else if (s == "mesh_t") D_(c.meshT.p, 12 * (size_t)c.nMeshT);
     else if (s == "iso") H_(&c.iso, 4);
+    else if (s == "iso_modes") { float v[2] = {c.isoPlain, c.isoWeighted}; H_(v, 8); }
     else if (s == "center_scale") { float v[4] = {c.center[0], c.center[1], c.center[2], c.scale}; H_(v, 16); }
     else if (s == "cg_iters") H_(c.cgIters, sizeof(int) * (D + 1));
     else if (s == "cg_phase_ns") H_(c.cgPhaseNs, sizeof(c.cgPhaseNs));
+    else if (s == "cascadic_rhs") D_(c.bCas.p ? c.bCas.p + 7 : nullptr, c.bCas.p ? 4 * (size_t)M : 0);
     else if (s == "detail_ms") {
         std::vector<float> ms;
         for (size_t k = 0; k + 1 < c.detailUsed; k++) { float v = 0; if (cudaEventElapsedTime(&v, c.detailEv[k], c.detailEv[k + 1]) != cudaSuccess) { cudaGetLastError(); v = -1; } ms.push_back(v); }
@@ -409,6 +423,9 @@ int64_t prb_host_tables(int depth, const char* name, void* dst, int64_t cap) {
     else if (s == "ff1") { src = t.ff1.data(); bytes = t.ff1.size() * 8; }
     else if (s == "d20") { src = t.d20.data(); bytes = t.d20.size() * 8; }
     else if (s == "d21") { src = t.d21.data(); bytes = t.d21.size() * 8; }
+    else if (s == "ff_cross") { src = t.ffX.data(); bytes = t.ffX.size() * 8; }
+    else if (s == "d2_cross") { src = t.d2X.data(); bytes = t.d2X.size() * 8; }
+    else if (s == "cross_offset") { src = t.crossOff.data(); bytes = t.crossOff.size() * 4; }
     else { set_error("unknown table " + s); return PRB_ERR_ARG; }
     if (dst && cap >= (int64_t)bytes && bytes) std::memcpy(dst, src, bytes);
     return (int64_t)bytes;

@@ -141,6 +141,7 @@ struct CgParams {
     unsigned epoch0;
     unsigned* barCount;            // arrival counter / release flag of cg_sync (zeroed before the launch)
     unsigned* barRelease;
+    int onlyDepth;                 // -1: all depths in lock-step (the reference's independent systems); d: solve depth d alone (cascadic mode)
     long long* phaseNs;            // optional [8]: time CTA 0 spent in phase C / its barrier / SpMV / barrier / phase B / barrier (ns, %globaltimer)
 };
 
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
     __syncthreads();
 
     // ---- depth 0: a 1x1 system, solved by one thread with the same recurrences
-    if (blockIdx.x == 0 && tid == 0) {
+    if (blockIdx.x == 0 && tid == 0 && P.onlyDepth <= 0) {
         float a00 = sSt[0][0];
         float x0 = 0.f, r = P.b[0], p = 0.f, r0 = 0.f;
         float r1 = (float)(double)(r * r);
@@ -402,6 +403,7 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
     {
         // b (the divergence) is an unpadded array, so its quads are not 16-byte aligned: scalar loads
         for (int d = 1; d <= D; d++) {
+            if (P.onlyDepth >= 0 && d != P.onlyDepth) continue;        // (the other depths keep their solution)
             const int i0 = P.row0[d], i1 = P.row1[d];
             double part = 0.0;
             for (int i = i0 + gthread; i < i1; i += nthreads) {
@@ -419,7 +421,7 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
     if (tid >= 1 && tid <= D) {
         float r1 = (float)cg_total<MG>(P, epoch, tid, P.dots + 64);
         sR1[tid] = r1; sIter[tid] = 1; sBeta[tid] = 0.f; sAlpha[tid] = 0.f; sPend[tid] = 0;
-        sActive[tid] = (r1 > P.tol2 && 1 <= P.maxIter) ? 1 : 0;
+        sActive[tid] = (r1 > P.tol2 && 1 <= P.maxIter && (P.onlyDepth < 0 || tid == P.onlyDepth)) ? 1 : 0;
     }
     __syncthreads();
 
@@ -775,8 +777,49 @@ __global__ void __launch_bounds__(kCgBlock, 1) k_cg_all_depths(const __grid_cons
             }
         }
     }
-    if (blockIdx.x == 0 && tid >= 1 && tid <= D) { P.itersOut[tid] = sIter[tid] - 1; P.resOut[tid] = sR1[tid]; }
+    if (blockIdx.x == 0 && tid >= 1 && tid <= D && (P.onlyDepth < 0 || tid == P.onlyDepth)) { P.itersOut[tid] = sIter[tid] - 1; P.resOut[tid] = sR1[tid]; }
     if (blockIdx.x == 0 && tid == 0) P.itersOut[15] = (int)epoch;
+}
+
+// OPT-IN cascadic mode (the reference solves its D+1 systems independently, main.cu:1237-1329): before depth d is
+// solved, the contribution of the coarser solutions is taken out of its right-hand side,
+//   b'_o = b_o - sum_{e < d} sum_{n in N27(ancestor_e(o))} L(o, n) x_n,   L = D2x FFy FFz + FFx D2y FFz + FFx FFy D2z
+// with the cross-depth 1-D integrals of bspline_host (ffX / d2X, indexed by u = off_o - 2^(d-e) (off_n - 1) per axis; computed in double
+// and narrowed to float like the reference's same-depth entries, main.cu:1199-1207).  One thread per node of depth d.
+__global__ void __launch_bounds__(256) k_cascadic_rhs(int d, int base, int count, const int* __restrict__ parent, const int* __restrict__ neighs, const ushort4* __restrict__ offs,
+                                                      const double* __restrict__ ffX, const double* __restrict__ d2X, const int* __restrict__ crossOff /* row d of the table */,
+                                                      const float* __restrict__ x, const float* __restrict__ bIn, float* __restrict__ bOut) {
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < count; l += gridDim.x * blockDim.x) {
+        const int o = base + l;
+        const ushort4 oo = offs[o];
+        double acc = 0.0;
+        int a = parent[o];
+        for (int e = d - 1; e >= 0 && a >= 0; --e) {
+            const int k = 1 << (d - e);
+            const ushort4 ao = offs[a];
+            const int rx = (int)oo.x - (int)ao.x * k, ry = (int)oo.y - (int)ao.y * k, rz = (int)oo.z - (int)ao.z * k;      // in [0, k)
+            const double* F = ffX + crossOff[e];
+            const double* S = d2X + crossOff[e];
+            double fx[3], fy[3], fz[3], sx[3], sy[3], sz[3];
+#pragma unroll
+            for (int t = 0; t < 3; t++) {            // neighbour direction t - 1 along the axis: u = r + (1 - (t - 1)) k
+                const int ux = rx + (2 - t) * k, uy = ry + (2 - t) * k, uz = rz + (2 - t) * k;
+                fx[t] = F[ux]; fy[t] = F[uy]; fz[t] = F[uz];
+                sx[t] = S[ux]; sy[t] = S[uy]; sz[t] = S[uz];
+            }
+            const int* nb = neighs + 27 * (i64)a;
+#pragma unroll
+            for (int j = 0; j < 27; j++) {
+                const int n = nb[j];
+                if (n < 0) continue;
+                const int jx = j / 9, jy = (j / 3) % 3, jz = j % 3;
+                const float L = (float)(sx[jx] * fy[jy] * fz[jz] + fx[jx] * sy[jy] * fz[jz] + fx[jx] * fy[jy] * sz[jz]);
+                acc += (double)(L * x[n]);
+            }
+            a = parent[a];
+        }
+        bOut[o] = bIn[o] - (float)acc;
+    }
 }
 
 int build_cg_table(Context& c) {
@@ -869,8 +912,27 @@ int stage_solve(Context& c) {
     if (gridSize < 1) gridSize = 1;
     mark(c, "solve:setup");
     void* args[] = {(void*)&P};
-    PRB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(gridSize), dim3(kCgBlock), args, dynSmem, st));
-    c.launches++;
+    P.onlyDepth = -1;
+    if (!c.cascadic) {
+        PRB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(gridSize), dim3(kCgBlock), args, dynSmem, st));
+        c.launches++;
+    } else {
+        // cascadic mode: depth by depth, coarse to fine; the right-hand side of depth d first loses what the coarser solutions explain
+        if (mg) { set_error("the cascadic mode is single-GPU"); return PRB_ERR_STATE; }
+        PRB_TRY(c.bCas.alloc((size_t)M + 16, st));
+        float* bc = c.bCas.p + 7;
+        PRB_CUDA(cudaMemcpyAsync(bc, c.divgv, sizeof(float) * (size_t)M, cudaMemcpyDeviceToDevice, st));
+        P.b = bc;
+        for (int d = 0; d <= D; d++) {
+            if (d >= 1)
+                PRB_LAUNCH(c, k_cascadic_rhs, grid_for(c, c.cnt[d], 256), 256, 0, d, c.base[d], c.cnt[d], c.parent.p, c.neighs.p, c.offs.p, c.dFfX.p, c.dD2X.p,
+                           c.dCrossOff.p + (size_t)d * (D + 1), c.xv, c.divgv, bc);
+            PRB_CUDA(cudaMemsetAsync(dots.p, 0, (96 + 32) * sizeof(double), st));
+            P.onlyDepth = d;
+            PRB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(gridSize), dim3(kCgBlock), args, dynSmem, st));
+            c.launches++;
+        }
+    }
     mark(c, "solve:kernel");
     int hIters[16];
     if (c.cgTiming) PRB_CUDA(cudaMemcpyAsync(c.cgPhaseNs, phaseNs.p, 8 * sizeof(long long), cudaMemcpyDeviceToHost, st));

@@ -352,3 +352,42 @@ def test_full_size_properties(config):
     if config == "scan5m_d10":
         rad = np.linalg.norm(w[: st["n_vertices"]], axis=1)
         assert np.median(np.abs(rad - 1.0)) < 0.02
+
+
+def test_density_weighted_iso_value_opt_in():
+    """SURVEY.md 8f-4 (NOT in the reference, off by default): iso value = mean of chi over the samples weighted by
+    1 / (samples in the ancestor cell three levels above the leaf).  Checked against a numpy restatement on the library's own
+    arrays; the default path is untouched; on the 20:1 scan the weighted value differs, on a uniform sphere it barely moves."""
+    from poissonrecon_gpu_b200 import PoissonRecon, synth
+
+    def both(p, n, D):
+        pr = PoissonRecon(D)
+        pr.set_points(p, n)
+        pr.run()
+        plain, weighted = pr.get("iso_modes", "<f4").tolist()
+        assert plain == float(pr.get("iso", "<f4")[0])                      # default = the reference's plain mean
+        base = pr.get("base", "<i4")
+        node = int(base[D]) + pr.get("p2n", "<i4").astype(np.int64)
+        parent = pr.get("parent", "<i4").astype(np.int64)
+        for _ in range(3):
+            node = parent[node]
+        w = 1.0 / pr.get("pnum", "<i4")[node].astype(np.float64)
+        pv = pr.get("pointvalue", "<f4").astype(np.float64)
+        expect = float((w * pv).sum() / w.sum())
+        assert abs(weighted - expect) <= 1e-5 * abs(expect)
+        v0, t0 = pr.mesh()
+        pr.set_option("iso_density_weighted", 1)
+        pr.set_points(p, n)
+        pr.run()
+        assert float(pr.get("iso", "<f4")[0]) == weighted
+        v1, t1 = pr.mesh()
+        assert t1.shape[0] > 0
+        pr.close()
+        return plain, weighted, t0.shape[0], t1.shape[0]
+
+    p, n = synth.nonuniform_scan(200_000)
+    plain, weighted, _, _ = both(p, n, 8)
+    assert abs(weighted - plain) > 1e-3 * abs(plain)
+    p, n = synth.sphere(100_000)
+    plain, weighted, nt0, nt1 = both(p, n, 7)
+    assert abs(weighted - plain) < 0.05 * abs(plain) and abs(nt1 - nt0) < 0.05 * nt0
