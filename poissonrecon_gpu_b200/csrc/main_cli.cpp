@@ -2,6 +2,7 @@
 //
 //   poisson_recon --in points.{ply,bnpts,txt} --out mesh.ply --depth D [--binary] [--device k] [--gpus N]
 //                 [--dump DIR] [--weld] [--no-refine] [--json] [--arena-gb G]
+//                 [--cascadic] [--density-weighted-iso]      (opt-in modes OUTSIDE reference parity, include/prb.h options)
 //
 // The reference hard-codes its paths (main.cu:3251-3252) and compiles the depth in
 // (main.cu:69); the `--name value` convention is the one its own (unused) parser implements
@@ -34,12 +35,12 @@
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 static void usage(const char* a0) {
-    std::fprintf(stderr, "usage: %s --in <points.ply|.bnpts|ascii> --out <mesh.ply> [--depth D=8] [--binary] [--device k] [--gpus N] [--dump DIR] [--weld] [--no-refine] [--json] [--arena-gb G]\n", a0);
+    std::fprintf(stderr, "usage: %s --in <points.ply|.bnpts|ascii> --out <mesh.ply> [--depth D=8] [--binary] [--device k] [--gpus N] [--dump DIR] [--weld] [--no-refine] [--json] [--arena-gb G] [--cascadic] [--density-weighted-iso]\n", a0);
 }
 
 struct Args {
     std::string in, out, dump;
-    int depth = 8, device = 0, binary = 0, refine = 1, json = 0, gpus = 1, weld = 0;
+    int depth = 8, device = 0, binary = 0, refine = 1, json = 0, gpus = 1, weld = 0, cascadic = 0, densityIso = 0;
     double arenaGb = 0;
 };
 
@@ -97,6 +98,8 @@ static int run_rank(const Args& a, int rank, int world, const std::string& dir, 
     prb_context* ctx = nullptr;
     if (prb_create(a.device + rank, a.depth, &ctx) != PRB_OK) { std::fprintf(stderr, "[rank %d] %s\n", rank, prb_last_error()); return 1; }
     prb_set_option(ctx, "refine", a.refine);
+    prb_set_option(ctx, "cascadic", a.cascadic);
+    prb_set_option(ctx, "iso_density_weighted", a.densityIso);
     if (world > 1) {
         const double gb = a.arenaGb > 0 ? a.arenaGb : (330.0 * (double)n + (double)(64 << 20)) / (double)(1 << 30);
         char mine[64];
@@ -162,11 +165,14 @@ int main(int argc, char** argv) {
         else if (s == "--binary") a.binary = 1;
         else if (s == "--weld") a.weld = 1;
         else if (s == "--no-refine") a.refine = 0;
+        else if (s == "--cascadic") a.cascadic = 1;
+        else if (s == "--density-weighted-iso") a.densityIso = 1;
         else if (s == "--json") a.json = 1;
         else if (s == "--help" || s == "-h") { usage(argv[0]); return 0; }
         else { std::fprintf(stderr, "unknown argument %s\n", s.c_str()); usage(argv[0]); return 2; }
     }
     if (a.in.empty() || a.out.empty() || a.gpus < 1 || a.gpus > 8) { usage(argv[0]); return 2; }
+    if (a.cascadic && a.gpus > 1) { std::fprintf(stderr, "--cascadic is a single-GPU mode\n"); return 2; }
     const double t0 = now_s();
     float *xyz = nullptr, *nrm = nullptr;
     int64_t n = 0;

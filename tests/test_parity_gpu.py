@@ -391,3 +391,78 @@ def test_density_weighted_iso_value_opt_in():
     p, n = synth.sphere(100_000)
     plain, weighted, nt0, nt1 = both(p, n, 7)
     assert abs(weighted - plain) < 0.05 * abs(plain) and abs(nt1 - nt0) < 0.05 * nt0
+
+
+def test_cascadic_mode_opt_in():
+    """SURVEY.md 8f-3 (NOT in the reference, off by default): depths solved coarse to fine, the right-hand side of depth d first loses
+    what the coarser solutions explain.  A numpy restatement of b' = b - sum_{e<d} L_{d,e} x_e (cross-depth integrals from
+    prb_host_tables, neighbour table, parent chain) must reproduce the library's right-hand side, every depth must solve its own
+    system A_dd x_d = b'_d, depth 0 is untouched, and the default mode is unchanged."""
+    from poissonrecon_gpu_b200 import PoissonRecon, api, synth
+    p, n = synth.sphere(20_000, seed=7)
+    D = 6
+    pr = PoissonRecon(D)
+    pr.set_points(p, n)
+    pr.run()
+    x_ind, t_ind = pr.get("x", "<f4"), pr.mesh()[1]
+    pr.set_option("cascadic", 1)
+    pr.set_points(p, n)
+    pr.run()
+    x, b, bc = pr.get("x", "<f4").astype(np.float64), pr.get("divergence", "<f4").astype(np.float64), pr.get("cascadic_rhs", "<f4").astype(np.float64)
+    base = pr.get("base", "<i4").astype(np.int64)
+    parent = pr.get("parent", "<i4").astype(np.int64)
+    nbr = pr.get("neighs", "<i4").reshape(-1, 27).astype(np.int64)
+    key = pr.get("key", "<u8").astype(np.int64)
+    M = key.shape[0]
+    depth = np.zeros(M, np.int64)
+    for d in range(D + 1):
+        depth[base[d]:base[d + 1]] = d
+    off = np.zeros((M, 3), np.int64)
+    for lv in range(1, D + 1):
+        c = (key >> (3 * (D - lv))) & 7
+        m = depth >= lv
+        sh = np.maximum(depth - lv, 0)
+        for a, bit in enumerate((2, 1, 0)):
+            off[:, a] |= np.where(m, ((c >> bit) & 1) << sh, 0)
+    lib = api.load_library()
+
+    def table(name, dt):
+        nb = lib.prb_host_tables(D, name.encode(), None, 0)
+        a = np.empty(nb // np.dtype(dt).itemsize, dt)
+        lib.prb_host_tables(D, name.encode(), a.ctypes.data, nb)
+        return a
+
+    ffX, d2X, co = table("ff_cross", "<f8"), table("d2_cross", "<f8"), table("cross_offset", "<i4").reshape(D + 1, D + 1)
+    st = pr.get("lap_stencil", "<f4").reshape(-1, 27).astype(np.float64)
+    assert np.array_equal(bc[: base[1]], b[: base[1]])                                        # depth 0 has nothing coarser
+    assert np.array_equal(x[:1].astype(np.float32), x_ind[:1])
+    for d in range(1, D + 1):
+        sl = np.arange(base[d], base[d + 1])
+        acc = np.zeros(sl.size)
+        anc = parent[sl]
+        for e in range(d - 1, -1, -1):
+            k = 1 << (d - e)
+            r = off[sl] - off[anc] * k
+            assert ((r >= 0) & (r < k)).all()
+            F, S = ffX[co[d, e]:co[d, e] + 3 * k], d2X[co[d, e]:co[d, e] + 3 * k]
+            for j in range(27):
+                dj = (j // 9 - 1, (j // 3) % 3 - 1, j % 3 - 1)
+                q = nbr[anc, j]
+                u = [r[:, a] + (1 - dj[a]) * k for a in range(3)]
+                L = (S[u[0]] * F[u[1]] * F[u[2]] + F[u[0]] * S[u[1]] * F[u[2]] + F[u[0]] * F[u[1]] * S[u[2]]).astype(np.float32).astype(np.float64)
+                acc += np.where(q >= 0, L * x[np.maximum(q, 0)], 0.0)
+            anc = parent[anc]
+        expect = b[sl] - acc
+        assert rel_l2(bc[sl], expect) <= 1e-5, d
+        ax = np.zeros(sl.size)
+        for j in range(27):
+            q = nbr[sl, j]
+            ax += np.where(q >= 0, x[np.maximum(q, 0)], 0.0) * st[d, j]
+        assert np.linalg.norm(bc[sl] - ax) <= 1e-4 * max(np.linalg.norm(bc[sl]), 1.0), d       # the depth solves ITS coupled system
+    assert rel_l2(x[base[D]:].astype(np.float32), x_ind[base[D]:]) > 1e-3                      # and that is another solution than the independent one
+    assert pr.mesh()[1].shape[0] > 0
+    pr.set_option("cascadic", 0)
+    pr.set_points(p, n)
+    pr.run()
+    assert np.array_equal(pr.get("x", "<f4"), x_ind) and np.array_equal(pr.mesh()[1], t_ind)   # default path untouched
+    pr.close()

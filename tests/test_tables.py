@@ -133,3 +133,47 @@ def test_full_tables_translation_invariance():
                 t = s - k * (oo - 1)
                 if 0 <= t < 3 * k:
                     assert dft[off[d] + t] == want, (d, oo, s)
+
+
+def test_cross_depth_integrals_against_quadrature():
+    """Tables of the opt-in cascadic mode (prb_host_tables ff_cross / d2_cross; not in the reference): <F_o, F_n> and <F_o', F_n'> for a
+    depth-d node o and a coarser depth-e node n, against Gauss-Legendre quadrature of the closed-form B-spline between the knots."""
+    import ctypes
+    from poissonrecon_gpu_b200 import api
+    lib = api.load_library()
+
+    def table(D, name, dt):
+        nb = lib.prb_host_tables(D, name.encode(), None, 0)
+        a = np.empty(nb // np.dtype(dt).itemsize, dt)
+        lib.prb_host_tables(D, name.encode(), a.ctypes.data, nb)
+        return a
+
+    D = 6
+    ff, d2, off = table(D, "ff_cross", "<f8"), table(D, "d2_cross", "<f8"), table(D, "cross_offset", "<i4").reshape(D + 1, D + 1)
+    assert ff.size == d2.size == sum(3 << (d - e) for d in range(D + 1) for e in range(d))
+
+    def B(t):
+        t = np.abs(t)
+        return np.where(t < 0.5, 1 - (4 / 3) * t * t, np.where(t < 1.5, (2 / 3) * (1.5 - t) ** 2, 0.0))
+
+    def dB(t):
+        a = np.abs(t)
+        return np.where(a < 0.5, -(8 / 3) * t, np.where(a < 1.5, -(4 / 3) * (1.5 - a) * np.sign(t), 0.0))
+
+    xs, ws = np.polynomial.legendre.leggauss(8)
+
+    def integ(f, knots):
+        pts = np.unique(knots)
+        return sum(0.5 * (b - a) * (ws * f(0.5 * (b - a) * xs + 0.5 * (a + b))).sum() for a, b in zip(pts[:-1], pts[1:]))
+
+    worst = 0.0
+    for d in range(1, D + 1):
+        for e in range(d):
+            k, w1, w2 = 1 << (d - e), 2.0 ** -d, 2.0 ** -e
+            for u in range(3 * k):
+                c1, c2 = (u + 0.5) * w1, 1.5 * w2                     # o at fine offset u, n at coarse offset 1: u = off_o - k (off_n - 1)
+                knots = np.concatenate([c1 + w1 * np.array([-1.5, -.5, .5, 1.5]), c2 + w2 * np.array([-1.5, -.5, .5, 1.5])])
+                F = integ(lambda x: B((x - c1) / w1) * B((x - c2) / w2), knots)
+                G = integ(lambda x: dB((x - c1) / w1) / w1 * dB((x - c2) / w2) / w2, knots)
+                worst = max(worst, abs(ff[off[d, e] + u] - F) / w1, abs(d2[off[d, e] + u] - G) * w1)
+    assert worst < 5e-5, worst          # the table code does its polynomial algebra in float, like the reference's (DF(0) = -1.3e-5)
