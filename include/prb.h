@@ -124,10 +124,13 @@ int prb_debug_sort(prb_context* ctx, const uint64_t* keys, int64_t n, int key_bi
  * every refinement brick and fail if a certified sign is wrong: test mode), "iso_density_weighted" (0; 1 = OPT-IN mode outside reference
  * parity, SURVEY.md 8f-4: the iso value becomes the mean of chi over the samples weighted by 1 / (samples in the sample's ancestor cell
  * at depth D-3), i.e. a mean over the surface instead of over the samples of an unevenly dense scan; prb_get_array("iso_modes") returns
- * both means), "cascadic" (0; 1 = OPT-IN mode outside reference parity, SURVEY.md 8f-3: the depths are solved coarse to fine and the
+ * [plain mean, weighted mean]; the weighted one is only computed with the option on), "cascadic" (0; 1 = OPT-IN mode outside reference parity, SURVEY.md 8f-3: the depths are solved coarse to fine and the
  * right-hand side of depth d first loses what the coarser solutions explain, b' = b - sum_{e<d} L_{d,e} x_e -- the coupling the
  * reference's independent per-depth systems omit; single GPU; prb_get_array("cascadic_rhs") returns b'), "cg_bulk", "div_mode",
- * "cg_timing", "detail" (INTEGRATION.md). */
+ * "cg_timing", "detail" (INTEGRATION.md), "early_mesh_copy" (0; 1 = the device -> host copy of the main marching-cubes piece into the
+ * pinned buffers prb_get_mesh returns starts before the refinement passes and runs under them; same mesh, no net gain measured),
+ * "mg_timeout_ms" (2000: how long a rank waits for a peer at a cross-GPU barrier before the run
+ * fails with PRB_ERR_CUDA instead of hanging; converted to SM cycles at 2 GHz). */
 int prb_set_option(prb_context* ctx, const char* key, double value);
 
 /* ---- Multi-GPU (new: the reference is single-GPU, devID = 0 hard-coded at CG_CUDA.cuh:356).

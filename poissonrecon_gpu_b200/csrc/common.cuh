@@ -90,8 +90,10 @@ template <class T>
 struct HBuf {
     T* p = nullptr;
     size_t cap = 0;
+    unsigned generation = 0;      // bumped by every reallocation (the new block may well sit at the old address)
     int reserve(size_t count) {
         if (count <= cap) return PRB_OK;
+        generation++;
         if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
@@ -136,6 +138,7 @@ struct MgDev {                                // passed by value to kernels
     int rank, world;
     MgHeader* hdr;                            // own header
     MgHeader* peerHdr[kMaxRanks];
+    long long spinCycles;                     // give-up limit of a peer wait, in SM clock cycles
 };
 struct MgState {
     int rank = 0, world = 1;
@@ -147,6 +150,7 @@ struct MgState {
     unsigned xchgCount = 0;                   // number of mg_exchange_ints calls so far (buffer parity)
     unsigned cgEpoch = 0;                     // the same for the in-kernel barriers of the CG solve (their own flag words)
     int minShardRows = 65536;                 // depths with fewer rows stay replicated
+    long long spinCycles = 4000000000ll;      // ~2 s at 2 GHz (option "mg_timeout_ms"): a rank that died must not hang the others (and the box)
     bool active() const { return world > 1; }
     void reset_allocs() { used = kMgHeaderBytes; }
     template <class T>
@@ -159,7 +163,7 @@ struct MgState {
     }
     MgDev dev() const {
         MgDev d;
-        d.rank = rank; d.world = world; d.hdr = (MgHeader*)arena;
+        d.rank = rank; d.world = world; d.hdr = (MgHeader*)arena; d.spinCycles = spinCycles;
         for (int r = 0; r < kMaxRanks; r++) d.peerHdr[r] = (MgHeader*)peer[r];
         return d;
     }
@@ -257,6 +261,15 @@ struct Context {
     HBuf<float> hMeshV;            // pinned host copies (prb_get_mesh)
     HBuf<int> hMeshT;
     bool hMeshValid = false;
+    // OPTIONAL early device -> host copy of the main marching-cubes piece (it leads the mesh and is final before the refinement passes
+    // start): runs on its own stream under the passes; prb_get_mesh then only copies what the passes added.  Off by default: measured
+    // on scan5m_d10 it saves the 1.2 ms download but the passes' ~50 short host round trips queue behind the bulk PCIe traffic and
+    // lose as much (36.8 vs 36.7 ms end to end, profiles/r02/e2e_early_copy_ab.txt)
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evMainPiece = nullptr, evEarlyCopy = nullptr, evPositions = nullptr, evNormals = nullptr;
+    bool normalsPending = false;  // the upload of the normals runs on copyStream behind the positions; the sort's gather pass waits for evNormals
+    i64 earlyV = 0, earlyT = 0;   // vertices / triangles already in hMeshV / hMeshT
+    int earlyMeshCopy = 0;        // option "early_mesh_copy"
     std::vector<PassRecord> passes;            // every pass of the reconstruction (all ranks), in output order
     struct PieceRecord { long long pass, vBase, nv, tBase, nt; };
     std::vector<PieceRecord> layout;           // the pieces of the mesh THIS context holds: global vertex / triangle offsets (1 GPU: all passes)
@@ -307,7 +320,8 @@ int build_cg_table(Context& c);       // solver.cu: sgTab -> sgTab4
 
 // exclusive scan of n ints on the context stream; returns the grand total through *total_host
 // (synchronises the stream) when total_host != nullptr.
-int exclusive_scan(Context& c, const int* in, int* out, i64 n, i64* total_host);
+int exclusive_scan(Context& c, const int* in, int* out, i64 n, i64* total_host, int hostSlot = 0);
+int ensure_copy_stream(Context& c);           // second stream + its events (uploads / downloads that run under compute)
 
 #define PRB_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
     do {                                                                        \

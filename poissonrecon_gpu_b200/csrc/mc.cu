@@ -113,6 +113,7 @@ __device__ __forceinline__ void accumulate_level(float& val, const int* __restri
 // sum[0] = sum of chi over the samples (the reference's iso value is their plain mean, main.cu:3494-3496); sum[1], sum[2] = the
 // density-weighted sums of the opt-in mode (not in the reference): weight 1 / (samples in the sample's ancestor cell
 // at depth dk), so that the mean runs over the SURFACE rather than over the samples of an unevenly dense scan.
+template <bool WEIGHTED>
 __global__ void __launch_bounds__(128) k_point_values(const float* __restrict__ P, const int* __restrict__ p2n, i64 N, int baseD,
                                                       const int* __restrict__ neighs, const int* __restrict__ parent, const ushort4* __restrict__ offs,
                                                       const int* __restrict__ pnum, int dk,
@@ -125,15 +126,17 @@ __global__ void __launch_bounds__(128) k_point_values(const float* __restrict__ 
         int cellSamples = 1;
         while (now != -1) {
             const ushort4 o = offs[now];
-            if ((int)o.w == dk) cellSamples = pnum[now];
+            if (WEIGHTED && (int)o.w == dk) cellSamples = pnum[now];
             accumulate_level(val, neighs + 27 * (i64)now, o, x, baseFn, pos);
             now = parent[now];
         }
         pv[i] = val;
         acc += (double)val;
-        const double w = 1.0 / (double)(cellSamples > 0 ? cellSamples : 1);
-        accW += w;
-        accWX += w * (double)val;
+        if (WEIGHTED) {
+            const double w = 1.0 / (double)(cellSamples > 0 ? cellSamples : 1);
+            accW += w;
+            accWX += w * (double)val;
+        }
     }
     __shared__ double red[3][4];
 #pragma unroll
@@ -163,9 +166,15 @@ int stage_iso(Context& c) {
     const int dk = c.D >= 3 ? c.D - 3 : 0;                 // depth of the density estimate of the weighted mode
     // multi-GPU: the samples are split evenly; the partial sums meet in the arena header
     const i64 p0 = c.mg.active() ? (c.N * c.mg.rank) / c.mg.world : 0, p1 = c.mg.active() ? (c.N * (c.mg.rank + 1)) / c.mg.world : c.N;
-    if (p1 > p0)
-        PRB_LAUNCH(c, k_point_values, grid_for(c, p1 - p0, 128, 16), 128, 0, c.P.p + 3 * p0, c.p2n.p + p0, p1 - p0, c.base[c.D], c.neighs.p, c.parent.p, c.offs.p, c.pnum.p, dk, c.xv,
-                   c.dBaseFn.p, c.pointValue.p + p0, sum.p);
+    // (the weighted sums cost 0.2 ms on 5 M samples: only taken when the opt-in mode asks for them)
+    if (p1 > p0) {
+        if (c.isoDensityWeighted)
+            PRB_LAUNCH(c, k_point_values<true>, grid_for(c, p1 - p0, 128, 16), 128, 0, c.P.p + 3 * p0, c.p2n.p + p0, p1 - p0, c.base[c.D], c.neighs.p, c.parent.p, c.offs.p, c.pnum.p, dk,
+                       c.xv, c.dBaseFn.p, c.pointValue.p + p0, sum.p);
+        else
+            PRB_LAUNCH(c, k_point_values<false>, grid_for(c, p1 - p0, 128, 16), 128, 0, c.P.p + 3 * p0, c.p2n.p + p0, p1 - p0, c.base[c.D], c.neighs.p, c.parent.p, c.offs.p, c.pnum.p, dk,
+                       c.xv, c.dBaseFn.p, c.pointValue.p + p0, sum.p);
+    }
     double h[3] = {0, 0, 0};
     if (c.mg.active()) {
         PRB_LAUNCH(c, k_mg_publish_sum, 1, 32, 0, c.mg.dev(), sum.p);
@@ -1737,10 +1746,9 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     i64 totV = 0, totT = 0;
     PRB_TRY(exclusive_scan(c, bflag.p, bexcl.p, nBricks, nullptr));
     PRB_CUDA(cudaMemcpyAsync(dCounts.p + 1, c.scanWork.ticket + 1, sizeof(int), cudaMemcpyDeviceToDevice, st));
-    PRB_TRY(exclusive_scan(c, brickV.p, brickVBase.p, nBricks, nullptr));
-    PRB_CUDA(cudaMemcpyAsync(c.hScanTotal + 1, c.scanWork.ticket + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PRB_TRY(exclusive_scan(c, brickV.p, brickVBase.p, nBricks, nullptr, 1));  // (total -> pinned word 1)
     PRB_TRY(exclusive_scan(c, brickT.p, brickTBase.p, nBricks, &totT));       // (the one host round trip of the pass: the output sizes)
-    totV = c.hScanTotal[1];
+    totV = ((volatile int*)c.hScanTotal)[1];
     outs.emplace_back();
     PassOut& po = outs.back();
     po.nv = (int)totV;
@@ -1881,6 +1889,8 @@ int stage_extract(Context& c) {
     c.layout.clear();
     c.subdivide.clear();
     c.hMeshValid = false;
+    if (c.copyStream) PRB_CUDA(cudaStreamSynchronize(c.copyStream));
+    c.earlyV = c.earlyT = 0;
     Topo R;
     R.nbr = c.neighs.p; R.rowBase = 0; R.minId = 0; R.cellBase = c.base[D]; R.nCells = c.cnt[D];
     const bool mg = c.mg.active();
@@ -1984,6 +1994,28 @@ int stage_extract(Context& c) {
     } else {
         PRB_TRY(run_mc_on_cells(c, R, local_view(c.vvalPtr, 0), c.offs.p + c.base[D], true, fmark, outs.back()));
         sh.rankV[0] = outs.back().nv; sh.rankT[0] = outs.back().nt;
+    }
+    // ---- the main piece is final from here on (it leads this rank's mesh and its triangles carry global vertex ids): with the option
+    // "early_mesh_copy" its device -> host copy starts now, on a second stream, and runs under the refinement passes; prb_get_mesh
+    // copies the rest.  (Off by default -- no net gain measured, see Context::earlyMeshCopy.)
+    bool earlyIssued = false;
+    if (c.earlyMeshCopy && c.doRefine && (outs[0].nv || outs[0].nt)) {
+        PRB_TRY(ensure_copy_stream(c));
+        // (a first run allocates the pinned buffers here, with the head room HBuf adds; if the refinement pieces do not fit later,
+        // prb_get_mesh reallocates and copies everything)
+        const size_t nv0 = (size_t)outs[0].nv, nt0 = (size_t)outs[0].nt;
+        PRB_TRY(c.hMeshV.reserve(3 * nv0 + 3 * (nv0 / 2) + 1));
+        PRB_TRY(c.hMeshT.reserve(3 * nt0 + 3 * (nt0 / 2) + 1));
+        PRB_CUDA(cudaEventRecord(c.evMainPiece, st));
+        PRB_CUDA(cudaStreamWaitEvent(c.copyStream, c.evMainPiece, 0));
+        const size_t kPiece = (size_t)1 << 21;
+        for (size_t o = 0; o < 12 * nv0; o += kPiece)
+            PRB_CUDA(cudaMemcpyAsync((char*)c.hMeshV.p + o, (const char*)outs[0].v.p + o, std::min(kPiece, 12 * nv0 - o), cudaMemcpyDeviceToHost, c.copyStream));
+        for (size_t o = 0; o < 12 * nt0; o += kPiece)
+            PRB_CUDA(cudaMemcpyAsync((char*)c.hMeshT.p + o, (const char*)outs[0].t.p + o, std::min(kPiece, 12 * nt0 - o), cudaMemcpyDeviceToHost, c.copyStream));
+        PRB_CUDA(cudaEventRecord(c.evEarlyCopy, c.copyStream));
+        c.earlyV = outs[0].nv; c.earlyT = outs[0].nt;
+        earlyIssued = true;
     }
     mark(c, "extract:main_pass");
     const int nMainParts = shard ? W : 1;
@@ -2105,6 +2137,7 @@ int stage_extract(Context& c) {
         av += pc.nv; at += pc.nt;
     }
     mark(c, "extract:assembled");
+    if (earlyIssued) PRB_CUDA(cudaStreamWaitEvent(st, c.evEarlyCopy, 0));      // the piece buffers go back to the arena: not before the copy has read them
     for (auto& o : outs) { o.v.release(); o.t.release(); }
     c.nMeshV = tv;
     c.nMeshT = tt;

@@ -4,9 +4,6 @@
 
 namespace prb {
 
-// spin limit of a peer wait: ~2 s at 2 GHz.  A rank that died must not hang the others (and the box).
-constexpr long long kMgSpinCycles = 4000000000ll;
-
 __device__ __forceinline__ void mg_store_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ unsigned mg_load_acquire_sys(const unsigned* p) {
     unsigned v;
@@ -24,7 +21,7 @@ __device__ __forceinline__ void mg_signal_wait(const MgDev& mg, unsigned epoch) 
     for (int r = 0; r < mg.world; r++) {
         if (r == mg.rank) continue;
         while ((int)(mg_load_acquire_sys(&mg.hdr->flags[r][0]) - epoch) < 0) {
-            if (clock64() - t0 > kMgSpinCycles) { mg.hdr->error = 1; return; }
+            if (clock64() - t0 > mg.spinCycles) { mg.hdr->error = 1; return; }
         }
     }
     __threadfence_system();

@@ -34,8 +34,8 @@ int scan_work_ensure(Context& c, size_t tiles) {
 }
 
 // exclusive scan of an int array (kernels in scan.cuh)
-int exclusive_scan(Context& c, const int* in, int* out, i64 n, i64* total_host) {
-    return exclusive_scan_op(c, ScanLoadInt{in}, out, n, total_host);
+int exclusive_scan(Context& c, const int* in, int* out, i64 n, i64* total_host, int hostSlot) {
+    return exclusive_scan_op(c, ScanLoadInt{in}, out, n, total_host, hostSlot);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -78,30 +78,22 @@ __global__ void k_bbox_final(const float* __restrict__ part, int nb, float* __re
 // semantics of the reference are kept: no FMA contraction in the normal length, IEEE division.
 // One block per SORT TILE (sort.cu): the digit histogram of the first radix pass is taken on the way.
 constexpr int kEncThreads = 256, kEncItems = 16;          // = kSortThreads, kSortItems (sort.cu)
-__global__ void __launch_bounds__(kEncThreads) k_normalise_encode_count(const float* __restrict__ xyz, const float* __restrict__ nrm, i64 n,
+__global__ void __launch_bounds__(kEncThreads) k_normalise_encode_count(const float* __restrict__ xyz, i64 n,
                                                                         float cx, float cy, float cz, float scale, int D, int bits, int nTiles,
-                                                                        float* __restrict__ P0, float* __restrict__ N0, u64* __restrict__ keys, int* __restrict__ idx,
+                                                                        float* __restrict__ P0, u64* __restrict__ keys, int* __restrict__ idx,
                                                                         int* __restrict__ counts) {
     extern __shared__ int sHist[];
     const int radix = 1 << bits;
     for (int d = threadIdx.x; d < radix; d += kEncThreads) sHist[d] = 0;
     __syncthreads();
     const float ctr[3] = {cx, cy, cz};
-    const float nscale = (float)(2 << D);
     const i64 t0 = (i64)blockIdx.x * (kEncThreads * kEncItems);
     for (int it = 0; it < kEncItems; it++) {
         const i64 i = t0 + it * kEncThreads + threadIdx.x;
         if (i >= n) break;
-        float p[3], q[3];
+        float p[3];
 #pragma unroll
-        for (int a = 0; a < 3; a++) {
-            p[a] = __fdiv_rn(__fsub_rn(xyz[3 * i + a], ctr[a]), scale);
-            q[a] = nrm[3 * i + a];
-        }
-        float sq = __fadd_rn(__fadd_rn(__fmul_rn(q[0], q[0]), __fmul_rn(q[1], q[1])), __fmul_rn(q[2], q[2]));
-        float len = (float)sqrt((double)sq);
-        if (len > 1e-6f) len = __fdiv_rn(1.0f, len);
-        len = __fmul_rn(len, nscale);
+        for (int a = 0; a < 3; a++) p[a] = __fdiv_rn(__fsub_rn(xyz[3 * i + a], ctr[a]), scale);
         // strict '>' against the running cell centre: a point on a cell boundary goes to the lower cell (Q5)
         float c[3] = {0.5f, 0.5f, 0.5f};
         float w = 0.25f;
@@ -115,7 +107,7 @@ __global__ void __launch_bounds__(kEncThreads) k_normalise_encode_count(const fl
             w *= 0.5f;
         }
 #pragma unroll
-        for (int a = 0; a < 3; a++) { P0[3 * i + a] = p[a]; N0[3 * i + a] = __fmul_rn(q[a], len); }
+        for (int a = 0; a < 3; a++) P0[3 * i + a] = p[a];
         keys[i] = k;
         idx[i] = (int)i;
         atomicAdd(&sHist[(int)(k & (u64)(radix - 1))], 1);
@@ -126,8 +118,8 @@ __global__ void __launch_bounds__(kEncThreads) k_normalise_encode_count(const fl
 int sort_tiles(i64 n);
 int sort_passes(int keyBits);
 int sort_digit_bits(int keyBits);
-int radix_sort_gather(Context& c, u64* keys0, int* idx0, u64* keysTmp, int* idxTmp, int* counts, i64 n, int keyBits, const float* P0, const float* N0,
-                      u64* keysOut, int* idxOut, float* P, float* Nr);
+int radix_sort_gather(Context& c, u64* keys0, int* idx0, u64* keysTmp, int* idxTmp, int* counts, i64 n, int keyBits, const float* P0, const float* N0, float nscale,
+                      cudaEvent_t normalsReady, u64* keysOut, int* idxOut, float* P, float* Nr);
 // number of non-empty nodes of EVERY depth in one pass over the sorted keys: sample i starts a new node at depth d iff its key differs from
 // its predecessor's in the top 3 d bits, i.e. at every depth >= h(i) = the level of the highest differing bit.  hist[h] counts the samples
 // by h; U_d = sum_{h <= d} hist[h].  One host round trip for all levels instead of one per level.
@@ -439,11 +431,10 @@ int stage_octree(Context& c) {
     // ---- A1/A2 keys + sort (thrust::sort_by_key x2 on 64-bit codes in the reference, main.cu:598-602;
     //      here one stable LSD sort over the 3D key bits with the sample index as payload)
     mark(c, "octree:bbox");
-    DBuf<float> P0, N0;
+    DBuf<float> P0;
     DBuf<u64> keys0;
     DBuf<int> idx0;
     PRB_TRY(P0.alloc(3 * (size_t)N, st));
-    PRB_TRY(N0.alloc(3 * (size_t)N, st));
     PRB_TRY(keys0.alloc((size_t)N, st));
     PRB_TRY(idx0.alloc((size_t)N, st));
     PRB_TRY(c.sortedKey.alloc((size_t)N, st));
@@ -460,11 +451,14 @@ int stage_octree(Context& c) {
         PRB_TRY(keysTmp.alloc(needTmp ? (size_t)N : 0, st));
         PRB_TRY(idxTmp.alloc(needTmp ? (size_t)N : 0, st));
         PRB_TRY(counts.alloc(((size_t)1 << bits) * (size_t)nTiles, st));
-        PRB_LAUNCH(c, k_normalise_encode_count, nTiles, kEncThreads, sizeof(int) << bits, c.rawPp, c.rawNp, N, c.center[0], c.center[1], c.center[2], c.scale, D, bits, nTiles,
-                   P0.p, N0.p, keys0.p, idx0.p, counts.p);
-        PRB_TRY(radix_sort_gather(c, keys0.p, idx0.p, keysTmp.p, idxTmp.p, counts.p, N, 3 * D, P0.p, N0.p, c.sortedKey.p, c.sortedIdx.p, c.P.p, c.Nr.p));
+        PRB_LAUNCH(c, k_normalise_encode_count, nTiles, kEncThreads, sizeof(int) << bits, c.rawPp, N, c.center[0], c.center[1], c.center[2], c.scale, D, bits, nTiles,
+                   P0.p, keys0.p, idx0.p, counts.p);
+        // the normals are first needed by the gather of the last pass (scaled there): their upload may still be running on the copy stream
+        PRB_TRY(radix_sort_gather(c, keys0.p, idx0.p, keysTmp.p, idxTmp.p, counts.p, N, 3 * D, P0.p, c.rawNp, (float)(2 << D), c.normalsPending ? c.evNormals : nullptr,
+                                  c.sortedKey.p, c.sortedIdx.p, c.P.p, c.Nr.p));
+        c.normalsPending = false;
     }
-    P0.release(); N0.release(); keys0.release(); idx0.release();
+    P0.release(); keys0.release(); idx0.release();
     mark(c, "octree:sorted");
     // ---- A3 unique leaves
     DBuf<int> flagN, exclN;

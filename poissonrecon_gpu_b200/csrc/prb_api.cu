@@ -20,6 +20,18 @@ static void release_all(Context& c) {
     c.xv = nullptr;
     c.divgv = nullptr;
     c.hMeshValid = false;
+    if (c.copyStream) cudaStreamSynchronize(c.copyStream);      // (an early mesh copy of the previous run that nobody fetched)
+    c.earlyV = c.earlyT = 0;
+}
+
+int ensure_copy_stream(Context& c) {
+    if (c.copyStream) return PRB_OK;
+    PRB_CUDA(cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking));
+    PRB_CUDA(cudaEventCreateWithFlags(&c.evMainPiece, cudaEventDisableTiming));
+    PRB_CUDA(cudaEventCreateWithFlags(&c.evEarlyCopy, cudaEventDisableTiming));
+    PRB_CUDA(cudaEventCreateWithFlags(&c.evPositions, cudaEventDisableTiming));
+    PRB_CUDA(cudaEventCreateWithFlags(&c.evNormals, cudaEventDisableTiming));
+    return PRB_OK;
 }
 
 int upload_tables(Context& c) {
@@ -118,6 +130,9 @@ void prb_destroy(prb_context* h) {
     for (int r = 0; r < kMaxRanks; r++)
         if (c.mg.peerOpen[r] && c.mg.peer[r]) cudaIpcCloseMemHandle(c.mg.peer[r]);
     if (c.mg.arena) cudaFree(c.mg.arena);
+    if (c.copyStream) { cudaStreamSynchronize(c.copyStream); cudaStreamDestroy(c.copyStream); }
+    for (cudaEvent_t e : {c.evMainPiece, c.evEarlyCopy, c.evPositions, c.evNormals})
+        if (e) cudaEventDestroy(e);
     c.hMeshV.release(); c.hMeshT.release();
     for (auto& e : c.ev) cudaEventDestroy(e);
     for (auto& e : c.detailEv) cudaEventDestroy(e);
@@ -136,6 +151,8 @@ int prb_set_option(prb_context* h, const char* key, double value) {
     else if (k == "iso_density_weighted") h->c.isoDensityWeighted = (int)value;
     else if (k == "cascadic") h->c.cascadic = (int)value;
     else if (k == "detail") h->c.detail = (int)value;
+    else if (k == "early_mesh_copy") h->c.earlyMeshCopy = (int)value;
+    else if (k == "mg_timeout_ms") h->c.mg.spinCycles = (long long)((value < 1.0 ? 1.0 : value) * 2.0e6);
     else if (k == "refine_bound_check") h->c.refineBoundCheck = (int)value;
     else if (k == "div_mode") h->c.divMode = (int)value;
     else if (k == "refine") h->c.doRefine = (int)value;
@@ -151,6 +168,7 @@ static int begin_run(Context& c, int64_t n) {
     c.vvalPtr = nullptr;
     c.rawPp = c.rawNp = c.Vp = nullptr;
     c.rawSharded = false;
+    c.normalsPending = false;
     c.N = n;
     c.launches = 0;
     c.detailUsed = 0;
@@ -169,8 +187,16 @@ int prb_set_points(prb_context* h, const float* xyz, const float* normals, int64
     PRB_TRY(c.rawP.alloc(3 * (size_t)n, c.stream));
     PRB_TRY(c.rawN.alloc(3 * (size_t)n, c.stream));
     c.rawPp = c.rawP.p; c.rawNp = c.rawN.p;
+    // positions first, on the context stream; the normals follow on the copy stream (ordered behind the positions, so the two uploads
+    // do not share the link) while the bounding box, the keys and the first sort passes already run: the gather of the last sort pass
+    // is the first reader of the normals
+    PRB_TRY(ensure_copy_stream(c));
     PRB_CUDA(cudaMemcpyAsync(c.rawPp, xyz, 12 * (size_t)n, cudaMemcpyDefault, c.stream));
-    PRB_CUDA(cudaMemcpyAsync(c.rawNp, normals, 12 * (size_t)n, cudaMemcpyDefault, c.stream));
+    PRB_CUDA(cudaEventRecord(c.evPositions, c.stream));
+    PRB_CUDA(cudaStreamWaitEvent(c.copyStream, c.evPositions, 0));
+    PRB_CUDA(cudaMemcpyAsync(c.rawNp, normals, 12 * (size_t)n, cudaMemcpyDefault, c.copyStream));
+    PRB_CUDA(cudaEventRecord(c.evNormals, c.copyStream));
+    c.normalsPending = true;
     PRB_CUDA(cudaEventRecord(c.ev[1], c.stream));
     c.stage = 1;
     return PRB_OK;
@@ -286,10 +312,16 @@ int prb_get_mesh(prb_context* h, const float** v, int64_t* nv, const int32_t** t
     if (c.stage < 5) { set_error("prb_get_mesh: extract not done"); return PRB_ERR_STATE; }
     PRB_DEVICE(c);
     if (!c.hMeshValid) {
+        // the leading piece may already be in the pinned buffers (stage_extract started its copy under the refinement passes); it is
+        // kept when the buffers did not have to grow
+        if (c.copyStream) PRB_CUDA(cudaStreamSynchronize(c.copyStream));
+        const unsigned gv0 = c.hMeshV.generation, gt0 = c.hMeshT.generation;
         PRB_TRY(c.hMeshV.reserve(3 * (size_t)c.nMeshV + 1));
         PRB_TRY(c.hMeshT.reserve(3 * (size_t)c.nMeshT + 1));
-        if (c.nMeshV) PRB_CUDA(cudaMemcpyAsync(c.hMeshV.p, c.meshV.p, 12 * (size_t)c.nMeshV, cudaMemcpyDeviceToHost, c.stream));
-        if (c.nMeshT) PRB_CUDA(cudaMemcpyAsync(c.hMeshT.p, c.meshT.p, 12 * (size_t)c.nMeshT, cudaMemcpyDeviceToHost, c.stream));
+        const bool kept = c.hMeshV.generation == gv0 && c.hMeshT.generation == gt0 && c.earlyV <= c.nMeshV && c.earlyT <= c.nMeshT;
+        const size_t ev = kept ? (size_t)c.earlyV : 0, et = kept ? (size_t)c.earlyT : 0;
+        if ((size_t)c.nMeshV > ev) PRB_CUDA(cudaMemcpyAsync(c.hMeshV.p + 3 * ev, c.meshV.p + 3 * ev, 12 * ((size_t)c.nMeshV - ev), cudaMemcpyDeviceToHost, c.stream));
+        if ((size_t)c.nMeshT > et) PRB_CUDA(cudaMemcpyAsync(c.hMeshT.p + 3 * et, c.meshT.p + 3 * et, 12 * ((size_t)c.nMeshT - et), cudaMemcpyDeviceToHost, c.stream));
         PRB_CUDA(cudaStreamSynchronize(c.stream));
         c.hMeshValid = true;
     }

@@ -107,7 +107,7 @@ __device__ __forceinline__ unsigned long long scan_ld(const unsigned long long* 
 __device__ __forceinline__ void scan_st(unsigned long long* p, unsigned long long v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory"); }
 template <class Op>
 __global__ void __launch_bounds__(kScanBlock) k_scan_lookback(Op in, int* out /* may alias the input */, i64 n, int nTiles, unsigned long long* __restrict__ desc, unsigned* __restrict__ ticket,
-                                                              unsigned epoch, int* __restrict__ total) {
+                                                              unsigned epoch, int* __restrict__ total, int* __restrict__ hostTotal /* pinned, or null */) {
     __shared__ int sm[33];
     __shared__ int sTile, sPrefix;
     if (threadIdx.x == 0) sTile = (int)atomicAdd(ticket, 1u);
@@ -148,7 +148,11 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_lookback(Op in, int* out /*
         }
         if (threadIdx.x == 0) {
             sPrefix = prefix;
-            if (tile == nTiles - 1) { *total = prefix + agg; *ticket = 0u; }      // every ticket has been drawn: rewind for the next call
+            if (tile == nTiles - 1) {                                           // every ticket has been drawn: rewind for the next call
+                *total = prefix + agg;
+                *ticket = 0u;
+                if (hostTotal) *hostTotal = prefix + agg;                       // straight into pinned host memory: no copy-engine round trip
+            }
         }
     }
     __syncthreads();
@@ -161,19 +165,25 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_lookback(Op in, int* out /*
 }
 
 // exclusive scan of in(0..n) into out on the context stream; the grand total is returned through
-// *total_host (synchronises the stream) when total_host != nullptr.
+// *total_host (synchronises the stream) when total_host != nullptr.  The last tile stores the total into the pinned word
+// c.hScanTotal[hostSlot] itself (hostSlot >= 0), so the host only waits for the stream; a caller that passes hostSlot > 0 without
+// total_host reads c.hScanTotal[hostSlot] after its own later synchronisation.
 template <class Op>
-int exclusive_scan_op(Context& c, Op in, int* out, i64 n, i64* total_host) {
-    if (n <= 0) { if (total_host) *total_host = 0; return PRB_OK; }
+int exclusive_scan_op(Context& c, Op in, int* out, i64 n, i64* total_host, int hostSlot = 0) {
+    if (n <= 0) {
+        if (total_host) *total_host = 0;
+        else if (hostSlot > 0 && c.hScanTotal) c.hScanTotal[hostSlot] = 0;
+        return PRB_OK;
+    }
     int nb = div_up(n, kScanTile);
     PRB_TRY(scan_work_ensure(c, (size_t)nb));
     ScanWork& w = c.scanWork;
     w.epoch++;
-    PRB_LAUNCH(c, k_scan_lookback<Op>, nb, kScanBlock, 0, in, out, n, nb, w.desc, w.ticket, w.epoch, (int*)(w.ticket + 1));
+    int* hostWord = (total_host || hostSlot > 0) ? c.hScanTotal + hostSlot : nullptr;
+    PRB_LAUNCH(c, k_scan_lookback<Op>, nb, kScanBlock, 0, in, out, n, nb, w.desc, w.ticket, w.epoch, (int*)(w.ticket + 1), hostWord);
     if (total_host) {
-        PRB_CUDA(cudaMemcpyAsync(c.hScanTotal, w.ticket + 1, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
         PRB_CUDA(cudaStreamSynchronize(c.stream));
-        *total_host = *c.hScanTotal;
+        *total_host = ((volatile int*)c.hScanTotal)[hostSlot];
     }
     return PRB_OK;
 }

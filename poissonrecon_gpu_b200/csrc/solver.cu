@@ -185,7 +185,7 @@ __device__ __forceinline__ void cg_sync(const CgParams& P, unsigned& epoch, unsi
                     const unsigned* in = &P.mg.hdr->cg[epoch & 1u][lane].epoch;
                     const long long t0 = clock64();
                     while ((int)(mg_load_acquire_sys(in) - epoch) < 0)
-                        if (clock64() - t0 > kMgSpinCycles) { P.mg.hdr->error = 1; break; }
+                        if (clock64() - t0 > P.mg.spinCycles) { P.mg.hdr->error = 1; break; }
                 }
                 __syncwarp();
             }

@@ -12,7 +12,8 @@
 //   scatter stable ranks inside the tile -- per 32-item row __match_any_sync on the digit, running
 //           per-warp digit counters in shared memory, then an 8-step scan over the warps -- and the
 //           scatter; the LAST pass also gathers the sample positions / normals (24 + 24 bytes per
-//           sample moved once, no separate gather kernel).
+//           sample moved once, no separate gather kernel) and scales the raw normals on the way
+//           (main.cu:553-571 semantics: unit length times 2^(D+1); no FMA contraction, IEEE division).
 // No cross-tile spinning: a tile's base comes from the scan, so the kernels have no forward-progress
 // requirements.  Algorithmic bytes per sample (k = 8): passes x (8 r count + 12 r + 12 w
 // scatter) + 48 r + 48 w gather.
@@ -42,7 +43,8 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_count(const u64* __restri
 template <bool GATHER>
 __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const u64* __restrict__ keysIn, const int* __restrict__ idxIn, i64 n, int shift, int bits, int nTiles,
                                                                const int* __restrict__ offsets, u64* __restrict__ keysOut, int* __restrict__ idxOut,
-                                                               const float* __restrict__ P0, const float* __restrict__ N0, float* __restrict__ P, float* __restrict__ Nr) {
+                                                               const float* __restrict__ P0, const float* __restrict__ N0 /* raw normals */, float nscale,
+                                                               float* __restrict__ P, float* __restrict__ Nr) {
     extern __shared__ int sCnt[];                           // [8 warps][radix]
     const int radix = 1 << bits, lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     for (int d = threadIdx.x; d < 8 * radix; d += kSortThreads) sCnt[d] = 0;
@@ -86,8 +88,13 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const u64* __rest
         idxOut[pos] = val[k];
         if (GATHER) {
             const i64 s = val[k];
+            const float q[3] = {N0[3 * s], N0[3 * s + 1], N0[3 * s + 2]};
+            const float sq = __fadd_rn(__fadd_rn(__fmul_rn(q[0], q[0]), __fmul_rn(q[1], q[1])), __fmul_rn(q[2], q[2]));
+            float len = (float)sqrt((double)sq);
+            if (len > 1e-6f) len = __fdiv_rn(1.0f, len);
+            len = __fmul_rn(len, nscale);
 #pragma unroll
-            for (int a = 0; a < 3; a++) { P[3 * pos + a] = P0[3 * s + a]; Nr[3 * pos + a] = N0[3 * s + a]; }
+            for (int a = 0; a < 3; a++) { P[3 * pos + a] = P0[3 * s + a]; Nr[3 * pos + a] = __fmul_rn(q[a], len); }
         }
     }
 }
@@ -97,8 +104,8 @@ int sort_passes(int keyBits) { return keyBits <= 0 ? 1 : (keyBits + kSortMaxBits
 int sort_digit_bits(int keyBits) { const int p = sort_passes(keyBits); return keyBits <= 0 ? 1 : (keyBits + p - 1) / p; }
 
 // keys0 / idx0: the unsorted pairs (clobbered); counts: [2^bits * tiles] ints, holding the pass-0 histogram on entry.
-int radix_sort_gather(Context& c, u64* keys0, int* idx0, u64* keysTmp, int* idxTmp, int* counts, i64 n, int keyBits, const float* P0, const float* N0,
-                      u64* keysOut, int* idxOut, float* P, float* Nr) {
+int radix_sort_gather(Context& c, u64* keys0, int* idx0, u64* keysTmp, int* idxTmp, int* counts, i64 n, int keyBits, const float* P0, const float* N0, float nscale,
+                      cudaEvent_t normalsReady /* or null */, u64* keysOut, int* idxOut, float* P, float* Nr) {
     const int passes = sort_passes(keyBits), bits = sort_digit_bits(keyBits), radix = 1 << bits, nTiles = sort_tiles(n);
     const size_t smemCnt = sizeof(int) * 8 * (size_t)radix;
     if (smemCnt > 48 * 1024) { set_error("sort: digit too wide"); return PRB_ERR_ARG; }
@@ -111,10 +118,11 @@ int radix_sort_gather(Context& c, u64* keys0, int* idx0, u64* keysTmp, int* idxT
         PRB_TRY(exclusive_scan(c, counts, counts, (i64)radix * nTiles, nullptr));
         u64* dstK = last ? keysOut : (srcK == keys0 ? keysTmp : keys0);
         int* dstI = last ? idxOut : (srcI == idx0 ? idxTmp : idx0);
-        if (last)
-            PRB_LAUNCH(c, k_sort_scatter<true>, nTiles, kSortThreads, smemCnt, srcK, srcI, n, shift, bits, nTiles, counts, dstK, dstI, P0, N0, P, Nr);
-        else
-            PRB_LAUNCH(c, k_sort_scatter<false>, nTiles, kSortThreads, smemCnt, srcK, srcI, n, shift, bits, nTiles, counts, dstK, dstI, nullptr, nullptr, nullptr, nullptr);
+        if (last) {
+            if (normalsReady) PRB_CUDA(cudaStreamWaitEvent(c.stream, normalsReady, 0));
+            PRB_LAUNCH(c, k_sort_scatter<true>, nTiles, kSortThreads, smemCnt, srcK, srcI, n, shift, bits, nTiles, counts, dstK, dstI, P0, N0, nscale, P, Nr);
+        } else
+            PRB_LAUNCH(c, k_sort_scatter<false>, nTiles, kSortThreads, smemCnt, srcK, srcI, n, shift, bits, nTiles, counts, dstK, dstI, nullptr, nullptr, 0.f, nullptr, nullptr);
         srcK = dstK;
         srcI = dstI;
     }
@@ -160,7 +168,7 @@ int prb_debug_sort(prb_context* h, const uint64_t* keys, int64_t n, int key_bits
     PRB_CUDA(cudaMemcpyAsync(i0.p, iota.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
     PRB_CUDA(cudaMemsetAsync(f0.p, 0, 12 * (size_t)n, st));
     PRB_LAUNCH(c, k_sort_count, nTiles, kSortThreads, sizeof(int) << bits, k0.p, (i64)n, 0, bits, nTiles, counts.p);
-    PRB_TRY(radix_sort_gather(c, k0.p, i0.p, k1.p, i1.p, counts.p, n, key_bits, f0.p, f0.p, ko.p, io.p, f1.p, f1.p + 3 * (size_t)n));
+    PRB_TRY(radix_sort_gather(c, k0.p, i0.p, k1.p, i1.p, counts.p, n, key_bits, f0.p, f0.p, 1.f, nullptr, ko.p, io.p, f1.p, f1.p + 3 * (size_t)n));
     PRB_CUDA(cudaMemcpyAsync(out_keys, ko.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
     PRB_CUDA(cudaMemcpyAsync(out_idx, io.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
     PRB_CUDA(cudaStreamSynchronize(st));

@@ -364,8 +364,14 @@ def test_density_weighted_iso_value_opt_in():
         pr = PoissonRecon(D)
         pr.set_points(p, n)
         pr.run()
-        plain, weighted = pr.get("iso_modes", "<f4").tolist()
-        assert plain == float(pr.get("iso", "<f4")[0])                      # default = the reference's plain mean
+        plain = float(pr.get("iso", "<f4")[0])                              # default = the reference's plain mean
+        assert pr.get("iso_modes", "<f4").tolist()[0] == plain
+        v0, t0 = pr.mesh()
+        pr.set_option("iso_density_weighted", 1)
+        pr.set_points(p, n)
+        pr.run()
+        plain1, weighted = pr.get("iso_modes", "<f4").tolist()              # (the weighted sums are only taken with the option on)
+        assert plain1 == plain
         base = pr.get("base", "<i4")
         node = int(base[D]) + pr.get("p2n", "<i4").astype(np.int64)
         parent = pr.get("parent", "<i4").astype(np.int64)
@@ -375,10 +381,6 @@ def test_density_weighted_iso_value_opt_in():
         pv = pr.get("pointvalue", "<f4").astype(np.float64)
         expect = float((w * pv).sum() / w.sum())
         assert abs(weighted - expect) <= 1e-5 * abs(expect)
-        v0, t0 = pr.mesh()
-        pr.set_option("iso_density_weighted", 1)
-        pr.set_points(p, n)
-        pr.run()
         assert float(pr.get("iso", "<f4")[0]) == weighted
         v1, t1 = pr.mesh()
         assert t1.shape[0] > 0
@@ -465,4 +467,28 @@ def test_cascadic_mode_opt_in():
     pr.set_points(p, n)
     pr.run()
     assert np.array_equal(pr.get("x", "<f4"), x_ind) and np.array_equal(pr.mesh()[1], t_ind)   # default path untouched
+    pr.close()
+
+
+def test_early_mesh_copy_option(sphere100k):
+    """prb_set_option("early_mesh_copy", 1): the main marching-cubes piece is downloaded under the refinement passes.  Same mesh as the
+    default, on a context's first run (the pinned buffers are allocated mid-run and may have to grow for the refinement pieces) and on
+    later ones, through both prb_get_mesh flavours."""
+    from poissonrecon_gpu_b200 import PoissonRecon
+    p, n, D = sphere100k
+    pr = PoissonRecon(D)
+    pr.set_points(p, n)
+    pr.run()
+    v0, t0 = pr.mesh()
+    pr.close()
+    pr = PoissonRecon(D)
+    pr.set_option("early_mesh_copy", 1)
+    for k in range(3):
+        pr.set_points(p[: p.shape[0] - 1000 * k], n[: p.shape[0] - 1000 * k])       # (sizes change between runs)
+        pr.run()
+        v, t = pr.mesh_host_view()
+        dv, dt = pr.get("mesh_v", "<f4").reshape(-1, 3), pr.get("mesh_t", "<i4").reshape(-1, 3)
+        assert np.array_equal(v, dv) and np.array_equal(t, dt), k
+        if k == 0:
+            assert np.array_equal(v, v0) and np.array_equal(t, t0)
     pr.close()
