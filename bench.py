@@ -454,6 +454,22 @@ def main():
         "digests": digests,
         "clocks": clk,
     }
+    if world == 1:
+        # secondary stages against the same HBM peak: SURVEY.md 8(d)'s compulsory bytes per unit x this run's units / the stage's device
+        # time.  The fractions are low by construction of the path, not by wasted traffic: outside the CG the work is 27-term sums over
+        # D + 1 levels in the reference's fixed float order (81 flops per vertex-level, latency / issue bound gathers), DESIGN.md section 3
+        sm = line["stages_ms"]
+        npd = st["nodes_per_depth"][: D + 1]
+        M, slotsD = st["n_nodes"], npd[D]
+        k, p = (4, -(-3 * D // 8)) if D <= 10 else (8, -(-3 * D // 8))
+        per_point = (84 + 16 * p) if k == 4 else (96 + 24 * p)
+        sec = [("octree (A0-A6 + block tables)", sm["ms_octree"], per_point * N + 55.5 * M, f"{per_point} B/point + 55.5 B/node"),
+               ("splat (A7)", sm["ms_splat"], 12 * slotsD + 24 * N, "12 B/depth-D slot + 24 B/point"),
+               ("divergence (A8)", sm["ms_divergence"], 4 * M + 12 * slotsD * (D + 1), "4 B/node + 12 B/depth-D slot/level"),
+               ("iso value (A11)", sm["ms_iso"], 16 * N, "12 B r + 4 B w per point"),
+               ("corner values + marching cubes + refinement (A12)", sm["ms_extract"], 36 * slotsD + 12 * (nv + nt), "36 B/depth-D slot + 12 B/vertex + 12 B/triangle")]
+        line["roofline_stages"] = [{"stage": nm, "ms": ms, "algorithmic_bytes": b, "per_unit": pu, "achieved": b / (ms * 1e-3) / 1e9, "unit": "GB/s", "frac": b / (ms * 1e-3) / 1e9 / peak}
+                                   for nm, ms, b, pu in sec]
     if not a.no_cpu_baseline and world == 1:
         r, s, cores, sample = cpu_oracle_rate(a.workload, 1)
         line["cpu_baseline"] = {"value": r, "unit": "Mpoints/s", "cores": cores, "kind": "port", "sample": sample, "seconds": s}

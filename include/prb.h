@@ -67,8 +67,11 @@ void prb_destroy(prb_context* ctx);
 const char* prb_last_error(void);
 
 /* Oriented samples: xyz and normals as float32 [n][3], raw file coordinates.  Pointers may be
- * host (pageable or pinned) or device memory; they are copied.  Replaces the two PointStream
- * passes + H2D copies of main.cu:530-581. */
+ * host (pageable or pinned) or device memory; they are copied ASYNCHRONOUSLY (positions on the
+ * context stream, normals behind them on a second stream, under the key generation and the first
+ * sort passes): pinned-host and device buffers must stay valid and unchanged until
+ * prb_build_octree / prb_run has returned.  Replaces the two PointStream passes + H2D copies of
+ * main.cu:530-581. */
 int prb_set_points(prb_context* ctx, const float* xyz, const float* normals, int64_t n);
 
 /* Staged execution (each requires the previous stage). */
