@@ -1212,14 +1212,33 @@ __device__ float rv_eval_slow(const RGeom& G, int r, int cx, int cy, int cz, int
     }
     return __fsub_rn(val, G.iso);
 }
-// grid points on the lower faces of every root: evaluated here when this root owns them
+// grid points on the lower faces of every root: evaluated here when this root owns them.  Tiles of 128 points of one root, 32-bit
+// index arithmetic; a point nobody reads is dropped BEFORE the owner search (8 cell look-ups across the neighbouring roots): its
+// owner, if it lies in this root at all, is one of the (at most 8) cells of this root around the point, and only bricks staged
+// for classification (needLow) read lower-face values.
 __global__ void __launch_bounds__(128) k_rv_low_values(RGeom G, const unsigned char* __restrict__ needed /* per brick (k_rv_brick_needed needLow), or null: all */) {
-    const int n1 = G.n + 1;
-    const i64 total = (i64)G.nr * 3 * n1 * n1;
-    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
-        int v = (int)(t % n1), u = (int)((t / n1) % n1), a = (int)((t / ((i64)n1 * n1)) % 3), r = (int)(t / ((i64)3 * n1 * n1));
+    const int n1 = G.n + 1, nn = n1 * n1, per = 3 * nn;
+    const unsigned tilesPerRoot = (unsigned)((per + 127) / 128);
+    const i64 nTiles = (i64)G.nr * tilesPerRoot;
+    const bool small = nTiles <= 0xffffffffll;
+    const i64 bricksPerRoot = (i64)(G.per >> 9);
+    for (i64 tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        const int r = small ? (int)((unsigned)tile / tilesPerRoot) : (int)(tile / tilesPerRoot);
+        const int i = (int)(tile - (i64)r * tilesPerRoot) * 128 + (int)threadIdx.x;
+        if (i >= per) continue;
+        const int a = i / nn, rem = i - a * nn, u = rem / n1, v = rem - u * n1;
+        const i64 t = (i64)r * per + i;                                    // = ((r * 3 + a) * n1 + u) * n1 + v
         int gx = a == 0 ? 0 : u, gy = a == 0 ? u : (a == 1 ? 0 : v), gz = a == 2 ? 0 : v;
         if ((a >= 1 && gx == 0) || (a == 2 && gy == 0)) continue;   // stored under the lowest zero axis
+        if (needed) {
+            const int bx0 = max(gx - 1, 0) >> 3, bx1 = min(gx, G.n - 1) >> 3, by0 = max(gy - 1, 0) >> 3, by1 = min(gy, G.n - 1) >> 3,
+                      bz0 = max(gz - 1, 0) >> 3, bz1 = min(gz, G.n - 1) >> 3;
+            bool any = false;
+            for (int bx = bx0; bx <= bx1; bx++)
+                for (int by = by0; by <= by1; by++)
+                    for (int bz = bz0; bz <= bz1; bz++) any = any || needed[r * bricksPerRoot + rv_morton(bx, by, bz)] != 0;
+            if (!any) continue;
+        }
         int r2, ox, oy, oz, jb;
         rv_point_owner(G, r, gx, gy, gz, r2, ox, oy, oz, jb);
         if (r2 != r || jb == 7) continue;
@@ -1459,22 +1478,36 @@ __global__ void __launch_bounds__(256) k_rv_brick_sign(const float* __restrict__
 // pass-wide offsets then come from a scan over bricks (hundreds of thousands) instead of cells
 // (hundreds of millions), and only the active bricks are visited again for the emission.
 __global__ void __launch_bounds__(512) k_rv_classify_brick(RGeom G, const unsigned char* __restrict__ bsign /* full[] flags */, unsigned char* __restrict__ cat, unsigned short* __restrict__ emask,
-                                                           unsigned short* __restrict__ vpre, int* __restrict__ brickV, int* __restrict__ brickT, int nBricks) {
+                                                           unsigned short* __restrict__ vpre, int* __restrict__ brickV, int* __restrict__ brickT, int nBricks,
+                                                           int chunk /* 1..64 bricks whose flags a CTA looks at together */) {
     __shared__ int sScan[33];
     __shared__ float sV[9 * 9 * 9];
+    __shared__ int sList[64], sWarpCnt[2];
     const int tid = threadIdx.x;
-    // persistent CTAs: most bricks leave after eight byte loads, far cheaper than a 512-thread CTA launch each
-    for (int brick = blockIdx.x; brick < nBricks; brick += gridDim.x) {
+    // persistent CTAs over chunks of bricks: the flags of a chunk are fetched together (one memory round trip per chunk instead of
+    // one per brick -- most bricks are certified and leave at once) and only the flagged bricks of the chunk are visited
+    const int nChunks = (nBricks + chunk - 1) / chunk;
+    for (int ch = blockIdx.x; ch < nChunks; ch += gridDim.x) {
+    __syncthreads();                                  // the previous chunk's list is consumed
+    const int mine = ch * chunk + tid;
+    const bool flagged = tid < chunk && mine < nBricks && bsign[mine] != 0;
+    unsigned bal = 0;
+    if (tid < 64) {
+        if (tid < chunk && mine < nBricks && !flagged) { brickV[mine] = 0; brickT[mine] = 0; }
+        bal = __ballot_sync(0xffffffffu, flagged);
+        if ((tid & 31) == 0) sWarpCnt[tid >> 5] = __popc(bal);
+    }
     __syncthreads();
+    if (flagged) sList[(tid >= 32 ? sWarpCnt[0] : 0) + __popc(bal & ((1u << (tid & 31)) - 1u))] = mine;
+    const int nList = sWarpCnt[0] + sWarpCnt[1];
+    for (int li = 0; li < nList; li++) {
+    __syncthreads();                                  // list written / the previous brick's shared values are consumed
+    const int brick = sList[li];
     const i64 cell0 = (i64)brick * 512;
     const int r = (int)(cell0 / G.per);
     const unsigned l0 = (unsigned)(cell0 - (i64)r * G.per);
     const int bx = (int)compact3(l0 >> 2), by = (int)compact3(l0 >> 1), bz = (int)compact3(l0);   // root-local origin of the brick
-    // bricks whose grid is certified to be of one strict sign (k_rv_brick_bound / k_rv_brick_full) produce nothing
-    if (!bsign[brick]) {
-        if (tid == 0) { brickV[brick] = 0; brickT[brick] = 0; }
-        continue;
-    }
+    // (bricks whose grid is certified to be of one strict sign, k_rv_brick_bound / k_rv_brick_full, produce nothing: not listed)
     const int cx = (int)compact3((unsigned)tid >> 2), cy = (int)compact3((unsigned)tid >> 1), cz = (int)compact3((unsigned)tid);
     const i64 store0 = rv_store(G, cell0);
     const float own = G.val7[store0 + tid];
@@ -1523,6 +1556,7 @@ __global__ void __launch_bounds__(512) k_rv_classify_brick(RGeom G, const unsign
         cat[store0 + tid] = (unsigned char)c;
         emask[store0 + tid] = (unsigned short)m;
         vpre[store0 + tid] = (unsigned short)pre;
+    }
     }
     }
 }
@@ -1740,7 +1774,12 @@ static int refine_pass_implicit(Context& c, const int* dRoots, int nr, int rd, b
     PRB_TRY(brickV.alloc((size_t)nBricks, st)); PRB_TRY(brickT.alloc((size_t)nBricks, st));
     PRB_TRY(brickVBase.alloc((size_t)nBricks, st)); PRB_TRY(brickTBase.alloc((size_t)nBricks, st));
     PRB_TRY(bflag.alloc((size_t)nBricks, st)); PRB_TRY(bexcl.alloc((size_t)nBricks, st));
-    PRB_LAUNCH(c, k_rv_classify_brick, (unsigned)std::min(nBricks, c.smCount * 4), 512, 0, G, full.p, cat.p, emask.p, c.wsVpre.p, brickV.p, brickT.p, nBricks);
+    {
+        // chunk: as many bricks per flag fetch as leaves every CTA several chunks (a small pass keeps one brick per chunk)
+        const int chunk = std::max(1, std::min(64, nBricks / (c.smCount * 4 * 4)));
+        const int nChunks = (nBricks + chunk - 1) / chunk;
+        PRB_LAUNCH(c, k_rv_classify_brick, (unsigned)std::min(nChunks, c.smCount * 4), 512, 0, G, full.p, cat.p, emask.p, c.wsVpre.p, brickV.p, brickT.p, nBricks, chunk);
+    }
     full.release();
     PRB_LAUNCH(c, k_brick_flags, grid_for(c, nBricks, 256), 256, 0, brickV.p, brickT.p, nBricks, bflag.p);
     i64 totV = 0, totT = 0;
